@@ -1,0 +1,821 @@
+// index.cu — host side of libcqs_b200.so: the C ABI declared in
+// include/cqs_b200.h.  Owns device memory, streams and the per-index mutex;
+// all arithmetic lives in the kernels (scan_single.cu, scan_batch.cu,
+// sparse_fuse.cu).  There is deliberately NO CPU fallback: every search either
+// launches the CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cqs_b200.h"
+#include "internal.h"
+
+namespace cqs {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
+using namespace cqs;
+
+static thread_local std::string t_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return code;
+}
+
+namespace {
+
+struct Shard {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  uint8_t* d_rows = nullptr;
+  uint64_t n_rows = 0, cap_rows = 0;
+  uint64_t first_row = 0;  // offset of this shard's row 0 inside the index
+  float* d_stage = nullptr;  // staging for row ingest
+  uint64_t stage_rows = 0;
+  float* d_query = nullptr;   // [kBatchMax][ld]
+  float* h_query = nullptr;   // pinned
+  uint32_t* d_bitset = nullptr;
+  uint64_t bitset_words = 0;
+  ckey_t* d_partial = nullptr;
+  uint32_t* d_partial_cnt = nullptr;
+  uint32_t* d_done = nullptr;
+  // dense result / pool
+  float* d_out_scores = nullptr;
+  uint64_t* d_out_rows = nullptr;
+  uint32_t* d_out_n = nullptr;
+  // sparse pool
+  float* d_sp_scores = nullptr;
+  uint64_t* d_sp_rows = nullptr;
+  uint32_t* d_sp_n = nullptr;
+  ckey_t* d_sp_partial = nullptr;
+  uint32_t* d_sp_partial_cnt = nullptr;
+  uint32_t* d_sp_done = nullptr;
+  uint32_t* d_q_tok = nullptr;
+  float* d_q_w = nullptr;
+  // fused output
+  uint64_t* d_f_rows = nullptr;
+  float* d_f_fused = nullptr;
+  float* d_f_dense = nullptr;
+  float* d_f_sraw = nullptr;
+  uint8_t* d_f_present = nullptr;
+  uint32_t* d_f_n = nullptr;
+  // pinned host mirror for results (sized for the fused output, the largest)
+  uint8_t* h_out = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  SparseDev sparse;
+};
+
+constexpr uint32_t kQuerySlots = 1;  // single-query path keeps one query resident
+constexpr uint32_t kSpMaxQ = 1024;
+constexpr size_t kHostOutBytes = kMaxK * (8 + 4 + 4 + 4 + 1) + 64;
+
+}  // namespace
+
+struct cqs_b200_index {
+  std::mutex mu;
+  uint32_t dim = 0;
+  RowLayout layout{};
+  int metric = 0, storage = 0;
+  bool finalized = false;
+  std::atomic<int> poisoned{0};
+  uint64_t row_base = 0;
+  uint64_t n_rows = 0, reserved = 0, rows_per_shard = 0;
+  float last_kernel_ms = 0.f;
+  std::vector<Shard> shards;
+};
+
+#define CK(ix, expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      if (ix) (ix)->poisoned.store(1);                                                     \
+      cudaGetLastError();                                                                  \
+      return fail(_e == cudaErrorMemoryAllocation ? CQS_B200_ERR_OOM : CQS_B200_ERR_CUDA,  \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,        \
+                  __LINE__);                                                               \
+    }                                                                                      \
+  } while (0)
+
+static size_t row_bytes(const cqs_b200_index* ix) {
+  return (size_t)ix->layout.ld * (ix->layout.mode == 0 ? 4 : 2);
+}
+
+static void free_shard(Shard& s) {
+  cudaSetDevice(s.device);
+  if (s.stream) cudaStreamSynchronize(s.stream);
+  cudaFree(s.d_rows); cudaFree(s.d_stage); cudaFree(s.d_query); cudaFree(s.d_bitset);
+  cudaFree(s.d_partial); cudaFree(s.d_partial_cnt); cudaFree(s.d_done);
+  cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
+  cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
+  cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
+  cudaFree(s.d_q_tok); cudaFree(s.d_q_w);
+  cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
+  cudaFree(s.d_f_present); cudaFree(s.d_f_n);
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
+  if (s.h_query) cudaFreeHost(s.h_query);
+  if (s.h_out) cudaFreeHost(s.h_out);
+  if (s.ev0) cudaEventDestroy(s.ev0);
+  if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Shard();
+}
+
+static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
+  s.device = device;
+  CK(ix, cudaSetDevice(device));
+  CK(ix, cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, device));
+  CK(ix, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(ix, cudaMalloc((void**)&s.d_query, sizeof(float) * ix->layout.ld * kQuerySlots));
+  CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld * kQuerySlots,
+                       cudaHostAllocDefault));
+  CK(ix, cudaMalloc((void**)&s.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
+  CK(ix, cudaMalloc((void**)&s.d_done, sizeof(uint32_t)));
+  CK(ix, cudaMemset(s.d_done, 0, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_out_scores, sizeof(float) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_out_rows, sizeof(uint64_t) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_out_n, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_sp_scores, sizeof(float) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_sp_rows, sizeof(uint64_t) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_sp_n, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_sp_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_sp_partial_cnt, sizeof(uint32_t) * kMaxGrid));
+  CK(ix, cudaMalloc((void**)&s.d_sp_done, sizeof(uint32_t)));
+  CK(ix, cudaMemset(s.d_sp_done, 0, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_q_tok, sizeof(uint32_t) * kSpMaxQ));
+  CK(ix, cudaMalloc((void**)&s.d_q_w, sizeof(float) * kSpMaxQ));
+  CK(ix, cudaMalloc((void**)&s.d_f_rows, sizeof(uint64_t) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_f_fused, sizeof(float) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_f_dense, sizeof(float) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_f_sraw, sizeof(float) * kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_f_present, kMaxK));
+  CK(ix, cudaMalloc((void**)&s.d_f_n, sizeof(uint32_t)));
+  CK(ix, cudaHostAlloc((void**)&s.h_out, kHostOutBytes, cudaHostAllocDefault));
+  CK(ix, cudaEventCreate(&s.ev0));
+  CK(ix, cudaEventCreate(&s.ev1));
+  return 0;
+}
+
+static int grow_shard(cqs_b200_index* ix, Shard& s, uint64_t want_rows) {
+  if (want_rows <= s.cap_rows) return 0;
+  uint64_t cap = std::max<uint64_t>(want_rows, s.cap_rows + s.cap_rows / 2);
+  cap = std::max<uint64_t>(cap, 1024);
+  CK(ix, cudaSetDevice(s.device));
+  uint8_t* nd = nullptr;
+  size_t rb = row_bytes(ix);
+  CK(ix, cudaMalloc((void**)&nd, cap * rb));
+  if (s.n_rows) CK(ix, cudaMemcpyAsync(nd, s.d_rows, s.n_rows * rb, cudaMemcpyDeviceToDevice, s.stream));
+  CK(ix, cudaStreamSynchronize(s.stream));
+  cudaFree(s.d_rows);
+  s.d_rows = nd;
+  s.cap_rows = cap;
+  return 0;
+}
+
+extern "C" {
+
+int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, int storage,
+                    cqs_b200_index** out) {
+  if (!out) return fail(CQS_B200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_dev < 1 || n_dev > 64) return fail(CQS_B200_ERR_INVALID, "n_dev must be in 1..64");
+  if (metric != CQS_B200_METRIC_COSINE && metric != CQS_B200_METRIC_DOT)
+    return fail(CQS_B200_ERR_INVALID, "unknown metric %d", metric);
+  if (storage != CQS_B200_STORAGE_F32 && storage != CQS_B200_STORAGE_BF16)
+    return fail(CQS_B200_ERR_INVALID, "unknown storage %d", storage);
+  RowLayout lay;
+  if (!choose_layout(dim, storage, &lay))
+    return fail(CQS_B200_ERR_INVALID, "unsupported dim %u (1..2048)", dim);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(CQS_B200_ERR_CUDA, "no CUDA device: %s (this backend has no CPU fallback)",
+                cudaGetErrorString(e));
+  }
+  cqs_b200_index* ix = new (std::nothrow) cqs_b200_index();
+  if (!ix) return fail(CQS_B200_ERR_OOM, "host allocation failed");
+  ix->dim = dim;
+  ix->layout = lay;
+  ix->metric = metric;
+  ix->storage = storage;
+  ix->shards.resize(n_dev);
+  for (int i = 0; i < n_dev; ++i) {
+    int dev = device_ids ? device_ids[i] : i;
+    if (dev < 0 || dev >= count) {
+      cqs_b200_destroy(ix);
+      return fail(CQS_B200_ERR_INVALID, "device id %d out of range (%d devices)", dev, count);
+    }
+    int rc = init_shard(ix, ix->shards[i], dev);
+    if (rc) {
+      cqs_b200_destroy(ix);
+      return rc;
+    }
+  }
+  *out = ix;
+  return CQS_B200_OK;
+}
+
+void cqs_b200_destroy(cqs_b200_index* ix) {
+  if (!ix) return;
+  for (auto& s : ix->shards) free_shard(s);
+  delete ix;
+}
+
+int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is finalized");
+  if (ix->n_rows) return fail(CQS_B200_ERR_INVALID, "reserve must precede the first append");
+  uint64_t nd = ix->shards.size();
+  uint64_t rps = (n_rows + nd - 1) / nd;
+  rps = (rps + 31) / 32 * 32;  // shard boundaries on bitset word boundaries
+  if (rps > 0xFFFFFFFFull) return fail(CQS_B200_ERR_INVALID, "more than 2^32-1 rows per device");
+  ix->reserved = n_rows;
+  ix->rows_per_shard = rps;
+  for (uint64_t i = 0; i < nd; ++i) {
+    ix->shards[i].first_row = i * rps;
+    int rc = grow_shard(ix, ix->shards[i], rps);
+    if (rc) return rc;
+  }
+  return CQS_B200_OK;
+}
+
+int cqs_b200_set_row_base(cqs_b200_index* ix, uint64_t row_base) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->row_base = row_base;
+  return CQS_B200_OK;
+}
+
+static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, bool on_device) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (n_rows == 0) return CQS_B200_OK;
+  if (!rows) return fail(CQS_B200_ERR_INVALID, "rows is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  if (ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is finalized (call cqs_b200_reopen)");
+  const uint64_t nd = ix->shards.size();
+  if (nd > 1 && !ix->rows_per_shard)
+    return fail(CQS_B200_ERR_INVALID, "n_dev > 1 requires cqs_b200_reserve before append");
+  if (on_device && nd > 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "device-pointer append needs a single-device index");
+  if (ix->rows_per_shard && ix->n_rows + n_rows > ix->rows_per_shard * nd)
+    return fail(CQS_B200_ERR_INVALID, "append exceeds the reserved size");
+  const size_t rb = row_bytes(ix);
+  const bool direct = (ix->layout.mode == 0 && ix->layout.ld == ix->dim);
+  uint64_t done = 0;
+  while (done < n_rows) {
+    uint64_t grow0 = ix->n_rows + done;  // row index inside the index
+    uint64_t si = ix->rows_per_shard ? grow0 / ix->rows_per_shard : 0;
+    Shard& s = ix->shards[si];
+    uint64_t local = grow0 - s.first_row;
+    uint64_t room = ix->rows_per_shard ? ix->rows_per_shard - local : (n_rows - done);
+    uint64_t take = std::min<uint64_t>(n_rows - done, room);
+    if (local + take > 0xFFFFFFFFull) return fail(CQS_B200_ERR_INVALID, "more than 2^32-1 rows per device");
+    CK(ix, cudaSetDevice(s.device));
+    int rc = grow_shard(ix, s, local + take);
+    if (rc) return rc;
+    const float* src = rows + done * ix->dim;
+    if (direct) {
+      CK(ix, cudaMemcpyAsync(s.d_rows + local * rb, src, take * rb,
+                             on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s.stream));
+    } else if (on_device) {
+      CK(ix, launch_convert_rows(src, ix->dim, take, s.d_rows, local, ix->layout, s.stream));
+    } else {
+      const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * ix->dim));
+      if (s.stage_rows < std::min(chunk, take)) {
+        cudaFree(s.d_stage);
+        s.d_stage = nullptr;
+        s.stage_rows = std::min(chunk, std::max<uint64_t>(take, 1024));
+        CK(ix, cudaMalloc((void**)&s.d_stage, s.stage_rows * sizeof(float) * ix->dim));
+      }
+      for (uint64_t c = 0; c < take; c += s.stage_rows) {
+        uint64_t m = std::min(s.stage_rows, take - c);
+        CK(ix, cudaMemcpyAsync(s.d_stage, src + c * ix->dim, m * sizeof(float) * ix->dim,
+                               cudaMemcpyHostToDevice, s.stream));
+        CK(ix, launch_convert_rows(s.d_stage, ix->dim, m, s.d_rows, local + c, ix->layout, s.stream));
+        CK(ix, cudaStreamSynchronize(s.stream));
+      }
+    }
+    CK(ix, cudaStreamSynchronize(s.stream));
+    s.n_rows = local + take;
+    done += take;
+  }
+  ix->n_rows += n_rows;
+  return CQS_B200_OK;
+}
+
+int cqs_b200_append_rows_f32(cqs_b200_index* ix, const float* rows, uint64_t n_rows) {
+  return append_impl(ix, rows, n_rows, false);
+}
+int cqs_b200_append_rows_f32_device(cqs_b200_index* ix, const float* d_rows, uint64_t n_rows) {
+  return append_impl(ix, d_rows, n_rows, true);
+}
+
+int cqs_b200_finalize(cqs_b200_index* ix) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  for (auto& s : ix->shards) {
+    CK(ix, cudaSetDevice(s.device));
+    cudaFree(s.d_stage);
+    s.d_stage = nullptr;
+    s.stage_rows = 0;
+    uint64_t words = (s.n_rows + 31) / 32;
+    if (words > s.bitset_words) {
+      cudaFree(s.d_bitset);
+      s.d_bitset = nullptr;
+      CK(ix, cudaMalloc((void**)&s.d_bitset, std::max<uint64_t>(words, 1) * 4));
+      s.bitset_words = words;
+    }
+    CK(ix, cudaStreamSynchronize(s.stream));
+  }
+  ix->finalized = true;
+  return CQS_B200_OK;
+}
+
+int cqs_b200_reopen(cqs_b200_index* ix) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->finalized = false;
+  return CQS_B200_OK;
+}
+
+static bool query_is_finite(const float* q, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (!isfinite(q[i])) return false;
+  return true;
+}
+
+// Host merge of per-device results (in-process multi-GPU): same order rule.
+struct HostCand {
+  uint32_t key;
+  uint64_t row;
+  float score;
+};
+static uint32_t host_ordered(float f) {
+  uint32_t b;
+  memcpy(&b, &f, 4);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// Upload query + (slice of) bitset to a shard and launch the dense scan into the
+// shard's dense pool buffers.  Asynchronous on s.stream.
+static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
+                        const uint32_t* bitset) {
+  CK(ix, cudaSetDevice(s.device));
+  memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
+  memcpy(s.h_query, query, sizeof(float) * ix->dim);
+  CK(ix, cudaMemcpyAsync(s.d_query, s.h_query, sizeof(float) * ix->layout.ld,
+                         cudaMemcpyHostToDevice, s.stream));
+  const uint32_t* d_bits = nullptr;
+  if (bitset) {
+    uint64_t words = (s.n_rows + 31) / 32;
+    CK(ix, cudaMemcpyAsync(s.d_bitset, bitset + s.first_row / 32, words * 4,
+                           cudaMemcpyHostToDevice, s.stream));
+    d_bits = s.d_bitset;
+  }
+  ScanArgs a;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = s.d_query;
+  a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
+  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  CK(ix, launch_scan_single(a, s.num_sms, s.stream));
+  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  return 0;
+}
+
+static int check_searchable(cqs_b200_index* ix) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned; rebuild it");
+  if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
+  return 0;
+}
+
+int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
+                    uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!query || !out_rows || !out_scores || !out_n)
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u exceeds max_k=%u", k, kMaxK);
+  if (k == 0 || ix->n_rows == 0) return CQS_B200_OK;      // src/cagra.rs:445
+  if (!query_is_finite(query, ix->dim)) return CQS_B200_OK;  // src/cagra.rs:458-470
+  std::lock_guard<std::mutex> g(ix->mu);
+  std::vector<Shard*> live;
+  for (auto& s : ix->shards)
+    if (s.n_rows) live.push_back(&s);
+  for (Shard* s : live) {
+    rc = launch_dense(ix, *s, query, k, bitset);
+    if (rc) return rc;
+    float* hs = (float*)s->h_out;
+    uint64_t* hr = (uint64_t*)(s->h_out + sizeof(float) * kMaxK);
+    uint32_t* hn = (uint32_t*)(s->h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
+    CK(ix, cudaMemcpyAsync(hs, s->d_out_scores, sizeof(float) * k, cudaMemcpyDeviceToHost, s->stream));
+    CK(ix, cudaMemcpyAsync(hr, s->d_out_rows, sizeof(uint64_t) * k, cudaMemcpyDeviceToHost, s->stream));
+    CK(ix, cudaMemcpyAsync(hn, s->d_out_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  }
+  float kms = 0.f;
+  for (Shard* s : live) {
+    CK(ix, cudaSetDevice(s->device));
+    CK(ix, cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    CK(ix, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    kms = std::max(kms, ms);
+  }
+  ix->last_kernel_ms = kms;
+  if (live.size() == 1) {
+    Shard* s = live[0];
+    uint32_t n = *(uint32_t*)(s->h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
+    n = std::min(n, k);
+    memcpy(out_scores, s->h_out, sizeof(float) * n);
+    memcpy(out_rows, s->h_out + sizeof(float) * kMaxK, sizeof(uint64_t) * n);
+    *out_n = n;
+    return CQS_B200_OK;
+  }
+  std::vector<HostCand> all;
+  for (Shard* s : live) {
+    const float* hs = (const float*)s->h_out;
+    const uint64_t* hr = (const uint64_t*)(s->h_out + sizeof(float) * kMaxK);
+    uint32_t n = std::min(*(uint32_t*)(s->h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK), k);
+    for (uint32_t i = 0; i < n; ++i) all.push_back({host_ordered(hs[i]), hr[i], hs[i]});
+  }
+  std::sort(all.begin(), all.end(), [](const HostCand& a, const HostCand& b) {
+    return a.key > b.key || (a.key == b.key && a.row < b.row);
+  });
+  uint32_t n = (uint32_t)std::min<size_t>(all.size(), k);
+  for (uint32_t i = 0; i < n; ++i) {
+    out_rows[i] = all[i].row;
+    out_scores[i] = all[i].score;
+  }
+  *out_n = n;
+  return CQS_B200_OK;
+}
+
+int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
+                           const uint32_t* d_bitset, float* d_out_scores, uint64_t* d_out_rows,
+                           uint32_t* d_out_n, void* stream) {
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!d_query || !d_out_scores || !d_out_rows || !d_out_n)
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u out of range 1..%u", k, kMaxK);
+  if (ix->shards.size() != 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "search_device needs a single-device index");
+  std::lock_guard<std::mutex> g(ix->mu);
+  Shard& s = ix->shards[0];
+  if (s.n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty index");
+  CK(ix, cudaSetDevice(s.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+  // the query must be zero padded to the row stride: stage it through d_query
+  CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
+  CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+  ScanArgs a;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = s.d_query;
+  a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
+  CK(ix, launch_scan_single(a, s.num_sms, st));
+  return CQS_B200_OK;
+}
+
+int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t* d_rows,
+                               uint32_t n_lists, uint32_t n_queries, uint32_t k,
+                               float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
+                               void* stream) {
+  if (!d_scores || !d_rows || !d_out_scores || !d_out_rows || !d_out_n)
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || (uint64_t)n_lists * k > 8192)
+    return fail(CQS_B200_ERR_INVALID, "n_lists*k must be in 1..8192");
+  cqs_b200_index* none = nullptr;
+  CK(none, cudaSetDevice(device));
+  MergeArgs a{d_scores, d_rows, n_lists, n_queries, k, d_out_scores, d_out_rows, d_out_n};
+  CK(none, launch_merge_topk(a, (cudaStream_t)stream));
+  return CQS_B200_OK;
+}
+
+int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                          const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                          uint32_t* out_n) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (nq && (!queries || !out_rows || !out_scores || !out_n))
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  for (uint32_t i = 0; i < nq; ++i) {
+    int rc = cqs_b200_search(ix, queries + (size_t)i * ix->dim, k, bitset,
+                             out_rows + (size_t)i * k, out_scores + (size_t)i * k, out_n + i);
+    if (rc) return rc;
+  }
+  return CQS_B200_OK;
+}
+
+// ---- sparse ------------------------------------------------------------------
+
+int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
+                           const float* w, uint32_t vocab) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (!indptr || vocab == 0) return fail(CQS_B200_ERR_INVALID, "NULL indptr / zero vocab");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  if (ix->shards.size() != 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "sparse leg needs a single-device index per process");
+  Shard& s = ix->shards[0];
+  const uint64_t n = s.n_rows;
+  const uint64_t nnz = indptr[n];
+  if (nnz && (!tok || !w)) return fail(CQS_B200_ERR_INVALID, "NULL tok / w");
+  // doc-major CSR -> token-major postings, stable in doc order (what
+  // SpladeIndex::build produces, src/splade/index.rs:197-203).
+  std::vector<uint64_t> tptr((size_t)vocab + 1, 0);
+  for (uint64_t d = 0; d < n; ++d) {
+    if (indptr[d + 1] < indptr[d]) return fail(CQS_B200_ERR_INVALID, "indptr not monotone at %llu", (unsigned long long)d);
+    for (uint64_t e = indptr[d]; e < indptr[d + 1]; ++e) {
+      if (tok[e] >= vocab) return fail(CQS_B200_ERR_INVALID, "token id %u >= vocab %u", tok[e], vocab);
+      tptr[tok[e] + 1]++;
+    }
+  }
+  for (uint32_t t = 0; t < vocab; ++t) tptr[t + 1] += tptr[t];
+  std::vector<uint32_t> pdoc(nnz);
+  std::vector<float> pw(nnz);
+  {
+    std::vector<uint64_t> cur(tptr.begin(), tptr.end() - 1);
+    for (uint64_t d = 0; d < n; ++d)
+      for (uint64_t e = indptr[d]; e < indptr[d + 1]; ++e) {
+        uint64_t pos = cur[tok[e]]++;
+        // a doc listing the same token twice would make two lanes update one
+        // accumulator in the same step; the SPLADE encoder never emits that
+        // (src/splade/mod.rs:685-729, one weight per vocabulary slot).
+        if (pos > tptr[tok[e]] && pdoc[pos - 1] == (uint32_t)d)
+          return fail(CQS_B200_ERR_INVALID, "doc %llu lists token %u twice", (unsigned long long)d, tok[e]);
+        pdoc[pos] = (uint32_t)d;
+        pw[pos] = w[e];
+      }
+  }
+  CK(ix, cudaSetDevice(s.device));
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
+  s.sparse = SparseDev();
+  CK(ix, cudaMalloc((void**)&s.sparse.d_tptr, sizeof(uint64_t) * ((size_t)vocab + 1)));
+  CK(ix, cudaMalloc((void**)&s.sparse.d_doc, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1)));
+  CK(ix, cudaMalloc((void**)&s.sparse.d_w, sizeof(float) * std::max<uint64_t>(nnz, 1)));
+  CK(ix, cudaMemcpy(s.sparse.d_tptr, tptr.data(), sizeof(uint64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice));
+  if (nnz) {
+    CK(ix, cudaMemcpy(s.sparse.d_doc, pdoc.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
+    CK(ix, cudaMemcpy(s.sparse.d_w, pw.data(), sizeof(float) * nnz, cudaMemcpyHostToDevice));
+  }
+  s.sparse.vocab = vocab;
+  s.sparse.nnz = nnz;
+  return CQS_B200_OK;
+}
+
+static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
+                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits) {
+  CK(ix, cudaMemcpyAsync(s.d_q_tok, q_tok, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, s.stream));
+  CK(ix, cudaMemcpyAsync(s.d_q_w, q_w, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, s.stream));
+  SparseArgs a;
+  a.sp = s.sparse; a.n_docs = s.n_rows; a.d_q_tok = s.d_q_tok; a.d_q_w = s.d_q_w; a.q_nnz = q_nnz;
+  a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;
+  a.d_out_scores = s.d_sp_scores; a.d_out_rows = s.d_sp_rows; a.d_out_n = s.d_sp_n;
+  CK(ix, launch_sparse_search(a, s.stream));
+  return 0;
+}
+
+int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const float* q_w,
+                           uint32_t q_nnz, uint32_t k, const uint32_t* bitset, uint64_t* out_rows,
+                           float* out_scores, uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!out_rows || !out_scores || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u exceeds max_k=%u", k, kMaxK);
+  if (q_nnz > kSpMaxQ) return fail(CQS_B200_ERR_INVALID, "query nnz %u exceeds %u", q_nnz, kSpMaxQ);
+  if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index required");
+  std::lock_guard<std::mutex> g(ix->mu);
+  Shard& s = ix->shards[0];
+  if (!s.sparse.d_tptr) return fail(CQS_B200_ERR_INVALID, "no sparse index attached");
+  if (k == 0 || q_nnz == 0 || s.n_rows == 0) return CQS_B200_OK;  // index.rs:236-238
+  if (!q_tok || !q_w) return fail(CQS_B200_ERR_INVALID, "NULL query");
+  CK(ix, cudaSetDevice(s.device));
+  const uint32_t* d_bits = nullptr;
+  if (bitset) {
+    CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
+    d_bits = s.d_bitset;
+  }
+  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, k, d_bits);
+  if (rc) return rc;
+  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  float* hs = (float*)s.h_out;
+  uint64_t* hr = (uint64_t*)(s.h_out + sizeof(float) * kMaxK);
+  uint32_t* hn = (uint32_t*)(s.h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
+  CK(ix, cudaMemcpyAsync(hs, s.d_sp_scores, sizeof(float) * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(hr, s.d_sp_rows, sizeof(uint64_t) * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(hn, s.d_sp_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaStreamSynchronize(s.stream));
+  CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  uint32_t n = std::min(*hn, k);
+  memcpy(out_scores, hs, sizeof(float) * n);
+  memcpy(out_rows, hr, sizeof(uint64_t) * n);
+  *out_n = n;
+  return CQS_B200_OK;
+}
+
+static int copy_fused_out(cqs_b200_index* ix, Shard& s, uint32_t cap, uint64_t* out_rows,
+                          float* out_fused, float* out_dense, float* out_sparse_raw,
+                          uint8_t* out_present, uint32_t* out_n, cudaStream_t st) {
+  uint8_t* h = s.h_out;
+  uint64_t* hr = (uint64_t*)h;
+  float* hf = (float*)(h + 8 * kMaxK);
+  float* hd = hf + kMaxK;
+  float* hs = hd + kMaxK;
+  uint8_t* hp = (uint8_t*)(hs + kMaxK);
+  uint32_t* hn = (uint32_t*)(hp + kMaxK);
+  CK(ix, cudaMemcpyAsync(hr, s.d_f_rows, 8 * cap, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaMemcpyAsync(hf, s.d_f_fused, 4 * cap, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaMemcpyAsync(hd, s.d_f_dense, 4 * cap, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaMemcpyAsync(hs, s.d_f_sraw, 4 * cap, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaMemcpyAsync(hp, s.d_f_present, cap, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaMemcpyAsync(hn, s.d_f_n, 4, cudaMemcpyDeviceToHost, st));
+  CK(ix, cudaStreamSynchronize(st));
+  uint32_t n = std::min(*hn, cap);
+  memcpy(out_rows, hr, 8 * n);
+  memcpy(out_fused, hf, 4 * n);
+  if (out_dense) memcpy(out_dense, hd, 4 * n);
+  if (out_sparse_raw) memcpy(out_sparse_raw, hs, 4 * n);
+  if (out_present) memcpy(out_present, hp, n);
+  *out_n = n;
+  return 0;
+}
+
+int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_t* q_tok,
+                           const float* q_w, uint32_t q_nnz, float alpha, uint32_t pool_k,
+                           const uint32_t* bitset, uint64_t* out_rows, float* out_fused,
+                           float* out_dense, float* out_sparse_raw, uint8_t* out_present,
+                           uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!query || !out_rows || !out_fused || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (pool_k > kMaxK) return fail(CQS_B200_ERR_INVALID, "pool_k=%u exceeds max_k=%u", pool_k, kMaxK);
+  if (q_nnz > kSpMaxQ) return fail(CQS_B200_ERR_INVALID, "query nnz %u exceeds %u", q_nnz, kSpMaxQ);
+  if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index required");
+  if (pool_k == 0 || ix->n_rows == 0) return CQS_B200_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  Shard& s = ix->shards[0];
+  if (!s.sparse.d_tptr) return fail(CQS_B200_ERR_INVALID, "no sparse index attached");
+  CK(ix, cudaSetDevice(s.device));
+  // dense leg: a malformed query yields an EMPTY dense pool (src/cagra.rs:458-470);
+  // the sparse leg still runs (search_hybrid_inner calls both unconditionally).
+  const bool dense_ok = query_is_finite(query, ix->dim);
+  CK(ix, cudaMemsetAsync(s.d_out_n, 0, 4, s.stream));
+  CK(ix, cudaMemsetAsync(s.d_sp_n, 0, 4, s.stream));
+  const uint32_t* d_bits = nullptr;
+  if (dense_ok) {
+    rc = launch_dense(ix, s, query, pool_k, bitset);
+    if (rc) return rc;
+    if (bitset) d_bits = s.d_bitset;
+  } else if (bitset) {
+    CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
+    d_bits = s.d_bitset;
+  }
+  if (q_nnz) {
+    if (!q_tok || !q_w) return fail(CQS_B200_ERR_INVALID, "NULL sparse query");
+    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits);
+    if (rc) return rc;
+  }
+  FuseArgs f;
+  f.d_dense_rows = s.d_out_rows; f.d_dense_scores = s.d_out_scores; f.d_n_dense = s.d_out_n;
+  f.d_sparse_rows = s.d_sp_rows; f.d_sparse_scores = s.d_sp_scores; f.d_n_sparse = s.d_sp_n;
+  f.alpha = alpha; f.pool_k = pool_k;
+  f.d_out_rows = s.d_f_rows; f.d_out_fused = s.d_f_fused; f.d_out_dense = s.d_f_dense;
+  f.d_out_sparse_raw = s.d_f_sraw; f.d_out_present = s.d_f_present; f.d_out_n = s.d_f_n;
+  CK(ix, launch_fuse_pools(f, s.stream));
+  rc = copy_fused_out(ix, s, pool_k, out_rows, out_fused, out_dense, out_sparse_raw, out_present,
+                      out_n, s.stream);
+  if (rc) return rc;
+  if (dense_ok) CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  return CQS_B200_OK;
+}
+
+int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* dense_scores,
+                        uint32_t n_dense, const uint64_t* sparse_rows, const float* sparse_scores,
+                        uint32_t n_sparse, float alpha, uint32_t pool_k, uint64_t* out_rows,
+                        float* out_fused, float* out_dense, float* out_sparse_raw,
+                        uint8_t* out_present, uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  if (!out_rows || !out_fused || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (n_dense > kMaxK || n_sparse > kMaxK || pool_k > 2 * kMaxK)
+    return fail(CQS_B200_ERR_INVALID, "pool larger than %u", kMaxK);
+  if ((n_dense && (!dense_rows || !dense_scores)) || (n_sparse && (!sparse_rows || !sparse_scores)))
+    return fail(CQS_B200_ERR_INVALID, "NULL pool");
+  uint32_t cap = std::min(pool_k, n_dense + n_sparse);
+  if (cap == 0) return CQS_B200_OK;
+  cqs_b200_index* none = nullptr;
+  CK(none, cudaSetDevice(device));
+  // one scratch allocation: [dense rows | sparse rows | dense sc | sparse sc | counts | outputs]
+  const size_t K = kMaxK, OUTK = 2 * kMaxK;
+  size_t bytes = 8 * K * 2 + 4 * K * 2 + 16 + OUTK * (8 + 4 + 4 + 4 + 1) + 16;
+  uint8_t* d = nullptr;
+  CK(none, cudaMalloc((void**)&d, bytes));
+  uint64_t* d_dr = (uint64_t*)d;
+  uint64_t* d_sr = d_dr + K;
+  float* d_ds = (float*)(d_sr + K);
+  float* d_ss = d_ds + K;
+  uint32_t* d_cnt = (uint32_t*)(d_ss + K);
+  uint64_t* o_rows = (uint64_t*)(d_cnt + 4);
+  float* o_f = (float*)(o_rows + OUTK);
+  float* o_d = o_f + OUTK;
+  float* o_s = o_d + OUTK;
+  uint8_t* o_p = (uint8_t*)(o_s + OUTK);
+  uint32_t cnt[2] = {n_dense, n_sparse};
+  int rc = CQS_B200_OK;
+  auto body = [&]() -> int {
+    if (n_dense) {
+      CK(none, cudaMemcpy(d_dr, dense_rows, 8 * n_dense, cudaMemcpyHostToDevice));
+      CK(none, cudaMemcpy(d_ds, dense_scores, 4 * n_dense, cudaMemcpyHostToDevice));
+    }
+    if (n_sparse) {
+      CK(none, cudaMemcpy(d_sr, sparse_rows, 8 * n_sparse, cudaMemcpyHostToDevice));
+      CK(none, cudaMemcpy(d_ss, sparse_scores, 4 * n_sparse, cudaMemcpyHostToDevice));
+    }
+    CK(none, cudaMemcpy(d_cnt, cnt, 8, cudaMemcpyHostToDevice));
+    FuseArgs f;
+    f.d_dense_rows = d_dr; f.d_dense_scores = d_ds; f.d_n_dense = d_cnt;
+    f.d_sparse_rows = d_sr; f.d_sparse_scores = d_ss; f.d_n_sparse = d_cnt + 1;
+    f.alpha = alpha; f.pool_k = cap;
+    f.d_out_rows = o_rows; f.d_out_fused = o_f; f.d_out_dense = o_d; f.d_out_sparse_raw = o_s;
+    f.d_out_present = o_p; f.d_out_n = d_cnt + 2;
+    CK(none, launch_fuse_pools(f, 0));
+    uint32_t n = 0;
+    CK(none, cudaMemcpy(&n, d_cnt + 2, 4, cudaMemcpyDeviceToHost));
+    n = std::min(n, cap);
+    CK(none, cudaMemcpy(out_rows, o_rows, 8 * n, cudaMemcpyDeviceToHost));
+    CK(none, cudaMemcpy(out_fused, o_f, 4 * n, cudaMemcpyDeviceToHost));
+    if (out_dense) CK(none, cudaMemcpy(out_dense, o_d, 4 * n, cudaMemcpyDeviceToHost));
+    if (out_sparse_raw) CK(none, cudaMemcpy(out_sparse_raw, o_s, 4 * n, cudaMemcpyDeviceToHost));
+    if (out_present) CK(none, cudaMemcpy(out_present, o_p, n, cudaMemcpyDeviceToHost));
+    *out_n = n;
+    return CQS_B200_OK;
+  };
+  rc = body();
+  cudaFree(d);
+  return rc;
+}
+
+int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, uint32_t dim,
+                             const float* queries, uint32_t nq, float threshold, int32_t* out_cat,
+                             float* out_margin) {
+  if (nq == 0) return CQS_B200_OK;
+  if (!centroids || !queries || !out_cat || !out_margin || n_c == 0 || dim == 0)
+    return fail(CQS_B200_ERR_INVALID, "NULL / empty argument");
+  cqs_b200_index* none = nullptr;
+  CK(none, cudaSetDevice(device));
+  float *d_c = nullptr, *d_q = nullptr, *d_m = nullptr;
+  int32_t* d_cat = nullptr;
+  int rc = CQS_B200_OK;
+  auto body = [&]() -> int {
+    CK(none, cudaMalloc((void**)&d_c, sizeof(float) * (size_t)n_c * dim));
+    CK(none, cudaMalloc((void**)&d_q, sizeof(float) * (size_t)nq * dim));
+    CK(none, cudaMalloc((void**)&d_m, sizeof(float) * nq));
+    CK(none, cudaMalloc((void**)&d_cat, sizeof(int32_t) * nq));
+    CK(none, cudaMemcpy(d_c, centroids, sizeof(float) * (size_t)n_c * dim, cudaMemcpyHostToDevice));
+    CK(none, cudaMemcpy(d_q, queries, sizeof(float) * (size_t)nq * dim, cudaMemcpyHostToDevice));
+    CK(none, launch_route_centroids(d_c, n_c, dim, d_q, nq, threshold, d_cat, d_m, 0));
+    CK(none, cudaMemcpy(out_cat, d_cat, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost));
+    CK(none, cudaMemcpy(out_margin, d_m, sizeof(float) * nq, cudaMemcpyDeviceToHost));
+    return CQS_B200_OK;
+  };
+  rc = body();
+  cudaFree(d_c); cudaFree(d_q); cudaFree(d_m); cudaFree(d_cat);
+  return rc;
+}
+
+// ---- introspection ---------------------------------------------------------
+
+uint64_t cqs_b200_len(const cqs_b200_index* ix) { return ix ? ix->n_rows : 0; }
+uint32_t cqs_b200_dim(const cqs_b200_index* ix) { return ix ? ix->dim : 0; }
+uint32_t cqs_b200_max_k(const cqs_b200_index*) { return kMaxK; }
+int cqs_b200_is_poisoned(const cqs_b200_index* ix) { return ix ? ix->poisoned.load() : 0; }
+int cqs_b200_scores_are_cosine(const cqs_b200_index* ix) {
+  return ix && ix->storage == CQS_B200_STORAGE_F32 && ix->metric == CQS_B200_METRIC_COSINE;
+}
+const char* cqs_b200_name(void) { return "B200"; }
+const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }
+uint64_t cqs_b200_kernel_launches(void) { return g_kernel_launches.load(); }
+float cqs_b200_last_kernel_ms(cqs_b200_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// internal.h — host-side declarations shared by the translation units of
+// libcqs_b200.so.  Nothing here is part of the C ABI (include/cqs_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+namespace cqs {
+
+typedef unsigned long long ckey_t;
+
+constexpr uint32_t kMaxK = 1024;        // CQS_B200_MAX_K
+constexpr uint32_t kMaxGrid = 1024;     // upper bound on scan CTAs (partial-list slots)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+// Row layout in HBM: row-major, `ld` elements per row (dim zero-padded up to
+// ld), 16-byte aligned rows.  mode: 0 = f32 (float4 per lane), 1 = bf16 with
+// 16-byte lane vectors (8 elems), 2 = bf16 with 8-byte lane vectors (4 elems).
+// nv = lane vectors per row per lane: ld == 32 * elems_per_vec * nv.
+struct RowLayout {
+  uint32_t ld;
+  int mode;
+  int nv;
+};
+// Returns false when dim is unsupported (0 or > 2048).
+bool choose_layout(uint32_t dim, int storage, RowLayout* out);
+
+struct ScanArgs {
+  const void* d_rows;       // [n_rows][ld] f32 or bf16
+  uint64_t n_rows;          // <= 2^32 - 1
+  RowLayout layout;
+  const float* d_query;     // f32[ld], zero padded
+  const uint32_t* d_bitset; // nullable, ceil(n_rows/32) words
+  uint32_t k;               // 1..kMaxK
+  uint64_t row_base;        // added to local rows in the output
+  ckey_t* d_partial;         // [kMaxGrid][kMaxK] scratch
+  uint32_t* d_partial_cnt;  // [kMaxGrid]
+  uint32_t* d_done;         // [1], zero between launches
+  float* d_out_scores;      // [k]
+  uint64_t* d_out_rows;     // [k]
+  uint32_t* d_out_n;        // [1]
+};
+// Kernel 1+3: single-query streaming scan with the top-k select fused in.
+cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);
+
+// f32 -> bf16 (RNE) / f32 row conversion into the padded layout.
+cudaError_t launch_convert_rows(const float* d_src, uint32_t dim, uint64_t n_rows, void* d_dst,
+                                uint64_t dst_row0, RowLayout layout, cudaStream_t stream);
+
+struct MergeArgs {
+  const float* d_scores;   // [n_lists][n_queries][k]
+  const uint64_t* d_rows;  // same shape, global rows; UINT64_MAX = empty slot
+  uint32_t n_lists, n_queries, k;
+  float* d_out_scores;     // [n_queries][k]
+  uint64_t* d_out_rows;
+  uint32_t* d_out_n;       // [n_queries]
+};
+cudaError_t launch_merge_topk(const MergeArgs& a, cudaStream_t stream);
+
+// ---- sparse (SPLADE) ----
+struct SparseDev {
+  // token-major postings (CSC): for token t, entries [tptr[t], tptr[t+1]) sorted by doc asc
+  uint64_t* d_tptr = nullptr;   // [vocab+1]
+  uint32_t* d_doc = nullptr;    // [nnz]
+  float* d_w = nullptr;         // [nnz]
+  uint32_t vocab = 0;
+  uint64_t nnz = 0;
+};
+struct SparseArgs {
+  SparseDev sp;
+  uint64_t n_docs;
+  const uint32_t* d_q_tok;  // [q_nnz] (query order)
+  const float* d_q_w;
+  uint32_t q_nnz;
+  const uint32_t* d_bitset;
+  uint32_t k;
+  uint64_t row_base;
+  ckey_t* d_partial;         // [n_blocks][kMaxK]
+  uint32_t* d_partial_cnt;
+  uint32_t* d_done;
+  float* d_out_scores;
+  uint64_t* d_out_rows;
+  uint32_t* d_out_n;
+};
+constexpr uint32_t kSparseDocsPerBlock = 4096;
+cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
+
+struct FuseArgs {
+  const uint64_t* d_dense_rows; const float* d_dense_scores; const uint32_t* d_n_dense;
+  const uint64_t* d_sparse_rows; const float* d_sparse_scores; const uint32_t* d_n_sparse;
+  float alpha; uint32_t pool_k;
+  uint64_t* d_out_rows; float* d_out_fused; float* d_out_dense; float* d_out_sparse_raw;
+  uint8_t* d_out_present; uint32_t* d_out_n;
+};
+cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t stream);
+
+cudaError_t launch_route_centroids(const float* d_centroids, uint32_t n_c, uint32_t dim,
+                                   const float* d_queries, uint32_t nq, float threshold,
+                                   int32_t* d_out_cat, float* d_out_margin, cudaStream_t stream);
+
+}  // namespace cqs

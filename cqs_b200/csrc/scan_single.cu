@@ -1,0 +1,397 @@
+// scan_single.cu — kernels 1 and 3 of the north star: the single-query exact
+// scan (GEMV-style streaming over f32 / bf16 rows, HBM-bound) with the top-k
+// selection fused into its epilogue, so the score vector never touches HBM.
+//
+// Replaces, per query: the row loop of Store::search_filtered_with_notes
+// (src/search/query.rs:453-482) = math::cosine_similarity per row
+// (src/math.rs:11-28) + BoundedScoreHeap::push (src/search/scoring/
+// candidate.rs:274-318) + into_sorted_vec (:321-329).
+//
+// Shape of the kernel
+//   * one warp owns a whole row at a time: 32 lanes x 16-byte vectors cover
+//     512 contiguous bytes per request, NV requests per row, all issued before
+//     the first FMA (U rows in flight per warp) -> fully coalesced 128-byte
+//     lines, ld.global.nc.L1::no_allocate (data is touched once).
+//   * the query lives in registers (NV*E floats per lane) for the whole kernel.
+//   * per lane 4 independent fp32 accumulators, then a 5-step shuffle
+//     butterfly: the summation tree is fixed (independent of grid size), error
+//     ~ (NV + 7) ulp-ish, well inside the 1e-5 relative contract.
+//   * a row whose key beats the CTA's current threshold is appended to a
+//     shared-memory candidate buffer; the CTA re-selects (bitonic sort) only
+//     when the buffer might overflow.  Each CTA emits <= k sorted keys; the
+//     last CTA to finish (atomic ticket) merges the G lists and writes the
+//     final (score desc, row asc) result.  One launch per query.
+//   * persistent grid: one 512-thread CTA per SM, tiles of 16*U rows handed
+//     out round-robin.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace cqs {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kCap = 4096;  // candidate slots per CTA (32 KB)
+
+struct ScanParams {
+  const uint8_t* rows;
+  uint64_t n_rows;
+  uint64_t row_bytes;
+  const float* query;
+  const uint32_t* bitset;
+  uint32_t k;
+  uint64_t row_base;
+  ckey_t* partial;
+  uint32_t* partial_cnt;
+  uint32_t* done;
+  float* out_scores;
+  uint64_t* out_rows;
+  uint32_t* out_n;
+};
+
+template <int MODE>
+struct LaneVec;
+template <>
+struct LaneVec<0> {  // f32, 4 elems / 16 B
+  static constexpr int E = 4;
+  static constexpr int BYTES = 16;
+  uint32_t r[4];
+  __device__ __forceinline__ void load(const uint8_t* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
+  __device__ __forceinline__ void fma(const float* q, float* acc) const {
+    acc[0] = fmaf(__uint_as_float(r[0]), q[0], acc[0]);
+    acc[1] = fmaf(__uint_as_float(r[1]), q[1], acc[1]);
+    acc[2] = fmaf(__uint_as_float(r[2]), q[2], acc[2]);
+    acc[3] = fmaf(__uint_as_float(r[3]), q[3], acc[3]);
+  }
+};
+template <>
+struct LaneVec<1> {  // bf16, 8 elems / 16 B
+  static constexpr int E = 8;
+  static constexpr int BYTES = 16;
+  uint32_t r[4];
+  __device__ __forceinline__ void load(const uint8_t* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
+  __device__ __forceinline__ void fma(const float* q, float* acc) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // bf16 -> f32 is a 16-bit shift (exact)
+      acc[(2 * i) & 3] = fmaf(__uint_as_float(r[i] << 16), q[2 * i], acc[(2 * i) & 3]);
+      acc[(2 * i + 1) & 3] =
+          fmaf(__uint_as_float(r[i] & 0xFFFF0000u), q[2 * i + 1], acc[(2 * i + 1) & 3]);
+    }
+  }
+};
+template <>
+struct LaneVec<2> {  // bf16, 4 elems / 8 B
+  static constexpr int E = 4;
+  static constexpr int BYTES = 8;
+  uint32_t r[2];
+  __device__ __forceinline__ void load(const uint8_t* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1])
+                 : "l"(p));
+  }
+  __device__ __forceinline__ void zero() { r[0] = r[1] = 0; }
+  __device__ __forceinline__ void fma(const float* q, float* acc) const {
+    acc[0] = fmaf(__uint_as_float(r[0] << 16), q[0], acc[0]);
+    acc[1] = fmaf(__uint_as_float(r[0] & 0xFFFF0000u), q[1], acc[1]);
+    acc[2] = fmaf(__uint_as_float(r[1] << 16), q[2], acc[2]);
+    acc[3] = fmaf(__uint_as_float(r[1] & 0xFFFF0000u), q[3], acc[3]);
+  }
+};
+
+template <int MODE, int NV, int U>
+__global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams p) {
+  using V = LaneVec<MODE>;
+  constexpr int E = V::E;
+  constexpr uint32_t kBurst = 1024;                       // max pushes per check interval
+  constexpr uint32_t kCheckEvery = kBurst / (kWarps * U); // iterations between checks
+  static_assert(kCap >= kMaxK + 2 * kBurst, "candidate buffer too small");
+
+  __shared__ ckey_t s_buf[kCap];
+  __shared__ uint32_t s_cnt;
+  __shared__ ckey_t s_thr;
+  __shared__ uint32_t s_last;
+  __shared__ uint32_t s_pos[kMaxGrid];
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TopK tk{s_buf, &s_cnt, &s_thr, kCap};
+  tk.init();
+
+  float q[NV * E];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int e = 0; e < E; ++e) q[v * E + e] = __ldg(p.query + (v * 32 + lane) * E + e);
+  __syncthreads();
+
+  const uint64_t n = p.n_rows;
+  const uint64_t tiles = (n + (uint64_t)kWarps * U - 1) / ((uint64_t)kWarps * U);
+  const uint32_t k = p.k;
+  ckey_t thr = 0;
+  uint32_t it = 0;
+  for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const uint64_t row0 = (tile * kWarps + warp) * U;
+    V d[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (row0 + u < n) {
+        const uint8_t* rp = p.rows + (row0 + u) * p.row_bytes + (size_t)lane * V::BYTES;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) d[u][v].load(rp + (size_t)v * 32 * V::BYTES);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) d[u][v].zero();
+      }
+    }
+    float s[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) d[u][v].fma(q + v * E, acc);
+      s[u] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+    float mine = s[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u)
+      if (lane == u) mine = s[u];
+    if (lane < U && row0 + lane < n) {
+      const uint64_t r = row0 + lane;
+      const uint32_t bits = __float_as_uint(mine);
+      bool ok = finite_bits(bits);
+      if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
+      if (ok) {
+        ckey_t key = make_key(mine, (uint32_t)r);
+        if (key > thr) tk.push(key);
+      }
+    }
+    if ((it % kCheckEvery) == kCheckEvery - 1) {
+      // thread 0's view of the count may miss pushes of this interval that
+      // are still in flight in other warps (< kBurst), hence the 2*kBurst.
+      int need = 0;
+      if (threadIdx.x == 0) {
+        uint32_t c = s_cnt;
+        need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
+      }
+      if (__syncthreads_or(need)) {
+        tk.compact(k);
+        thr = s_thr;
+      }
+    }
+  }
+  tk.compact(k);
+  const uint32_t mycnt = s_cnt;
+  for (uint32_t i = threadIdx.x; i < mycnt; i += kThreads)
+    p.partial[(size_t)blockIdx.x * kMaxK + i] = s_buf[i];
+  if (threadIdx.x == 0) p.partial_cnt[blockIdx.x] = mycnt;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t ticket = atomicAdd(p.done, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  merge_partials_and_emit(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x, blockIdx.x,
+                          p.row_base, p.out_scores, p.out_rows, p.out_n);
+  if (threadIdx.x == 0) *p.done = 0;
+}
+
+bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
+  if (dim == 0 || dim > 2048) return false;
+  static const int kNv[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  auto pick = [&](uint32_t per_nv) -> int {
+    uint32_t need = (dim + per_nv - 1) / per_nv;
+    for (int nv : kNv)
+      if ((uint32_t)nv >= need) return nv;
+    return 0;
+  };
+  if (storage == 0) {
+    int nv = pick(128);
+    if (!nv) return false;
+    *out = {(uint32_t)nv * 128u, 0, nv};
+    return true;
+  }
+  // bf16: prefer 16-byte lane vectors when they do not add padding
+  int nv8 = pick(256), nv4 = pick(128);
+  if (nv8 && (!nv4 || (uint32_t)nv8 * 256u <= (uint32_t)nv4 * 128u)) {
+    *out = {(uint32_t)nv8 * 256u, 1, nv8};
+    return true;
+  }
+  if (!nv4) return false;
+  *out = {(uint32_t)nv4 * 128u, 2, nv4};
+  return true;
+}
+
+template <int MODE, int NV>
+static cudaError_t launch_nv(const ScanParams& p, int grid, cudaStream_t st) {
+  constexpr int U = (NV <= 3) ? 4 : (NV <= 6 ? 2 : 1);
+  scan_topk_kernel<MODE, NV, U><<<grid, kThreads, 0, st>>>(p);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const ScanParams& p, int nv, int grid, cudaStream_t st) {
+  switch (nv) {
+    case 1: return launch_nv<MODE, 1>(p, grid, st);
+    case 2: return launch_nv<MODE, 2>(p, grid, st);
+    case 3: return launch_nv<MODE, 3>(p, grid, st);
+    case 4: return launch_nv<MODE, 4>(p, grid, st);
+    case 6: return launch_nv<MODE, 6>(p, grid, st);
+    case 8: return launch_nv<MODE, 8>(p, grid, st);
+    case 12: return launch_nv<MODE, 12>(p, grid, st);
+    case 16: return launch_nv<MODE, 16>(p, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) {
+  if (a.n_rows == 0 || a.k == 0 || a.k > kMaxK || a.n_rows > 0xFFFFFFFFull)
+    return cudaErrorInvalidValue;
+  ScanParams p;
+  p.rows = (const uint8_t*)a.d_rows;
+  p.n_rows = a.n_rows;
+  p.row_bytes = (uint64_t)a.layout.ld * (a.layout.mode == 0 ? 4 : 2);
+  p.query = a.d_query;
+  p.bitset = a.d_bitset;
+  p.k = a.k;
+  p.row_base = a.row_base;
+  p.partial = a.d_partial;
+  p.partial_cnt = a.d_partial_cnt;
+  p.done = a.d_done;
+  p.out_scores = a.d_out_scores;
+  p.out_rows = a.d_out_rows;
+  p.out_n = a.d_out_n;
+  const int U = (a.layout.nv <= 3) ? 4 : (a.layout.nv <= 6 ? 2 : 1);
+  uint64_t tiles = (a.n_rows + (uint64_t)kWarps * U - 1) / ((uint64_t)kWarps * U);
+  int grid = (int)(tiles < (uint64_t)num_sms ? tiles : (uint64_t)num_sms);
+  if (grid > (int)kMaxGrid) grid = kMaxGrid;
+  switch (a.layout.mode) {
+    case 0: return launch_mode<0>(p, a.layout.nv, grid, st);
+    case 1: return launch_mode<1>(p, a.layout.nv, grid, st);
+    case 2: return launch_mode<2>(p, a.layout.nv, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ---- row ingest: f32 [n][dim] -> padded f32 / bf16(RNE) [n][ld] -------------
+__global__ void convert_rows_kernel(const float* __restrict__ src, uint32_t dim, uint64_t n_rows,
+                                    uint8_t* __restrict__ dst, uint64_t dst_row0, uint32_t ld,
+                                    int is_bf16) {
+  const uint64_t total = n_rows * ld;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = i / ld;
+    uint32_t c = (uint32_t)(i - r * ld);
+    float v = c < dim ? src[r * dim + c] : 0.f;
+    uint64_t o = (dst_row0 + r) * ld + c;
+    if (is_bf16)
+      ((__nv_bfloat16*)dst)[o] = __float2bfloat16_rn(v);
+    else
+      ((float*)dst)[o] = v;
+  }
+}
+
+cudaError_t launch_convert_rows(const float* d_src, uint32_t dim, uint64_t n_rows, void* d_dst,
+                                uint64_t dst_row0, RowLayout layout, cudaStream_t st) {
+  if (n_rows == 0) return cudaSuccess;
+  uint64_t total = n_rows * layout.ld;
+  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  convert_rows_kernel<<<grid, 256, 0, st>>>(d_src, dim, n_rows, (uint8_t*)d_dst, dst_row0,
+                                            layout.ld, layout.mode != 0);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+// ---- cross-shard merge (after the all-gather) ------------------
+// One CTA per query; n_lists*k <= 8192 candidates sorted by (score desc, row asc).
+// Global rows need all 64 bits, so the sort runs on (ordered score, row) pairs.
+struct Cand {
+  uint32_t s;  // ordered score, 0 = empty
+  uint64_t r;
+};
+__device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
+  return a.s > b.s || (a.s == b.s && a.r < b.r);  // a ranks ahead of b
+}
+constexpr uint32_t kMergeCap = 8192;
+__global__ void __launch_bounds__(512) merge_topk_kernel(const MergeArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t* s_s = (uint32_t*)smem;                       // [P]
+  uint64_t* s_r = (uint64_t*)(smem + sizeof(uint32_t) * kMergeCap);  // [P]
+  const uint32_t qi = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+  const uint32_t total = a.n_lists * a.k;
+  const uint32_t P = next_pow2(total);
+  for (uint32_t i = tid; i < P; i += T) {
+    uint32_t s = 0;
+    uint64_t r = ~0ull;
+    if (i < total) {
+      uint32_t l = i / a.k, j = i - l * a.k;
+      size_t off = ((size_t)l * a.n_queries + qi) * a.k + j;
+      r = a.d_rows[off];
+      uint32_t bits = __float_as_uint(a.d_scores[off]);
+      if (r != ~0ull && finite_bits(bits)) s = ordered_u32(bits);
+    }
+    s_s[i] = s;
+    s_r[i] = r;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= P; size <<= 1)
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (P >> 1); i += T) {
+        uint32_t pos = 2 * i - (i & (stride - 1));
+        Cand x{s_s[pos], s_r[pos]}, y{s_s[pos + stride], s_r[pos + stride]};
+        bool dir = ((pos & size) == 0);
+        if (cand_before(y, x) == dir) {
+          s_s[pos] = y.s; s_r[pos] = y.r;
+          s_s[pos + stride] = x.s; s_r[pos + stride] = x.r;
+        }
+      }
+      __syncthreads();
+    }
+  __shared__ uint32_t s_n;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < a.k; i += T) {
+    bool valid = i < P && s_s[i] != 0;
+    a.d_out_scores[(size_t)qi * a.k + i] =
+        valid ? __uint_as_float(unordered_u32(s_s[i])) : __uint_as_float(0xFF800000u);
+    a.d_out_rows[(size_t)qi * a.k + i] = valid ? s_r[i] : ~0ull;
+    if (valid) atomicAdd(&s_n, 1u);
+  }
+  __syncthreads();
+  if (tid == 0) a.d_out_n[qi] = s_n;
+}
+
+cudaError_t launch_merge_topk(const MergeArgs& a, cudaStream_t st) {
+  if (a.n_queries == 0 || a.k == 0) return cudaSuccess;
+  if ((uint64_t)a.n_lists * a.k > kMergeCap) return cudaErrorInvalidValue;
+  size_t smem = (sizeof(uint32_t) + sizeof(uint64_t)) * kMergeCap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    attr_set = true;
+  }
+  merge_topk_kernel<<<a.n_queries, 512, smem, st>>>(a);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+}  // namespace cqs

@@ -1,0 +1,236 @@
+"""Python mirror of the reference's ``VectorIndex`` trait for the B200 backend
+(src/index.rs:139-239) — the shape the Rust shim in INTEGRATION.md has.
+
+Chunk-id strings stay on this side (``id_map``), the library speaks row
+indices (src/cagra.rs:268).  Rows are sorted by chunk id once at build so the
+device tie-break (row asc) equals the reference's (id asc).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check, ptr
+
+
+@dataclass
+class IndexResult:  # src/index.rs:129
+    id: str
+    score: float
+
+
+def _sort_key(s: str) -> bytes:
+    return s.encode("utf-8")  # Rust String ordering is bytewise
+
+
+class B200Index:
+    """impl VectorIndex for B200Index (name() == "B200")."""
+
+    def __init__(self, dim: int, metric: str = "cosine", storage: str = "f32",
+                 devices: Optional[Sequence[int]] = None, row_base: int = 0):
+        self._h = C.c_void_p()
+        self._dim = int(dim)
+        self.storage = storage
+        devs = list(devices) if devices is not None else [0]
+        arr = (C.c_int * len(devs))(*devs)
+        check(lib.cqs_b200_create(arr, len(devs), self._dim,
+                                  capi.METRIC_COSINE if metric == "cosine" else capi.METRIC_DOT,
+                                  capi.STORAGE_F32 if storage == "f32" else capi.STORAGE_BF16,
+                                  C.byref(self._h)))
+        self.id_map: list[str] = []
+        self.row_base = int(row_base)
+        if row_base:
+            check(lib.cqs_b200_set_row_base(self._h, int(row_base)))
+        self._bitset_cache: dict = {}
+
+    # ---- build -----------------------------------------------------------
+    @classmethod
+    def build(cls, ids: Sequence[str], embeddings: np.ndarray, **kw) -> "B200Index":
+        """The try_open / build_from_store analogue (src/cagra.rs:842-919): takes the
+        (chunk_id, embedding) feed in any order, drops zero / non-finite rows like
+        prepare_index_data (src/hnsw/mod.rs:716-736), sorts by chunk id, uploads."""
+        emb = np.ascontiguousarray(embeddings, dtype=np.float32)
+        ok = np.isfinite(emb).all(axis=1) & (np.abs(emb).sum(axis=1) > 0)
+        keep = np.nonzero(ok)[0]
+        order = sorted(keep.tolist(), key=lambda i: _sort_key(ids[i]))
+        ix = cls(emb.shape[1], **kw)
+        ix.reserve(len(order))
+        ix.append([ids[i] for i in order], emb[order])
+        ix.finalize()
+        return ix
+
+    def reserve(self, n: int) -> None:
+        check(lib.cqs_b200_reserve(self._h, int(n)))
+
+    def append(self, ids: Optional[Sequence[str]], rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        assert rows.ndim == 2 and rows.shape[1] == self._dim
+        check(lib.cqs_b200_append_rows_f32(self._h, ptr(rows), rows.shape[0]))
+        if ids is not None:
+            self.id_map.extend(ids)
+
+    def append_device(self, d_ptr: int, n_rows: int) -> None:
+        check(lib.cqs_b200_append_rows_f32_device(self._h, C.c_void_p(d_ptr), int(n_rows)))
+
+    def finalize(self) -> None:
+        check(lib.cqs_b200_finalize(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib.cqs_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- VectorIndex -------------------------------------------------------
+    def __len__(self) -> int:
+        return int(lib.cqs_b200_len(self._h))
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    def name(self) -> str:
+        return lib.cqs_b200_name().decode()
+
+    def dim(self) -> int:
+        return int(lib.cqs_b200_dim(self._h))
+
+    def is_poisoned(self) -> bool:
+        return bool(lib.cqs_b200_is_poisoned(self._h))
+
+    def max_k(self) -> Optional[int]:
+        return int(lib.cqs_b200_max_k(self._h))
+
+    def index_scores_are_cosine(self) -> bool:
+        return bool(lib.cqs_b200_scores_are_cosine(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(lib.cqs_b200_last_kernel_ms(self._h))
+
+    def search_rows(self, query: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
+        """Row-level search: (rows u64[n], scores f32[n]).  Errors surface as
+        exceptions here; ``search`` maps them to an empty result like the shim."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self._dim:
+            return np.empty(0, np.uint64), np.empty(0, np.float32)  # src/cagra.rs:449-456
+        kk = max(int(k), 0)
+        rows = np.empty(max(kk, 1), np.uint64)
+        scores = np.empty(max(kk, 1), np.float32)
+        n = C.c_uint32(0)
+        bs = None if bitset is None else np.ascontiguousarray(bitset, dtype=np.uint32)
+        check(lib.cqs_b200_search(self._h, ptr(q), kk, ptr(bs), ptr(rows), ptr(scores), C.byref(n)))
+        return rows[: n.value].copy(), scores[: n.value].copy()
+
+    def _results(self, rows, scores) -> list[IndexResult]:
+        out = []
+        for r, s in zip(rows.tolist(), scores.tolist()):
+            local = r - self.row_base
+            if 0 <= local < len(self.id_map):  # drop out-of-range slots (src/cagra.rs:642-669)
+                out.append(IndexResult(self.id_map[local], float(np.float32(s))))
+        return out
+
+    def search(self, query: np.ndarray, k: int) -> list[IndexResult]:
+        try:
+            return self._results(*self.search_rows(query, k))
+        except capi.B200Error:
+            return []  # every device failure -> empty Vec (src/cagra.rs:541-627)
+
+    def bitset_for(self, flt: Callable[[str], bool]):
+        """Predicate -> (bitset, included): bit i%32 of word i/32 (src/cagra.rs:747-757)."""
+        n = len(self.id_map)
+        mask = np.fromiter((bool(flt(i)) for i in self.id_map), dtype=bool, count=n)
+        pad = (-n) % 32
+        bits = np.concatenate([mask, np.zeros(pad, bool)]).astype(np.uint8)
+        return np.packbits(bits, bitorder="little").view("<u4").copy(), int(mask.sum())
+
+    def search_with_filter(self, query: np.ndarray, k: int, flt: Callable[[str], bool]) -> list[IndexResult]:
+        n = len(self.id_map)
+        if n == 0 or k == 0:
+            return []
+        bitset, included = self.bitset_for(flt)
+        if included == n:               # all pass -> unfiltered path (src/cagra.rs:759-762)
+            return self.search(query, k)
+        if included == 0:               # none pass (:764-767)
+            return []
+        try:
+            return self._results(*self.search_rows(query, min(k, included), bitset))
+        except capi.B200Error:
+            return []
+
+    # ---- inherent (no trait counterpart) ---------------------------------------
+    def search_batch_rows(self, queries: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self._dim
+        nq = q.shape[0]
+        rows = np.empty((nq, max(k, 1)), np.uint64)
+        scores = np.empty((nq, max(k, 1)), np.float32)
+        n = np.zeros(nq, np.uint32)
+        bs = None if bitset is None else np.ascontiguousarray(bitset, dtype=np.uint32)
+        check(lib.cqs_b200_search_batch(self._h, ptr(q), nq, int(k), ptr(bs), ptr(rows), ptr(scores), ptr(n)))
+        return rows, scores, n
+
+    # ---- SPLADE leg / hybrid (row level) ------------------------------------------
+    def sparse_attach(self, indptr: np.ndarray, tok: np.ndarray, w: np.ndarray, vocab: int) -> None:
+        ip = np.ascontiguousarray(indptr, dtype=np.uint64)
+        t = np.ascontiguousarray(tok, dtype=np.uint32)
+        ww = np.ascontiguousarray(w, dtype=np.float32)
+        check(lib.cqs_b200_sparse_attach(self._h, ptr(ip), ptr(t), ptr(ww), int(vocab)))
+
+    def search_sparse_rows(self, q_tok, q_w, k: int, bitset=None):
+        t = np.ascontiguousarray(q_tok, dtype=np.uint32)
+        w = np.ascontiguousarray(q_w, dtype=np.float32)
+        rows = np.empty(max(k, 1), np.uint64)
+        scores = np.empty(max(k, 1), np.float32)
+        n = C.c_uint32(0)
+        bs = None if bitset is None else np.ascontiguousarray(bitset, dtype=np.uint32)
+        check(lib.cqs_b200_search_sparse(self._h, ptr(t), ptr(w), t.shape[0], int(k), ptr(bs),
+                                         ptr(rows), ptr(scores), C.byref(n)))
+        return rows[: n.value].copy(), scores[: n.value].copy()
+
+    def search_hybrid_rows(self, query, q_tok, q_w, alpha: float, pool_k: int, bitset=None):
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        t = np.ascontiguousarray(q_tok, dtype=np.uint32)
+        w = np.ascontiguousarray(q_w, dtype=np.float32)
+        kk = max(int(pool_k), 1)
+        rows = np.empty(kk, np.uint64)
+        fused = np.empty(kk, np.float32)
+        dense = np.empty(kk, np.float32)
+        sraw = np.empty(kk, np.float32)
+        present = np.empty(kk, np.uint8)
+        n = C.c_uint32(0)
+        bs = None if bitset is None else np.ascontiguousarray(bitset, dtype=np.uint32)
+        check(lib.cqs_b200_search_hybrid(self._h, ptr(q), ptr(t), ptr(w), t.shape[0], float(alpha),
+                                         int(pool_k), ptr(bs), ptr(rows), ptr(fused), ptr(dense),
+                                         ptr(sraw), ptr(present), C.byref(n)))
+        m = n.value
+        return dict(rows=rows[:m].copy(), fused=fused[:m].copy(), dense=dense[:m].copy(),
+                    sparse_raw=sraw[:m].copy(), present=present[:m].copy())
+
+
+def fuse_pools(dense_rows, dense_scores, sparse_rows, sparse_scores, alpha: float, pool_k: int, device: int = 0):
+    """a11 on caller-supplied pools (src/search/query.rs:914-1005)."""
+    dr = np.ascontiguousarray(dense_rows, dtype=np.uint64)
+    ds = np.ascontiguousarray(dense_scores, dtype=np.float32)
+    sr = np.ascontiguousarray(sparse_rows, dtype=np.uint64)
+    ss = np.ascontiguousarray(sparse_scores, dtype=np.float32)
+    cap = max(min(int(pool_k), dr.shape[0] + sr.shape[0]), 1)
+    rows = np.empty(cap, np.uint64)
+    fused = np.empty(cap, np.float32)
+    dense = np.empty(cap, np.float32)
+    sraw = np.empty(cap, np.float32)
+    present = np.empty(cap, np.uint8)
+    n = C.c_uint32(0)
+    check(lib.cqs_b200_fuse_pools(device, ptr(dr), ptr(ds), dr.shape[0], ptr(sr), ptr(ss), sr.shape[0],
+                                  float(alpha), int(pool_k), ptr(rows), ptr(fused), ptr(dense), ptr(sraw),
+                                  ptr(present), C.byref(n)))
+    m = n.value
+    return dict(rows=rows[:m].copy(), fused=fused[:m].copy(), dense=dense[:m].copy(),
+                sparse_raw=sraw[:m].copy(), present=present[:m].copy())

@@ -1,0 +1,175 @@
+/* cqs_b200.h — C ABI of the B200-native exact retrieval backend for cqs.
+ *
+ * This is the drop-in boundary: the only surface the reference's Rust side
+ * binds (INTEGRATION.md shows the `extern "C"` block and the
+ * `impl VectorIndex for B200Index` shim).  Every entry point cites the
+ * reference interface it replaces (paths relative to jamie8johnson/cqs
+ * v1.51.0).
+ *
+ * Conventions (mirroring the existing FFI backend, src/cagra.rs):
+ *   - return 0 on success, a negative CQS_B200_ERR_* otherwise; never throws,
+ *     never aborts.  `cqs_b200_last_error()` gives a thread-local message.
+ *   - inputs are borrowed for the duration of the call; outputs are
+ *     caller-allocated (capacity k, or nq*k for batches).
+ *   - the device side speaks ROW INDICES only; chunk-id strings stay with the
+ *     caller as `id_map[row]` (src/cagra.rs:268).  Rows must be appended in
+ *     ascending chunk-id order so that the tie-break "(score desc, row asc)"
+ *     equals the reference's "(score desc, id asc)"
+ *     (src/search/scoring/candidate.rs:303-329).
+ *   - any CUDA failure sets a sticky poison bit (`cqs_b200_is_poisoned`),
+ *     the analogue of src/cagra.rs:276,472-489 / src/index.rs:203-205.
+ *   - an index handle is internally serialised by one mutex
+ *     (src/cagra.rs:263) and may be shared across threads.
+ *   - score of a row = f32 dot(query, row) (== cosine for the unit-norm
+ *     embeddings cqs stores; this is exactly math::cosine_similarity,
+ *     src/math.rs:11-28).  Rows whose score is NaN/Inf are dropped
+ *     (src/math.rs:23-27 -> None; candidate.rs:275).
+ */
+#ifndef CQS_B200_H
+#define CQS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CQS_B200_OK 0
+#define CQS_B200_ERR_INVALID (-1)   /* bad argument / wrong state            */
+#define CQS_B200_ERR_CUDA (-2)      /* CUDA runtime failure (poisons index)   */
+#define CQS_B200_ERR_POISONED (-3)  /* index already poisoned; rebuild it     */
+#define CQS_B200_ERR_OOM (-4)       /* device or host allocation failed       */
+#define CQS_B200_ERR_UNSUPPORTED (-5)
+
+#define CQS_B200_METRIC_COSINE 0    /* DistanceMetric::Cosine  src/index.rs:45 */
+#define CQS_B200_METRIC_DOT 1       /* DistanceMetric::DotProduct             */
+#define CQS_B200_STORAGE_F32 0      /* rows kept as f32 (BLOB layout, src/store/helpers/embeddings.rs:14-41) */
+#define CQS_B200_STORAGE_BF16 1     /* rows rounded (RNE) to bf16; the rounded matrix IS the corpus */
+
+#define CQS_B200_MAX_K 1024u        /* VectorIndex::max_k()  src/index.rs:217  */
+
+typedef struct cqs_b200_index cqs_b200_index; /* opaque */
+
+/* ---- lifecycle ----------------------------------------------------------
+ * Replaces CagraIndex::build_from_store_with_metric + CagraBackend::try_open
+ * (src/cagra.rs:842-919, :1664-1803): the "build" of an exact-scan backend is
+ * streaming the f32 BLOBs into HBM.
+ * device_ids/n_dev: shards the rows in contiguous blocks over n_dev GPUs of
+ * this process (n_dev > 1 requires cqs_b200_reserve before the first append). */
+int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, int storage,
+                    cqs_b200_index** out);
+/* Pre-size for n_rows total rows (avoids regrowth; mandatory for n_dev > 1). */
+int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows);
+/* Global row number of local row 0.  Used when one process holds one shard of a
+ * corpus that is row-sharded across processes; reported rows
+ * are row_base + local row. */
+int cqs_b200_set_row_base(cqs_b200_index* ix, uint64_t row_base);
+/* Host rows, row-major f32[n_rows][dim] — the store.embedding_batches feed
+ * (src/cagra.rs:888-916).  Copied; caller keeps ownership. */
+int cqs_b200_append_rows_f32(cqs_b200_index* ix, const float* rows, uint64_t n_rows);
+/* Same, but `d_rows` is a device pointer on the index's (single) device. */
+int cqs_b200_append_rows_f32_device(cqs_b200_index* ix, const float* d_rows, uint64_t n_rows);
+/* Seal the index: after this, searches are allowed and appends are rejected
+ * until cqs_b200_reopen (the TieredIndex::extend analogue, src/tiered.rs:317-360). */
+int cqs_b200_finalize(cqs_b200_index* ix);
+int cqs_b200_reopen(cqs_b200_index* ix);
+void cqs_b200_destroy(cqs_b200_index* ix); /* syncs all streams first (src/cagra.rs:289-301) */
+
+/* ---- VectorIndex::search / search_with_filter  (src/index.rs:146,167) ------
+ * query: f32[dim].  bitset: NULL or ceil(len/32) words, bit (i%32) of word
+ * (i/32) set = row i passes (src/cagra.rs:747-757).
+ * Output sorted (score desc by f32 total order, row asc); *out_n <= k.
+ * k == 0, empty index or a non-finite query -> *out_n = 0, returns 0
+ * (src/cagra.rs:445-470).  k > CQS_B200_MAX_K -> CQS_B200_ERR_INVALID. */
+int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
+                    uint64_t* out_rows, float* out_scores, uint32_t* out_n);
+
+/* nq independent queries (no trait counterpart — exposed as an inherent
+ * B200Index::search_batch).  queries: f32[nq][dim]; outputs
+ * [nq][k] with out_n[nq].  With bf16 storage and nq >= 64 this runs the
+ * tcgen05 tile scan over bf16-rounded queries, over-fetches, and re-scores the
+ * candidates with the f32 queries; results are identical to nq calls of
+ * cqs_b200_search. */
+int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                          const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                          uint32_t* out_n);
+
+/* ---- SPLADE leg: SpladeIndex::build / search_with_filter -------------------
+ * (src/splade/index.rs:191-211, :223-291).  Doc-major CSR over the SAME rows
+ * (row i of the CSR is chunk i): indptr[len+1], tok/w[indptr[len]]. Copied. */
+int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
+                           const float* w, uint32_t vocab);
+/* Sparse-only search: score[c] = sum over query tokens IN QUERY ORDER of
+ * qw*dw (separate f32 mul and add), only chunks touched by >= 1 posting. */
+int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const float* q_w,
+                           uint32_t q_nnz, uint32_t k, const uint32_t* bitset, uint64_t* out_rows,
+                           float* out_scores, uint32_t* out_n);
+
+/* ---- hybrid: the two leg calls + alpha fusion of search_hybrid_inner -------
+ * (src/search/query.rs:880-1005).  pool_k = cap_k_to_backend(candidate_count).
+ * Output: the fused pool, sorted (fused desc, row asc), truncated to pool_k,
+ * with the per-leg values the SearchLegs inspector reports
+ * (src/search/query.rs:39-208): out_dense = raw cosine (0.0 if absent),
+ * out_sparse_raw = raw SPLADE dot (0.0 if absent), out_present bit0 = in dense
+ * pool, bit1 = in sparse pool.  Output capacity: pool_k each. */
+int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_t* q_tok,
+                           const float* q_w, uint32_t q_nnz, float alpha, uint32_t pool_k,
+                           const uint32_t* bitset, uint64_t* out_rows, float* out_fused,
+                           float* out_dense, float* out_sparse_raw, uint8_t* out_present,
+                           uint32_t* out_n);
+
+/* The fusion step alone on caller-supplied pools (what search_hybrid_inner does
+ * after the two leg calls, src/search/query.rs:914-1005).  Pools are in leg
+ * order (dense first in the union).  Runs on `device`.  Output capacity:
+ * min(pool_k, n_dense + n_sparse). */
+int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* dense_scores,
+                        uint32_t n_dense, const uint64_t* sparse_rows, const float* sparse_scores,
+                        uint32_t n_sparse, float alpha, uint32_t pool_k, uint64_t* out_rows,
+                        float* out_fused, float* out_dense, float* out_sparse_raw,
+                        uint8_t* out_present, uint32_t* out_n);
+
+/* ---- CentroidClassifier::classify  (src/search/router.rs:1415-1444) --------
+ * centroids f32[n_c][dim], queries f32[nq][dim] (host).  out_cat[q] = index of
+ * the best centroid if best-second >= threshold else -1; out_margin[q]. */
+int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, uint32_t dim,
+                             const float* queries, uint32_t nq, float threshold, int32_t* out_cat,
+                             float* out_margin);
+
+/* ---- row-sharded corpora across processes -------------------
+ * Local top-k left ON THE DEVICE so a collective can follow without a host
+ * round trip.  d_query f32[dim] (device), d_bitset nullable (device, local
+ * rows).  d_out_scores f32[k], d_out_rows u64[k] (GLOBAL rows), d_out_n u32[1];
+ * unused slots are filled with (-inf, UINT64_MAX).  `stream` is a
+ * cudaStream_t (0 = the index's own stream).  Asynchronous. */
+int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
+                           const uint32_t* d_bitset, float* d_out_scores, uint64_t* d_out_rows,
+                           uint32_t* d_out_n, void* stream);
+/* Merge n_lists gathered candidate lists of k slots each (the all-gather
+ * result) into the global top-k, same ordering rule.  All pointers device.
+ * Batched: n_queries independent merges laid out [list][query][k]. */
+int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t* d_rows,
+                               uint32_t n_lists, uint32_t n_queries, uint32_t k,
+                               float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
+                               void* stream);
+
+/* ---- introspection: VectorIndex::{len,dim,max_k,is_poisoned,name} ----------
+ * (src/index.rs:149-217) */
+uint64_t cqs_b200_len(const cqs_b200_index* ix);
+uint32_t cqs_b200_dim(const cqs_b200_index* ix);
+uint32_t cqs_b200_max_k(const cqs_b200_index* ix);
+int cqs_b200_is_poisoned(const cqs_b200_index* ix);
+/* 1 iff returned scores are the brute-force cosine itself (f32 storage),
+ * VectorIndex::index_scores_are_cosine, src/index.rs:236. */
+int cqs_b200_scores_are_cosine(const cqs_b200_index* ix);
+const char* cqs_b200_name(void);        /* "B200" */
+const char* cqs_b200_last_error(void);  /* thread-local */
+/* Number of CUDA kernels this library has launched in this process. */
+uint64_t cqs_b200_kernel_launches(void);
+/* Device time (ms) of the dominant kernel of the most recent search call on
+ * this index, from CUDA events recorded on the launching stream. */
+float cqs_b200_last_kernel_ms(cqs_b200_index* ix);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CQS_B200_H */

@@ -1,0 +1,263 @@
+"""GPU parity: dense exact scan + fused top-k (kernels 1 and 3) vs the oracle.
+
+All calls go through the C ABI (ctypes) — cqs_b200.B200Index is the mirror of
+the reference's VectorIndex (src/index.rs:139-239)."""
+import numpy as np
+import pytest
+
+from oracle import cqs_oracle as O, c_oracle as CO
+from tests.parity import assert_topk_parity, bits
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def cqs():
+    import cqs_b200
+    return cqs_b200
+
+
+@pytest.fixture(scope="module")
+def config1():
+    """BASELINE configs[0]: 17,523 x 768 f32 from the reference's own generator
+    (examples/exp_level_scale.rs:200-224), 218 queries: the generator stream
+    continued, plus 32 'row + noise' self-match queries; 32 exact duplicate rows."""
+    rows, st = CO.synth_vectors(17523, 768)
+    rows[100:132] = rows[5000:5032]            # exact duplicates -> ties broken by row asc
+    q, _ = CO.synth_vectors(218, 768, st)
+    rng = np.random.default_rng(1)
+    pick = rng.choice(17523, size=32, replace=False)
+    noisy = rows[pick] + rng.standard_normal((32, 768)).astype(f32) * f32(0.002)
+    noisy /= np.linalg.norm(noisy, axis=1, keepdims=True)
+    q[:32] = noisy.astype(f32)
+    q[32] = rows[5003]                          # exact self-match, hits the duplicate pair
+    return rows, q
+
+
+@pytest.fixture(scope="module")
+def index1(cqs, config1):
+    rows, _ = config1
+    ix = cqs.B200Index(768, storage="f32")
+    ix.append(None, rows)
+    ix.finalize()
+    yield ix
+    ix.close()
+
+
+def test_config1_top20_all_218_queries(index1, config1):
+    rows, queries = config1
+    assert len(index1) == 17523 and index1.dim() == 768 and index1.name() == "B200"
+    assert index1.index_scores_are_cosine() and index1.max_k() == 1024 and not index1.is_poisoned()
+    for qi in range(queries.shape[0]):
+        full = O.dense_scores(rows, queries[qi])
+        o_rows, o_sc = O.topk_rows(full, 20)
+        g_rows, g_sc = index1.search_rows(queries[qi], 20)
+        assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+
+
+def test_config1_duplicates_tie_break_is_row_ascending(index1, config1):
+    rows, queries = config1
+    g_rows, g_sc = index1.search_rows(queries[32], 4)   # query == rows[5003] == rows[103]
+    assert g_rows[0] == 103 and g_rows[1] == 5003
+    assert bits(g_sc[0]) == bits(g_sc[1])
+
+
+def test_config1_production_pool_k500_and_k1024(index1, config1):
+    rows, queries = config1
+    for qi in (0, 33, 100):
+        full = O.dense_scores(rows, queries[qi])
+        for k in (500, 1024):
+            o_rows, o_sc = O.topk_rows(full, k)
+            g_rows, g_sc = index1.search_rows(queries[qi], k)
+            assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+
+
+@pytest.mark.parametrize("k", [1, 2, 7, 32, 33, 100])
+def test_config1_various_k(index1, config1, k):
+    rows, queries = config1
+    full = O.dense_scores(rows, queries[40])
+    o_rows, o_sc = O.topk_rows(full, k)
+    g_rows, g_sc = index1.search_rows(queries[40], k)
+    assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+
+
+def test_filter_bitset_semantics(index1, config1):
+    rows, queries = config1
+    n = rows.shape[0]
+    rng = np.random.default_rng(2)
+    full = O.dense_scores(rows, queries[50])
+    for frac in (0.5, 0.01):
+        mask = rng.random(n) < frac
+        bs = O.mask_to_bitset(mask)
+        o_rows, o_sc = O.topk_rows(full, 20, mask)
+        g_rows, g_sc = index1.search_rows(queries[50], 20, bs)
+        assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+        assert mask[g_rows.astype(np.int64)].all()          # only passing ids
+    one = np.zeros(n, bool); one[n - 1] = True               # last row only, k > included
+    g_rows, g_sc = index1.search_rows(queries[50], 20, O.mask_to_bitset(one))
+    assert g_rows.tolist() == [n - 1]
+    none = np.zeros(n, bool)
+    g_rows, _ = index1.search_rows(queries[50], 20, O.mask_to_bitset(none))
+    assert g_rows.shape[0] == 0
+
+
+def test_query_guards_and_k_edges(cqs, index1, config1):
+    rows, queries = config1
+    q = queries[0]
+    assert index1.search(q, 0) == []                                      # k = 0 (src/cagra.rs:445)
+    assert index1.search_rows(q[:100], 5)[0].shape[0] == 0                # wrong dim -> empty
+    for bad in (np.nan, np.inf, -np.inf):                                 # tests/hnsw_test.rs:460-552
+        qq = q.copy(); qq[7] = bad
+        assert index1.search_rows(qq, 5)[0].shape[0] == 0
+    with pytest.raises(cqs.B200Error):                                    # k > max_k is refused loudly...
+        index1.search_rows(q, 1025)
+    assert index1.search(q, 1025) == []                                   # ...and the trait method maps it to empty
+    assert not index1.is_poisoned()
+    # idempotent
+    a = index1.search_rows(q, 20); b = index1.search_rows(q, 20)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 127, 1000])
+def test_small_corpora_k_larger_than_n(cqs, n):
+    rows = O.fast_unit_rows(n, 768, seed=n)
+    ix = cqs.B200Index(768)
+    ix.append(None, rows); ix.finalize()
+    q = O.fast_unit_rows(1, 768, seed=99)[0]
+    g_rows, g_sc = ix.search_rows(q, 50)
+    full = O.dense_scores(rows, q)
+    o_rows, o_sc = O.topk_rows(full, 50)
+    assert g_rows.shape[0] == min(n, 50)                                  # <= n unique real ids
+    assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+    ix.close()
+
+
+def test_empty_index_returns_empty(cqs):
+    ix = cqs.B200Index(768)
+    ix.finalize()
+    assert len(ix) == 0 and ix.is_empty()
+    assert ix.search(np.ones(768, f32), 5) == []
+    ix.close()
+
+
+def test_zero_and_nonfinite_rows_in_corpus(cqs):
+    rows = O.fast_unit_rows(500, 768, seed=4)
+    rows[10] = 0.0                       # zero vector: finite score 0.0 (src/cagra.rs:2606-2640)
+    rows[20, 5] = np.nan                 # NaN row: cosine_similarity -> None -> never a candidate
+    rows[30, 6] = np.inf
+    ix = cqs.B200Index(768)
+    ix.append(None, rows); ix.finalize()
+    q = O.fast_unit_rows(1, 768, seed=5)[0]
+    g_rows, g_sc = ix.search_rows(q, 500)
+    assert g_rows.shape[0] == 498 and np.all(np.isfinite(g_sc))
+    assert 20 not in g_rows.tolist() and 30 not in g_rows.tolist() and 10 in g_rows.tolist()
+    full = O.dense_scores(rows, q)
+    o_rows, o_sc = O.topk_rows(full, 500)
+    assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+    ix.close()
+
+
+@pytest.mark.parametrize("dim", [768, 1024, 384, 100, 1536, 2048, 8])
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_dims_and_storage(cqs, dim, storage):
+    n = 3000
+    rows = O.fast_unit_rows(n, dim, seed=dim)
+    ix = cqs.B200Index(dim, storage=storage)
+    ix.append(None, rows[:1700]); ix.append(None, rows[1700:])            # two appends (regrowth path)
+    ix.finalize()
+    corpus = O.bf16_to_f32(O.f32_to_bf16_rne(rows)) if storage == "bf16" else rows
+    assert ix.index_scores_are_cosine() == (storage == "f32")
+    for s in range(3):
+        q = O.fast_unit_rows(1, dim, seed=1000 + s)[0]
+        full = O.dense_scores(corpus, q)
+        o_rows, o_sc = O.topk_rows(full, 20)
+        g_rows, g_sc = ix.search_rows(q, 20)
+        assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+    ix.close()
+
+
+def test_clustered_corpus_near_ties_bf16_and_f32(cqs):
+    rows = O.fast_unit_rows(20000, 768, seed=8, clustered=True)
+    q = rows[123] + np.random.default_rng(0).standard_normal(768).astype(f32) * f32(0.01)
+    q /= np.linalg.norm(q)
+    for storage in ("f32", "bf16"):
+        ix = cqs.B200Index(768, storage=storage)
+        ix.append(None, rows); ix.finalize()
+        corpus = O.bf16_to_f32(O.f32_to_bf16_rne(rows)) if storage == "bf16" else rows
+        full = O.dense_scores(corpus, q)
+        for k in (20, 500):
+            o_rows, o_sc = O.topk_rows(full, k)
+            g_rows, g_sc = ix.search_rows(q, k)
+            assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+        ix.close()
+
+
+def test_vector_index_trait_mirror_ids_filter_and_order(cqs):
+    """B200Index::{build, search, search_with_filter} at the id level: the feed
+    arrives in rowid order, ids tie-break ascending (candidate.rs:321-329)."""
+    rng = np.random.default_rng(12)
+    n = 400
+    emb = O.fast_unit_rows(n, 768, seed=12)
+    ids = [f"f{int(x):05d}.rs:1:{int(x) * 7919 % 100000:08x}" for x in rng.permutation(n)]
+    emb[7] = emb[3]                                  # tie between ids[3] and ids[7]
+    emb[50] = 0.0                                    # dropped at build like prepare_index_data
+    ix = cqs.B200Index.build(ids, emb)
+    assert len(ix) == n - 1 and ix.id_map == sorted(i for j, i in enumerate(ids) if j != 50)
+    res = ix.search(emb[3], 5)
+    assert [r.id for r in res[:2]] == sorted([ids[3], ids[7]])
+    assert all(res[i].score >= res[i + 1].score for i in range(len(res) - 1))
+    # literal oracle over (id, score): BoundedScoreHeap semantics
+    h = O.BoundedScoreHeap(5)
+    for j, cid in enumerate(ids):
+        if j == 50:
+            continue
+        h.push(cid, float(O.cosine_similarity(emb[3], emb[j])))
+    assert [r.id for r in res] == [i for i, _ in h.into_sorted_vec()]
+    only_rs = lambda cid: cid.endswith("0") or cid.endswith("a")
+    res = ix.search_with_filter(emb[3], 10, only_rs)
+    assert res and all(only_rs(r.id) for r in res)
+    assert ix.search_with_filter(emb[3], 10, lambda cid: False) == []     # all-reject -> empty
+    assert [r.id for r in ix.search_with_filter(emb[3], 5, lambda cid: True)] == [r.id for r in ix.search(emb[3], 5)]
+    ix.close()
+
+
+def test_search_batch_equals_single_calls(index1, config1):
+    rows, queries = config1
+    r, s, n = index1.search_batch_rows(queries[:16], 20)
+    for i in range(16):
+        a, b = index1.search_rows(queries[i], 20)
+        assert n[i] == 20 and np.array_equal(r[i], a) and np.array_equal(bits(s[i]), bits(b))
+
+
+def test_config2_full_size_1m_f32(cqs):
+    """BASELINE configs[1] at full size: 1,000,000 x 768 f32, top-20 and top-500;
+    oracle on 3 queries plus size-independent properties (self-match, idempotence,
+    sortedness, filter subset)."""
+    n, dim = 1_000_000, 768
+    ix = cqs.B200Index(dim)
+    ix.reserve(n)
+    blocks = []
+    for b in range(10):
+        blk = O.fast_unit_rows(n // 10, dim, seed=100 + b)
+        ix.append(None, blk)
+        blocks.append(blk)
+    ix.finalize()
+    rows = np.concatenate(blocks)
+    del blocks
+    assert len(ix) == n
+    for s in range(3):
+        q = O.fast_unit_rows(1, dim, seed=2000 + s)[0]
+        full = O.dense_scores(rows, q)
+        for k in (20, 500):
+            o_rows, o_sc = O.topk_rows(full, k)
+            g_rows, g_sc = ix.search_rows(q, k)
+            assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+    for i in (0, 123_456, n - 1):                        # self-match
+        g_rows, g_sc = ix.search_rows(rows[i], 1)
+        assert g_rows[0] == i and abs(g_sc[0] - 1.0) < 1e-5
+    mask = np.zeros(n, bool); mask[::7] = True
+    g_rows, _ = ix.search_rows(rows[77], 20, O.mask_to_bitset(mask))
+    assert (g_rows % 7 == 0).all() and g_rows[0] == 77
+    assert ix.last_kernel_ms() > 0
+    ix.close()
