@@ -195,7 +195,10 @@ def main():
     nq_total = Q * (args.steps + args.warmup)
     queries = make_queries(nq_total, 7)          # identical on every rank (same seed)
     d_queries = torch.from_numpy(queries).to(dev)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library treats stream == NULL as "use the
+    # index's own stream", and CUDA events only see the stream they are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)

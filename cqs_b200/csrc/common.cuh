@@ -40,38 +40,127 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
   return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
 }
 
-// In-place descending bitonic sort of buf[0..P), P a power of two, by the whole
-// CTA.  Ends with a __syncthreads().
-__device__ __forceinline__ void bitonic_sort_desc(ckey_t* buf, uint32_t P) {
-  const uint32_t T = blockDim.x, tid = threadIdx.x;
-  for (uint32_t size = 2; size <= P; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t i = tid; i < (P >> 1); i += T) {
-        uint32_t pos = 2 * i - (i & (stride - 1));
-        ckey_t a = buf[pos], b = buf[pos + stride];
-        bool dir = ((pos & size) == 0);
-        if ((a < b) == dir) {
-          buf[pos] = b;
-          buf[pos + stride] = a;
+// A set of threads of one CTA that synchronise on a named barrier: the whole CTA
+// (barrier 0) or, in the warp-specialised scan, just the consumer warps.
+struct Group {
+  uint32_t tid, nthr, bar;
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory");
+  }
+  __device__ __forceinline__ bool any(bool p) const {  // barrier + OR-reduction
+    uint32_t r;
+    asm volatile(
+        "{\n.reg .pred q, o;\nsetp.ne.u32 q, %3, 0;\n"
+        "bar.red.or.pred o, %1, %2, q;\nselp.u32 %0, 1, 0, o;\n}\n"
+        : "=r"(r)
+        : "r"(bar), "r"(nthr), "r"((uint32_t)p)
+        : "memory");
+    return r != 0;
+  }
+};
+
+// ---- block sort ---------------------------------------------------------------
+// In-place descending bitonic sort of buf[0..P) by the group; P is a power of two
+// and a multiple of kSortChunk.  A warp owns a 256-key chunk in registers (8 keys
+// per lane, element index = base + r*32 + lane): network strides < 32 are lane
+// shuffles, strides 32..128 are register-to-register, only strides >= 256 go
+// through shared memory with a barrier.  Sorting 2048 keys costs 10 barriers
+// instead of the 66 of the plain shared-memory network.
+constexpr uint32_t kSortR = 8;
+constexpr uint32_t kSortChunk = 32 * kSortR;  // 256
+
+// Apply the strides stride_start, stride_start/2, .., 1 (stride_start <= 128) of
+// the bitonic merge of width `size` to one chunk held in registers.
+__device__ __forceinline__ void sort_chunk_pass(ckey_t (&reg)[kSortR], uint32_t lane,
+                                                uint32_t base, uint32_t size,
+                                                uint32_t stride_start) {
+#pragma unroll
+  for (int ls = 7; ls >= 0; --ls) {
+    const uint32_t st = 1u << ls;
+    if (st > stride_start) continue;
+    if (st >= 32) {
+      const uint32_t rs = st >> 5;
+#pragma unroll
+      for (uint32_t r = 0; r < kSortR; ++r) {
+        if (r & rs) continue;
+        const uint32_t i = base + r * 32 + lane;  // lower index of the pair
+        const bool dir = (i & size) == 0;
+        const ckey_t a = reg[r], b2 = reg[r | rs];
+        if ((a < b2) == dir) {
+          reg[r] = b2;
+          reg[r | rs] = a;
         }
       }
-      __syncthreads();
+    } else {
+      const bool lower = (lane & st) == 0;
+#pragma unroll
+      for (uint32_t r = 0; r < kSortR; ++r) {
+        const uint32_t il = (base + r * 32 + lane) & ~st;
+        const bool dir = (il & size) == 0;
+        const ckey_t mine = reg[r];
+        const ckey_t other = __shfl_xor_sync(0xffffffffu, mine, st);
+        const bool take_max = (lower == dir);
+        reg[r] = take_max ? (mine > other ? mine : other) : (mine < other ? mine : other);
+      }
     }
   }
 }
 
-// CTA-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
-// Any thread may push() a key that beats the current threshold; the CTA calls
+__device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uint32_t P) {
+  const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
+  const uint32_t nchunks = P / kSortChunk;
+  ckey_t reg[kSortR];
+  // phase 1: every chunk fully sorted (direction alternates with bit 8 of the index)
+  for (uint32_t c = warp; c < nchunks; c += nwarps) {
+    const uint32_t base = c * kSortChunk;
+#pragma unroll
+    for (uint32_t r = 0; r < kSortR; ++r) reg[r] = buf[base + r * 32 + lane];
+    for (uint32_t size = 2; size <= kSortChunk; size <<= 1)
+      sort_chunk_pass(reg, lane, base, size, size >> 1);
+#pragma unroll
+    for (uint32_t r = 0; r < kSortR; ++r) buf[base + r * 32 + lane] = reg[r];
+  }
+  g.sync();
+  for (uint32_t size = 2 * kSortChunk; size <= P; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride >= kSortChunk; stride >>= 1) {
+      for (uint32_t i = g.tid; i < (P >> 1); i += g.nthr) {
+        const uint32_t pos = 2 * i - (i & (stride - 1));
+        const ckey_t a = buf[pos], b2 = buf[pos + stride];
+        const bool dir = ((pos & size) == 0);
+        if ((a < b2) == dir) {
+          buf[pos] = b2;
+          buf[pos + stride] = a;
+        }
+      }
+      g.sync();
+    }
+    for (uint32_t c = warp; c < nchunks; c += nwarps) {
+      const uint32_t base = c * kSortChunk;
+#pragma unroll
+      for (uint32_t r = 0; r < kSortR; ++r) reg[r] = buf[base + r * 32 + lane];
+      sort_chunk_pass(reg, lane, base, size, kSortChunk >> 1);
+#pragma unroll
+      for (uint32_t r = 0; r < kSortR; ++r) buf[base + r * 32 + lane] = reg[r];
+    }
+    g.sync();
+  }
+}
+
+constexpr uint32_t kRankSortMax = 512;  // compact() uses a rank sort up to this many keys
+
+// Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
+// Any thread may push() a key that beats the current threshold; the group calls
 // compact() (collectively) often enough that the buffer cannot overflow: the
 // caller guarantees at most (CAP - k) pushes between two compactions.
 struct TopK {
-  ckey_t* buf;      // shared, CAP entries
+  ckey_t* buf;     // shared, CAP entries
   uint32_t* cnt;   // shared
-  ckey_t* thr;      // shared: k-th best key so far (0 while fewer than k)
+  ckey_t* thr;     // shared: k-th best key so far (0 while fewer than k)
   uint32_t cap;
+  Group g;
 
   __device__ __forceinline__ void init() {
-    if (threadIdx.x == 0) {
+    if (g.tid == 0) {
       *cnt = 0;
       *thr = 0;
     }
@@ -82,67 +171,138 @@ struct TopK {
   }
   // Collective.  Afterwards buf[0..min(n,k)) holds the best keys, descending.
   __device__ __forceinline__ void compact(uint32_t k) {
-    __syncthreads();
+    g.sync();
     uint32_t n = min(*cnt, cap);
-    uint32_t P = next_pow2(n);
-    for (uint32_t i = n + threadIdx.x; i < P; i += blockDim.x) buf[i] = 0;
-    __syncthreads();
-    if (n > 1) bitonic_sort_desc(buf, P);
-    if (threadIdx.x == 0) {
+    if (n <= kRankSortMax) {
+      // small n: rank sort.  Every thread counts how many keys beat its own (all
+      // threads read the same address each step -> shared-memory broadcast) and
+      // scatters the key to that rank in the scratch half of the buffer.  Keys are
+      // unique (the row is part of the key).
+      ckey_t* scratch = buf + (cap >> 1);
+      for (uint32_t i = g.tid; i < n; i += g.nthr) {
+        const ckey_t mine = buf[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) rank += (buf[j] > mine) ? 1u : 0u;
+        scratch[rank] = mine;
+      }
+      g.sync();
+      for (uint32_t i = g.tid; i < n; i += g.nthr) buf[i] = scratch[i];
+      g.sync();
+    } else {
+      uint32_t P = max(next_pow2(n), kSortChunk);  // cap >= kSortChunk
+      for (uint32_t i = n + g.tid; i < P; i += g.nthr) buf[i] = 0;
+      g.sync();
+      block_sort_desc(g, buf, P);
+    }
+    if (g.tid == 0) {
       *cnt = min(n, k);
       *thr = (n >= k && k > 0) ? buf[k - 1] : 0;
     }
-    __syncthreads();
+    g.sync();
   }
 };
 
 constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the partial-list scratch
 
 // Last-CTA merge of the per-CTA sorted candidate lists (shared by the dense and
-// the sparse kernels).  On entry tk holds this CTA's own sorted list and
-// threshold.  Every list is sorted descending, so a list is abandoned at its
-// first key <= threshold; lists advance by `budget` keys per round so the
-// accumulator cannot overflow.  Collective.  Writes the final result:
-// (score desc, row asc), unused slots = (-inf, UINT64_MAX).
+// the sparse kernels).  All G lists (the caller's own included) are read back
+// from the partial-list scratch in L2.  Collective over tk.g.
+//
+//  1. bound: with m = ceil(k/G), S = the first m keys of every list has >= k
+//     members whenever k candidates exist at all, so the k-th largest key of S is
+//     a lower bound T0 of the global k-th best.  S (<= k + G keys) is loaded with
+//     independent L2 loads and T0 found by rank counting.  For k <= G this leaves
+//     ~k survivors out of G*k candidates.
+//  2. rounds: in round r every still-active list exposes its window
+//     [r*b, (r+1)*b) and all window slots are examined in parallel; keys above the
+//     threshold are pushed; a list retires at its first key <= threshold (lists
+//     are sorted) or when exhausted.  b*G <= cap - k, so the accumulator cannot
+//     overflow between compactions.  s_pos[l] = keys list l still offers.
+//  3. emit: (score desc, row asc); unused slots = (-inf, UINT64_MAX).
 __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_pos, uint32_t k,
                                                         const ckey_t* partial,
                                                         const uint32_t* partial_cnt, uint32_t G,
-                                                        uint32_t self, uint64_t row_base,
-                                                        float* out_scores, uint64_t* out_rows,
-                                                        uint32_t* out_n) {
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
-  for (uint32_t l = tid; l < G; l += T) s_pos[l] = 0;
-  __syncthreads();
-  uint32_t budget = (tk.cap - k) / G;
-  if (budget == 0) budget = 1;
-  uint32_t group = (tk.cap - k) / budget;  // lists per compaction: group * budget <= cap - k
-  if (group == 0) group = 1;
-  while (true) {
-    int more = 0;
-    for (uint32_t g0 = 0; g0 < G; g0 += group) {
-      ckey_t thr = *tk.thr;
-      uint32_t g1 = min(G, g0 + group);
-      for (uint32_t l = g0 + tid; l < g1; l += T) {
-        if (l == self) continue;
-        uint32_t len = __ldcg(partial_cnt + l);
-        uint32_t pos = s_pos[l];
-        uint32_t pushed = 0;
-        while (pos < len && pushed < budget) {
-          ckey_t key = __ldcg(partial + (size_t)l * kPartialStride + pos);
-          if (key <= thr) {  // sorted list: nothing further can qualify
-            pos = len;
-            break;
+                                                        uint64_t row_base, float* out_scores,
+                                                        uint64_t* out_rows, uint32_t* out_n,
+                                                        unsigned long long* trace = nullptr) {
+  const uint32_t tid = tk.g.tid, T = tk.g.nthr;
+  for (uint32_t l = tid; l < G; l += T) s_pos[l] = __ldcg(partial_cnt + l);
+  if (tid == 0) {
+    *tk.cnt = 0;
+    *tk.thr = 0;
+  }
+  tk.g.sync();
+  // ---- 1. lower bound from the list heads ----
+  const uint32_t m = (k + G - 1) / G;
+  const uint32_t sn = G * m;  // <= k + G - 1 <= cap / 2
+  ckey_t* S = tk.buf + (tk.cap >> 1);
+  for (uint32_t t = tid; t < sn; t += T) {
+    const uint32_t l = t / m, pos = t - l * m;
+    S[t] = (pos < s_pos[l]) ? __ldcg(partial + (size_t)l * kPartialStride + pos) : 0;
+  }
+  tk.g.sync();
+  for (uint32_t t = tid; t < sn; t += T) {
+    const ckey_t mine = S[t];
+    if (mine == 0) continue;
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < sn; ++j) rank += (S[j] > mine) ? 1u : 0u;
+    if (rank == k - 1) *tk.thr = mine - 1;  // keys >= the k-th largest of S pass "key > thr"
+  }
+  tk.g.sync();
+  // ---- 2. rounds ----
+  uint32_t b = (tk.cap / 2 - k) / G;  // the upper half of buf is scratch for compact()
+  if (b == 0) b = 1;
+  if (b > kPartialStride) b = kPartialStride;
+  constexpr int kMlp = 8;  // independent L2 loads in flight per thread
+  for (uint32_t r = 0;; ++r) {
+    const ckey_t thr = *tk.thr;
+    const uint32_t lo = r * b, total = G * b;
+    bool more = false;
+    for (uint32_t base = 0; base < total; base += T * kMlp) {
+      ckey_t keys[kMlp];
+      bool tail[kMlp];
+#pragma unroll
+      for (int j = 0; j < kMlp; ++j) {
+        const uint32_t t = base + j * T + tid;
+        keys[j] = 0;
+        tail[j] = false;
+        if (t < total) {
+          const uint32_t l = t / b, pos = lo + (t - l * b), len = s_pos[l];
+          if (pos < len) {
+            keys[j] = __ldcg(partial + (size_t)l * kPartialStride + pos);
+            tail[j] = (pos == lo + b - 1) && (pos + 1 < len);
           }
-          tk.push(key);
-          ++pos;
-          ++pushed;
         }
-        s_pos[l] = pos;
-        if (pos < len) more = 1;
       }
-      tk.compact(k);
+#pragma unroll
+      for (int j = 0; j < kMlp; ++j)
+        if (keys[j] > thr) {
+          tk.push(keys[j]);
+          if (tail[j]) more = true;  // window full of winners and the list goes on
+        }
     }
-    if (!__syncthreads_or(more)) break;
+    const bool any_more = tk.g.any(more);
+    if (trace && tid == 0 && r == 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[5]));
+      trace[7] = *tk.cnt;
+    }
+    {
+      // compact() would replace the head bound by the k-th best of what was pushed so
+      // far; both are valid lower bounds, keep the larger one.
+      const ckey_t before = *tk.thr;
+      tk.compact(k);
+      if (tid == 0 && before > *tk.thr) *tk.thr = before;
+      tk.g.sync();
+    }
+    if (trace && tid == 0 && r == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
+    if (!any_more) break;
+    // retire lists whose window ended at or below the (old) threshold, or that are exhausted
+    for (uint32_t l = tid; l < G; l += T) {
+      const uint32_t len = s_pos[l], last = lo + b - 1;
+      if (len == 0) continue;
+      if (last + 1 >= len || __ldcg(partial + (size_t)l * kPartialStride + last) <= thr) s_pos[l] = 0;
+    }
+    tk.g.sync();
   }
   uint32_t n = *tk.cnt;
   for (uint32_t i = tid; i < k; i += T) {

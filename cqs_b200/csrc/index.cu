@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -75,6 +76,7 @@ struct Shard {
   // pinned host mirror for results (sized for the fused output, the largest)
   uint8_t* h_out = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long* d_trace = nullptr;  // development aid (CQS_B200_TRACE=1)
   SparseDev sparse;
 };
 
@@ -123,7 +125,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
   cudaFree(s.d_q_tok); cudaFree(s.d_q_w);
   cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
-  cudaFree(s.d_f_present); cudaFree(s.d_f_n);
+  cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
   if (s.h_query) cudaFreeHost(s.h_query);
   if (s.h_out) cudaFreeHost(s.h_out);
@@ -166,6 +168,10 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaHostAlloc((void**)&s.h_out, kHostOutBytes, cudaHostAllocDefault));
   CK(ix, cudaEventCreate(&s.ev0));
   CK(ix, cudaEventCreate(&s.ev1));
+  if (getenv("CQS_B200_TRACE")) {
+    CK(ix, cudaMalloc((void**)&s.d_trace, sizeof(unsigned long long) * kMaxGrid * 8));
+    CK(ix, cudaMemset(s.d_trace, 0, sizeof(unsigned long long) * kMaxGrid * 8));
+  }
   return 0;
 }
 
@@ -394,6 +400,7 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
   a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
+  a.d_trace = s.d_trace;
   CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
   CK(ix, cudaEventRecord(s.ev1, s.stream));
@@ -483,11 +490,15 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   if (s.n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty index");
   CK(ix, cudaSetDevice(s.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-  // the query must be zero padded to the row stride: stage it through d_query
-  CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
-  CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+  const float* qp = d_query;
+  if (ix->layout.ld != ix->dim) {
+    // the query must be zero padded to the row stride: stage it through d_query
+    CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
+    CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+    qp = s.d_query;
+  }
   ScanArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = s.d_query;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
   a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
@@ -817,5 +828,12 @@ const char* cqs_b200_name(void) { return "B200"; }
 const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }
 uint64_t cqs_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 float cqs_b200_last_kernel_ms(cqs_b200_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
+// development aid, not declared in the public header: copies the trace stamps of shard 0
+int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) {
+  if (!ix || ix->shards.empty() || !ix->shards[0].d_trace) return CQS_B200_ERR_INVALID;
+  cudaSetDevice(ix->shards[0].device);
+  return cudaMemcpy(out, ix->shards[0].d_trace, sizeof(unsigned long long) * n_words,
+                    cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
+}
 
 }  // extern "C"

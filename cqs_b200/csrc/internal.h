@@ -41,6 +41,7 @@ struct ScanArgs {
   float* d_out_scores;      // [k]
   uint64_t* d_out_rows;     // [k]
   uint32_t* d_out_n;        // [1]
+  void* d_trace = nullptr;  // optional [kMaxGrid][8] u64 timestamps (CQS_B200_TRACE=1)
 };
 // Kernel 1+3: single-query streaming scan with the top-k select fused in.
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);

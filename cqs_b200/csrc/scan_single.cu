@@ -7,22 +7,25 @@
 // (src/math.rs:11-28) + BoundedScoreHeap::push (src/search/scoring/
 // candidate.rs:274-318) + into_sorted_vec (:321-329).
 //
-// Shape of the kernel
-//   * one warp owns a whole row at a time: 32 lanes x 16-byte vectors cover
-//     512 contiguous bytes per request, NV requests per row, all issued before
-//     the first FMA (U rows in flight per warp) -> fully coalesced 128-byte
-//     lines, ld.global.nc.L1::no_allocate (data is touched once).
+// Shape of the kernel (one persistent 288-thread CTA per SM)
+//   * warp 0 is the PRODUCER: one elected lane streams the corpus with 1-D TMA
+//     bulk copies (cp.async.bulk.shared.global, 24-32 KB per stage — rows are
+//     contiguous in HBM so a tile of rows is one linear copy) into a 4-5 stage
+//     shared-memory ring guarded by full/empty mbarriers.  ~128 KB in flight
+//     per SM is the measured sweet spot on B200 (tools/bw_probe.cu: 7.4 TB/s
+//     read-only versus 6.9 TB/s for the best register-staged LDG.128 loop).
+//   * warps 1-8 are CONSUMERS: a warp owns whole rows of the stage; 32 lanes x
+//     16-byte LDS cover 512 contiguous bytes (conflict-free), NV per row; the
+//     stage is released as soon as its rows sit in registers.
 //   * the query lives in registers (NV*E floats per lane) for the whole kernel.
 //   * per lane 4 independent fp32 accumulators, then a 5-step shuffle
 //     butterfly: the summation tree is fixed (independent of grid size), error
-//     ~ (NV + 7) ulp-ish, well inside the 1e-5 relative contract.
+//     a few ulp, well inside the 1e-5 relative contract.
 //   * a row whose key beats the CTA's current threshold is appended to a
-//     shared-memory candidate buffer; the CTA re-selects (bitonic sort) only
-//     when the buffer might overflow.  Each CTA emits <= k sorted keys; the
-//     last CTA to finish (atomic ticket) merges the G lists and writes the
+//     shared-memory candidate buffer; the consumers re-select (bitonic sort)
+//     only when the buffer might overflow.  Each CTA emits <= k sorted keys;
+//     the last CTA to finish (atomic ticket) merges the G lists and writes the
 //     final (score desc, row asc) result.  One launch per query.
-//   * persistent grid: one 512-thread CTA per SM, tiles of 16*U rows handed
-//     out round-robin.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -30,9 +33,44 @@
 
 namespace cqs {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr uint32_t kCap = 4096;  // candidate slots per CTA (32 KB)
+constexpr int kWarps = 8;                       // consumer warps
+constexpr int kConsumers = kWarps * 32;
+constexpr int kThreads = kConsumers + 32;       // + producer warp
+constexpr uint32_t kCap = 4096;                 // candidate slots per CTA (32 KB)
+constexpr uint32_t kStageTarget = 24576;        // bytes per pipeline stage (target)
+constexpr uint32_t kInFlight = 131072;          // bytes in flight per SM (target)
+
+// ---- mbarrier / TMA bulk-copy primitives ---------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t cnt) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem)),
+      "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
 
 struct ScanParams {
   const uint8_t* rows;
@@ -48,7 +86,15 @@ struct ScanParams {
   float* out_scores;
   uint64_t* out_rows;
   uint32_t* out_n;
+  unsigned long long* trace;  // optional [grid][8] globaltimer stamps (development aid)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot) do { if (p.trace && ctid == 0) p.trace[blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
 
 template <int MODE>
 struct LaneVec;
@@ -57,10 +103,9 @@ struct LaneVec<0> {  // f32, 4 elems / 16 B
   static constexpr int E = 4;
   static constexpr int BYTES = 16;
   uint32_t r[4];
-  __device__ __forceinline__ void load(const uint8_t* p) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "l"(p));
+  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
   }
   __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
   __device__ __forceinline__ void fma(const float* q, float* acc) const {
@@ -75,10 +120,9 @@ struct LaneVec<1> {  // bf16, 8 elems / 16 B
   static constexpr int E = 8;
   static constexpr int BYTES = 16;
   uint32_t r[4];
-  __device__ __forceinline__ void load(const uint8_t* p) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "l"(p));
+  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
   }
   __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
   __device__ __forceinline__ void fma(const float* q, float* acc) const {
@@ -96,10 +140,9 @@ struct LaneVec<2> {  // bf16, 4 elems / 8 B
   static constexpr int E = 4;
   static constexpr int BYTES = 8;
   uint32_t r[2];
-  __device__ __forceinline__ void load(const uint8_t* p) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                 : "=r"(r[0]), "=r"(r[1])
-                 : "l"(p));
+  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
+    uint2 v = *reinterpret_cast<const uint2*>(p);
+    r[0] = v.x; r[1] = v.y;
   }
   __device__ __forceinline__ void zero() { r[0] = r[1] = 0; }
   __device__ __forceinline__ void fma(const float* q, float* acc) const {
@@ -110,107 +153,201 @@ struct LaneVec<2> {  // bf16, 4 elems / 8 B
   }
 };
 
-template <int MODE, int NV, int U>
+template <int MODE, int NV>
+struct ScanCfg {
+  using V = LaneVec<MODE>;
+  static constexpr uint32_t ROWB = NV * 32 * V::BYTES;  // bytes per (padded) row
+  static constexpr uint32_t U0 = kStageTarget / (kWarps * ROWB);
+  static constexpr uint32_t U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);  // rows per consumer warp per stage
+  static constexpr uint32_t RPS = kWarps * U;                   // rows per stage
+  static constexpr uint32_t STAGE_BYTES = RPS * ROWB;
+  static constexpr uint32_t S0 = kInFlight / STAGE_BYTES;
+  static constexpr uint32_t STAGES = S0 < 2 ? 2 : (S0 > 8 ? 8 : S0);
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + kCap * sizeof(ckey_t);
+};
+
+// SMALLK (k <= 32): every consumer warp keeps its own sorted top-32 in registers
+// (lane i holds the i-th best key); a row that beats the warp's k-th key is
+// inserted with one ballot and one shuffle.  No shared-memory traffic, no
+// barriers and no re-selection stalls while streaming.  Larger k use the
+// CTA-level shared-memory accumulator (TopK).
+template <int MODE, int NV, bool SMALLK>
 __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams p) {
+  using Cfg = ScanCfg<MODE, NV>;
   using V = LaneVec<MODE>;
   constexpr int E = V::E;
+  constexpr int U = Cfg::U;
   constexpr uint32_t kBurst = 1024;                       // max pushes per check interval
-  constexpr uint32_t kCheckEvery = kBurst / (kWarps * U); // iterations between checks
+  constexpr uint32_t kCheckEvery = kBurst / Cfg::RPS;     // tiles between checks
+  static_assert(kCheckEvery >= 1, "stage too large");
   static_assert(kCap >= kMaxK + 2 * kBurst, "candidate buffer too small");
 
-  __shared__ ckey_t s_buf[kCap];
+  extern __shared__ __align__(128) uint8_t smem[];
+  ckey_t* s_buf = reinterpret_cast<ckey_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  __shared__ __align__(8) uint64_t s_full[Cfg::STAGES];
+  __shared__ __align__(8) uint64_t s_empty[Cfg::STAGES];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   __shared__ uint32_t s_last;
   __shared__ uint32_t s_pos[kMaxGrid];
 
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  TopK tk{s_buf, &s_cnt, &s_thr, kCap};
-  tk.init();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t n = p.n_rows;
+  const uint64_t tiles = (n + Cfg::RPS - 1) / Cfg::RPS;
 
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (threadIdx.x < 32) {
+    // ===== producer warp: one lane streams row tiles into the ring =====
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&s_empty[s], ph ^ 1);
+        const uint64_t row0 = tile * Cfg::RPS;
+        const uint64_t rows = (n - row0 < Cfg::RPS) ? (n - row0) : Cfg::RPS;
+        const uint32_t bytes = (uint32_t)(rows * Cfg::ROWB);
+        mbar_expect_tx(&s_full[s], bytes);
+        bulk_g2s(smem + (size_t)s * Cfg::STAGE_BYTES, p.rows + row0 * Cfg::ROWB, bytes, &s_full[s]);
+        if (++s == Cfg::STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const uint32_t ctid = threadIdx.x - 32, warp = ctid >> 5;
+  TopK tk{s_buf, &s_cnt, &s_thr, kCap, Group{ctid, kConsumers, 1}};
+  tk.init();
   float q[NV * E];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int e = 0; e < E; ++e) q[v * E + e] = __ldg(p.query + (v * 32 + lane) * E + e);
-  __syncthreads();
+  tk.g.sync();
+  TRACE(0);
 
-  const uint64_t n = p.n_rows;
-  const uint64_t tiles = (n + (uint64_t)kWarps * U - 1) / ((uint64_t)kWarps * U);
   const uint32_t k = p.k;
   ckey_t thr = 0;
-  uint32_t it = 0;
+  ckey_t slot = 0, wthr = 0;  // SMALLK: this lane's entry of the warp's sorted list / its k-th key
+  uint32_t it = 0, s = 0, ph = 0;
   for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-    const uint64_t row0 = (tile * kWarps + warp) * U;
+    mbar_wait(&s_full[s], ph);
+    const uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES + (size_t)(warp * U) * Cfg::ROWB +
+                        (size_t)lane * V::BYTES;
     V d[U][NV];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (row0 + u < n) {
-        const uint8_t* rp = p.rows + (row0 + u) * p.row_bytes + (size_t)lane * V::BYTES;
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) d[u][v].load(rp + (size_t)v * 32 * V::BYTES);
-      } else {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) d[u][v].zero();
-      }
+      for (int v = 0; v < NV; ++v) d[u][v].load(st + (size_t)u * Cfg::ROWB + (size_t)v * 32 * V::BYTES);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);  // rows are in registers: hand the stage back
+    if (++s == Cfg::STAGES) {
+      s = 0;
+      ph ^= 1;
     }
-    float s[U];
+    const uint64_t row0 = tile * Cfg::RPS + (uint64_t)warp * U;
+    float sc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int v = 0; v < NV; ++v) d[u][v].fma(q + v * E, acc);
-      s[u] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+      sc[u] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
-    float mine = s[0];
+      for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
+    float mine = sc[0];
 #pragma unroll
     for (int u = 1; u < U; ++u)
-      if (lane == u) mine = s[u];
+      if (lane == u) mine = sc[u];
+    ckey_t mykey = 0;
     if (lane < U && row0 + lane < n) {
       const uint64_t r = row0 + lane;
       const uint32_t bits = __float_as_uint(mine);
       bool ok = finite_bits(bits);
       if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
-      if (ok) {
-        ckey_t key = make_key(mine, (uint32_t)r);
-        if (key > thr) tk.push(key);
-      }
+      if (ok) mykey = make_key(mine, (uint32_t)r);
     }
+    if (SMALLK) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const ckey_t key = __shfl_sync(0xffffffffu, mykey, u);
+        if (key > wthr) {  // warp-uniform
+          const uint32_t pos = __popc(__ballot_sync(0xffffffffu, slot > key));
+          const ckey_t up = __shfl_up_sync(0xffffffffu, slot, 1);
+          slot = lane < pos ? slot : (lane == pos ? key : up);
+          wthr = __shfl_sync(0xffffffffu, slot, k - 1);
+        }
+      }
+      continue;
+    }
+    if (mykey > thr) tk.push(mykey);
     if ((it % kCheckEvery) == kCheckEvery - 1) {
-      // thread 0's view of the count may miss pushes of this interval that
+      // consumer 0's view of the count may miss pushes of this interval that
       // are still in flight in other warps (< kBurst), hence the 2*kBurst.
-      int need = 0;
-      if (threadIdx.x == 0) {
+      bool need = false;
+      if (ctid == 0) {
         uint32_t c = s_cnt;
         need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
       }
-      if (__syncthreads_or(need)) {
+      if (tk.g.any(need)) {
         tk.compact(k);
         thr = s_thr;
       }
     }
   }
-  tk.compact(k);
-  const uint32_t mycnt = s_cnt;
-  for (uint32_t i = threadIdx.x; i < mycnt; i += kThreads)
-    p.partial[(size_t)blockIdx.x * kMaxK + i] = s_buf[i];
-  if (threadIdx.x == 0) p.partial_cnt[blockIdx.x] = mycnt;
+  TRACE(1);
+  if (SMALLK) {
+    // combine the 8 warp lists: rank sort of 256 keys straight into the partial list
+    s_buf[ctid] = (lane < k) ? slot : 0;
+    tk.g.sync();
+    const ckey_t mine = s_buf[ctid];
+    if (mine != 0) {
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < kConsumers; ++j) rank += (s_buf[j] > mine) ? 1u : 0u;
+      if (rank < k) {
+        p.partial[(size_t)blockIdx.x * kMaxK + rank] = mine;
+        atomicAdd(&s_cnt, 1u);
+      }
+    }
+    tk.g.sync();
+    TRACE(2);
+    if (ctid == 0) p.partial_cnt[blockIdx.x] = s_cnt;
+  } else {
+    tk.compact(k);
+    TRACE(2);
+    const uint32_t mycnt = s_cnt;
+    for (uint32_t i = ctid; i < mycnt; i += kConsumers)
+      p.partial[(size_t)blockIdx.x * kMaxK + i] = s_buf[i];
+    if (ctid == 0) p.partial_cnt[blockIdx.x] = mycnt;
+  }
   __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  tk.g.sync();
+  if (ctid == 0) {
     uint32_t ticket = atomicAdd(p.done, 1u);
     s_last = (ticket == gridDim.x - 1);
   }
-  __syncthreads();
+  tk.g.sync();
+  TRACE(3);
   if (!s_last) return;
   __threadfence();
-  merge_partials_and_emit(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x, blockIdx.x,
-                          p.row_base, p.out_scores, p.out_rows, p.out_n);
-  if (threadIdx.x == 0) *p.done = 0;
+  merge_partials_and_emit(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x, p.row_base,
+                          p.out_scores, p.out_rows, p.out_n,
+                          p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+  TRACE(4);
+  if (ctid == 0) *p.done = 0;
 }
 
 bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
@@ -240,24 +377,31 @@ bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
 }
 
 template <int MODE, int NV>
-static cudaError_t launch_nv(const ScanParams& p, int grid, cudaStream_t st) {
-  constexpr int U = (NV <= 3) ? 4 : (NV <= 6 ? 2 : 1);
-  scan_topk_kernel<MODE, NV, U><<<grid, kThreads, 0, st>>>(p);
+static cudaError_t launch_nv(const ScanParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = ScanCfg<MODE, NV>;
+  uint64_t tiles = (p.n_rows + Cfg::RPS - 1) / Cfg::RPS;
+  int grid = (int)(tiles < (uint64_t)num_sms ? tiles : (uint64_t)num_sms);
+  if (grid > (int)kMaxGrid) grid = kMaxGrid;
+  auto kern = (p.k <= 32) ? scan_topk_kernel<MODE, NV, true> : scan_topk_kernel<MODE, NV, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, Cfg::SMEM, st>>>(p);
   g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
 template <int MODE>
-static cudaError_t launch_mode(const ScanParams& p, int nv, int grid, cudaStream_t st) {
+static cudaError_t launch_mode(const ScanParams& p, int nv, int num_sms, cudaStream_t st) {
   switch (nv) {
-    case 1: return launch_nv<MODE, 1>(p, grid, st);
-    case 2: return launch_nv<MODE, 2>(p, grid, st);
-    case 3: return launch_nv<MODE, 3>(p, grid, st);
-    case 4: return launch_nv<MODE, 4>(p, grid, st);
-    case 6: return launch_nv<MODE, 6>(p, grid, st);
-    case 8: return launch_nv<MODE, 8>(p, grid, st);
-    case 12: return launch_nv<MODE, 12>(p, grid, st);
-    case 16: return launch_nv<MODE, 16>(p, grid, st);
+    case 1: return launch_nv<MODE, 1>(p, num_sms, st);
+    case 2: return launch_nv<MODE, 2>(p, num_sms, st);
+    case 3: return launch_nv<MODE, 3>(p, num_sms, st);
+    case 4: return launch_nv<MODE, 4>(p, num_sms, st);
+    case 6: return launch_nv<MODE, 6>(p, num_sms, st);
+    case 8: return launch_nv<MODE, 8>(p, num_sms, st);
+    case 12: return launch_nv<MODE, 12>(p, num_sms, st);
+    case 16: return launch_nv<MODE, 16>(p, num_sms, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -279,14 +423,11 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.out_scores = a.d_out_scores;
   p.out_rows = a.d_out_rows;
   p.out_n = a.d_out_n;
-  const int U = (a.layout.nv <= 3) ? 4 : (a.layout.nv <= 6 ? 2 : 1);
-  uint64_t tiles = (a.n_rows + (uint64_t)kWarps * U - 1) / ((uint64_t)kWarps * U);
-  int grid = (int)(tiles < (uint64_t)num_sms ? tiles : (uint64_t)num_sms);
-  if (grid > (int)kMaxGrid) grid = kMaxGrid;
+  p.trace = (unsigned long long*)a.d_trace;
   switch (a.layout.mode) {
-    case 0: return launch_mode<0>(p, a.layout.nv, grid, st);
-    case 1: return launch_mode<1>(p, a.layout.nv, grid, st);
-    case 2: return launch_mode<2>(p, a.layout.nv, grid, st);
+    case 0: return launch_mode<0>(p, a.layout.nv, num_sms, st);
+    case 1: return launch_mode<1>(p, a.layout.nv, num_sms, st);
+    case 2: return launch_mode<2>(p, a.layout.nv, num_sms, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -332,7 +473,7 @@ __device__ __forceinline__ bool cand_before(const Cand& a, const Cand& b) {
 }
 constexpr uint32_t kMergeCap = 8192;
 __global__ void __launch_bounds__(512) merge_topk_kernel(const MergeArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   uint32_t* s_s = (uint32_t*)smem;                       // [P]
   uint64_t* s_r = (uint64_t*)(smem + sizeof(uint32_t) * kMergeCap);  // [P]
   const uint32_t qi = blockIdx.x, tid = threadIdx.x, T = blockDim.x;

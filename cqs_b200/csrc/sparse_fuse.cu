@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_search_kernel(const Spar
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpSmem& s = *reinterpret_cast<SpSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
-  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap};
+  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{threadIdx.x, kSpThreads, 0}};
   tk.init();
   __syncthreads();
   const uint32_t k = p.k;
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_search_kernel(const Spar
   __syncthreads();
   if (!s.last) return;
   __threadfence();
-  merge_partials_and_emit(tk, s.pos, k, p.partial, p.partial_cnt, gridDim.x, blockIdx.x,
-                             p.row_base, p.out_scores, p.out_rows, p.out_n);
+  merge_partials_and_emit(tk, s.pos, k, p.partial, p.partial_cnt, gridDim.x, p.row_base,
+                          p.out_scores, p.out_rows, p.out_n);
   if (tid == 0) *p.done = 0;
 }
 
