@@ -145,8 +145,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
                        cudaHostAllocDefault));
   CK(ix, cudaMalloc((void**)&s.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
-  CK(ix, cudaMalloc((void**)&s.d_done, sizeof(uint32_t)));
-  CK(ix, cudaMemset(s.d_done, 0, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_done, 4 * sizeof(uint32_t)));
+  CK(ix, cudaMemset(s.d_done, 0, 4 * sizeof(uint32_t)));
   CK(ix, cudaMalloc((void**)&s.d_out_scores, sizeof(float) * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_out_rows, sizeof(uint64_t) * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_out_n, sizeof(uint32_t)));

@@ -37,7 +37,7 @@ struct ScanArgs {
   uint64_t row_base;        // added to local rows in the output
   ckey_t* d_partial;         // [kMaxGrid][kMaxK] scratch
   uint32_t* d_partial_cnt;  // [kMaxGrid]
-  uint32_t* d_done;         // [1], zero between launches
+  uint32_t* d_done;         // [2]: CTA ticket + tile counter, zero between launches
   float* d_out_scores;      // [k]
   uint64_t* d_out_rows;     // [k]
   uint32_t* d_out_n;        // [1]
