@@ -77,6 +77,15 @@ struct Shard {
   uint8_t* h_out = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long* d_trace = nullptr;  // development aid (CQS_B200_TRACE=1)
+  // batched tensor-core path (bf16 storage), allocated on first use
+  float* d_bq = nullptr;          // [kBatchMaxQ][ld] padded f32 queries
+  void* d_bscratch = nullptr;
+  float* d_bout_scores = nullptr; // [kBatchMaxQ][kMaxK]
+  uint64_t* d_bout_rows = nullptr;
+  uint32_t* d_bout_n = nullptr;   // [kBatchMaxQ]
+  uint32_t* d_bflags = nullptr;   // [kBatchMaxQ]
+  float* d_maxnorm = nullptr;     // [1]
+  float max_row_norm = 0.f;
   SparseDev sparse;
 };
 
@@ -96,6 +105,7 @@ struct cqs_b200_index {
   uint64_t row_base = 0;
   uint64_t n_rows = 0, reserved = 0, rows_per_shard = 0;
   float last_kernel_ms = 0.f;
+  uint32_t last_batch_reruns = 0;  // queries the batched path sent to the exact kernel (cumulative)
   std::vector<Shard> shards;
 };
 
@@ -126,6 +136,8 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_q_tok); cudaFree(s.d_q_w);
   cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
+  cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
+  cudaFree(s.d_bout_n); cudaFree(s.d_bflags); cudaFree(s.d_maxnorm);
   cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
   if (s.h_query) cudaFreeHost(s.h_query);
   if (s.h_out) cudaFreeHost(s.h_out);
@@ -293,6 +305,9 @@ static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, b
     uint64_t take = std::min<uint64_t>(n_rows - done, room);
     if (local + take > 0xFFFFFFFFull) return fail(CQS_B200_ERR_INVALID, "more than 2^32-1 rows per device");
     CK(ix, cudaSetDevice(s.device));
+    // a device-side source may still be being produced on another stream of the
+    // caller (e.g. a framework's default stream): the build path simply waits.
+    if (on_device) CK(ix, cudaDeviceSynchronize());
     int rc = grow_shard(ix, s, local + take);
     if (rc) return rc;
     const float* src = rows + done * ix->dim;
@@ -347,6 +362,13 @@ int cqs_b200_finalize(cqs_b200_index* ix) {
       s.d_bitset = nullptr;
       CK(ix, cudaMalloc((void**)&s.d_bitset, std::max<uint64_t>(words, 1) * 4));
       s.bitset_words = words;
+    }
+    if (ix->layout.mode != 0 && s.n_rows) {
+      // exactness bound of the batched tensor-core path needs max |row|
+      if (!s.d_maxnorm) CK(ix, cudaMalloc((void**)&s.d_maxnorm, sizeof(float)));
+      CK(ix, launch_max_row_norm(s.d_rows, s.n_rows, ix->layout, s.d_maxnorm, s.stream));
+      CK(ix, cudaMemcpyAsync(&s.max_row_norm, s.d_maxnorm, sizeof(float), cudaMemcpyDeviceToHost,
+                             s.stream));
     }
     CK(ix, cudaStreamSynchronize(s.stream));
   }
@@ -521,16 +543,94 @@ int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t
   return CQS_B200_OK;
 }
 
+// Tensor-core path for one chunk of <= kBatchMaxQ queries on a single-device bf16 index.
+static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
+                           const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                           uint32_t* out_n, std::vector<uint32_t>* rerun) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  const uint32_t ld = ix->layout.ld;
+  if (!s.d_bq) {
+    CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
+    CK(ix, cudaMalloc(&s.d_bscratch, batch_scratch_bytes(kBatchMaxQ, ld)));
+    CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
+    CK(ix, cudaMalloc((void**)&s.d_bflags, sizeof(uint32_t) * kBatchMaxQ));
+  }
+  // pad queries to the row stride; a non-finite query yields an empty result
+  // (src/cagra.rs:458-470): it is scanned as a zero vector and blanked afterwards
+  std::vector<float> padded((size_t)nq * ld, 0.f);
+  std::vector<uint8_t> bad(nq, 0);
+  for (uint32_t i = 0; i < nq; ++i) {
+    const float* q = queries + (size_t)i * ix->dim;
+    if (query_is_finite(q, ix->dim)) memcpy(&padded[(size_t)i * ld], q, sizeof(float) * ix->dim);
+    else bad[i] = 1;
+  }
+  CK(ix, cudaMemcpyAsync(s.d_bq, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, s.stream));
+  const uint32_t* d_bits = nullptr;
+  if (bitset) {
+    CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
+    d_bits = s.d_bitset;
+  }
+  BatchArgs a;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_queries = s.d_bq; a.nq = nq;
+  a.k = k; a.d_bitset = d_bits; a.row_base = ix->row_base + s.first_row;
+  a.max_row_norm = s.max_row_norm; a.d_scratch = s.d_bscratch;
+  a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
+  a.d_flags = s.d_bflags;
+  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  CK(ix, launch_scan_batch(a, s.num_sms, s.stream));
+  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  std::vector<uint32_t> flags(nq), ns(nq);
+  CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(out_rows, s.d_bout_rows, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(ns.data(), s.d_bout_n, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(flags.data(), s.d_bflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaStreamSynchronize(s.stream));
+  CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  for (uint32_t i = 0; i < nq; ++i) {
+    out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
+    if (flags[i] && !bad[i]) rerun->push_back(i);
+  }
+  return CQS_B200_OK;
+}
+
 int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
                           const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
                           uint32_t* out_n) {
-  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  int rc = check_searchable(ix);
+  if (rc) return rc;
   if (nq && (!queries || !out_rows || !out_scores || !out_n))
     return fail(CQS_B200_ERR_INVALID, "NULL argument");
-  for (uint32_t i = 0; i < nq; ++i) {
-    int rc = cqs_b200_search(ix, queries + (size_t)i * ix->dim, k, bitset,
-                             out_rows + (size_t)i * k, out_scores + (size_t)i * k, out_n + i);
+  if (k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u exceeds max_k=%u", k, kMaxK);
+  for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
+  if (k == 0 || ix->n_rows == 0 || nq == 0) return CQS_B200_OK;
+  const bool tensor_path = ix->storage == CQS_B200_STORAGE_BF16 && ix->shards.size() == 1 &&
+                           nq >= 8 && ix->n_rows < (1ull << 31);
+  if (!tensor_path) {
+    for (uint32_t i = 0; i < nq; ++i) {
+      rc = cqs_b200_search(ix, queries + (size_t)i * ix->dim, k, bitset, out_rows + (size_t)i * k,
+                           out_scores + (size_t)i * k, out_n + i);
+      if (rc) return rc;
+    }
+    return CQS_B200_OK;
+  }
+  for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
+    const uint32_t m = std::min(kBatchMaxQ, nq - q0);
+    std::vector<uint32_t> rerun;
+    rc = search_batch_tc(ix, queries + (size_t)q0 * ix->dim, m, k, bitset, out_rows + (size_t)q0 * k,
+                         out_scores + (size_t)q0 * k, out_n + q0, &rerun);
     if (rc) return rc;
+    // queries whose candidate pool could not be proven complete: exact single-query scan
+    for (uint32_t i : rerun) {
+      rc = cqs_b200_search(ix, queries + (size_t)(q0 + i) * ix->dim, k, bitset,
+                           out_rows + (size_t)(q0 + i) * k, out_scores + (size_t)(q0 + i) * k,
+                           out_n + q0 + i);
+      if (rc) return rc;
+    }
+    ix->last_batch_reruns += (uint32_t)rerun.size();
   }
   return CQS_B200_OK;
 }
@@ -828,7 +928,15 @@ const char* cqs_b200_name(void) { return "B200"; }
 const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }
 uint64_t cqs_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 float cqs_b200_last_kernel_ms(cqs_b200_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
-// development aid, not declared in the public header: copies the trace stamps of shard 0
+// development aids, not declared in the public header
+uint32_t cqs_b200_debug_batch_reruns(cqs_b200_index* ix) { return ix ? ix->last_batch_reruns : 0; }
+int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) {
+  if (!ix || ix->shards.empty() || !ix->shards[0].d_bflags) return CQS_B200_ERR_INVALID;
+  cudaSetDevice(ix->shards[0].device);
+  return cudaMemcpy(out, ix->shards[0].d_bflags, 4 * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
+}
+float cqs_b200_debug_max_row_norm(cqs_b200_index* ix) { return ix && !ix->shards.empty() ? ix->shards[0].max_row_norm : -1.f; }
+// copies the trace stamps of shard 0
 int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) {
   if (!ix || ix->shards.empty() || !ix->shards[0].d_trace) return CQS_B200_ERR_INVALID;
   cudaSetDevice(ix->shards[0].device);

@@ -60,6 +60,32 @@ struct MergeArgs {
 };
 cudaError_t launch_merge_topk(const MergeArgs& a, cudaStream_t stream);
 
+// ---- batched tensor-core scan (kernel 2) ----
+constexpr uint32_t kBatchMaxQ = 1024;        // queries per launch_scan_batch call
+constexpr uint32_t kBatchCap = 20480;        // candidate slots per query pool
+constexpr uint32_t kBatchDenseRows = 18944;  // round 0 (74 chunks of 256 rows)
+struct BatchArgs {
+  const void* d_rows;        // bf16 [n_rows][ld]
+  uint64_t n_rows;           // < 2^31
+  RowLayout layout;          // mode 1 or 2 (bf16)
+  const float* d_queries;    // f32 [nq][ld], zero padded beyond dim
+  uint32_t nq;               // <= kBatchMaxQ
+  uint32_t k;
+  const uint32_t* d_bitset;  // nullable
+  uint64_t row_base;
+  float max_row_norm;        // max L2 norm over the corpus rows (exactness bound)
+  void* d_scratch;           // batch_scratch_bytes(round_up(nq,128), ld)
+  float* d_out_scores;       // [nq][k]
+  uint64_t* d_out_rows;      // [nq][k]
+  uint32_t* d_out_n;         // [nq]
+  uint32_t* d_flags;         // [nq]: 1 = not provably exact, caller re-runs the exact scan
+};
+size_t batch_scratch_bytes(uint32_t nq_pad, uint32_t ld);
+uint32_t batch_kprime(uint32_t k);
+cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_max_row_norm(const void* d_rows, uint64_t n_rows, RowLayout layout, float* d_out,
+                                cudaStream_t stream);
+
 // ---- sparse (SPLADE) ----
 struct SparseDev {
   // token-major postings (CSC): for token t, entries [tptr[t], tptr[t+1]) sorted by doc asc

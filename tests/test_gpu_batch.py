@@ -1,0 +1,117 @@
+"""GPU parity: batched tensor-core scan (kernel 2: tcgen05 + TMA + TMEM epilogue)
+with exact re-scoring.  Contract: results identical to nq single-query searches
+(which are themselves checked against the oracle in test_gpu_dense.py)."""
+import numpy as np
+import pytest
+
+from oracle import cqs_oracle as O
+from tests.parity import assert_topk_parity, bits
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def cqs():
+    import cqs_b200
+    return cqs_b200
+
+
+def _build(cqs, rows, storage="bf16"):
+    ix = cqs.B200Index(rows.shape[1], storage=storage)
+    ix.append(None, rows)
+    ix.finalize()
+    return ix
+
+
+def _check_batch_equals_single(ix, queries, k, bitset=None):
+    r, s, n = ix.search_batch_rows(queries, k, bitset)
+    for i in range(queries.shape[0]):
+        a, b = ix.search_rows(queries[i], k, bitset)
+        assert n[i] == a.shape[0], (i, n[i], a.shape[0])
+        assert np.array_equal(r[i, :n[i]], a), f"query {i}: ids differ from the single-query path"
+        assert np.array_equal(bits(s[i, :n[i]]), bits(b)), f"query {i}: score bits differ"
+    return r, s, n
+
+
+@pytest.mark.parametrize("n,nq,k", [(3000, 130, 20), (300, 9, 20), (18944, 128, 20), (19000, 64, 7)])
+def test_batch_small_dense_round_only(cqs, n, nq, k):
+    rows = O.fast_unit_rows(n, 768, seed=n)
+    ix = _build(cqs, rows)
+    q = O.fast_unit_rows(nq, 768, seed=n + 1)
+    _check_batch_equals_single(ix, q, k)
+    ix.close()
+
+
+def test_batch_multi_round_200k_and_oracle(cqs):
+    n, nq = 200_000, 256
+    rows = O.fast_unit_rows(n, 768, seed=31)
+    ix = _build(cqs, rows)
+    q = O.fast_unit_rows(nq, 768, seed=32)
+    q[:16] = rows[1000:1016]                       # self matches
+    for k in (20, 100):
+        r, s, nn = _check_batch_equals_single(ix, q, k)
+    corpus = O.bf16_to_f32(O.f32_to_bf16_rne(rows))
+    for i in (0, 5, 100, 255):                      # and against the f64 oracle directly
+        full = O.dense_scores(corpus, q[i])
+        o_rows, o_sc = O.topk_rows(full, 100)
+        assert_topk_parity(r[i], s[i], o_rows, o_sc, full)
+    mask = np.random.default_rng(3).random(n) < 0.3
+    _check_batch_equals_single(ix, q[:64], 20, O.mask_to_bitset(mask))
+    from cqs_b200.capi import lib
+    import ctypes as C
+    lib.cqs_b200_debug_batch_reruns.restype = C.c_uint32
+    lib.cqs_b200_debug_batch_reruns.argtypes = [C.c_void_p]
+    # random unit vectors: (almost) every query must be served by the tensor-core path itself
+    assert lib.cqs_b200_debug_batch_reruns(ix._h) <= 8
+    ix.close()
+
+
+def test_batch_near_duplicates_force_exact_fallback_still_identical(cqs):
+    """300 near-identical rows tie within bf16 rounding: the k' pool cannot be proven
+    complete, the library must fall back to the exact kernel and still be identical."""
+    rng = np.random.default_rng(5)
+    rows = O.fast_unit_rows(40_000, 768, seed=41)
+    base = rows[7].copy()
+    for j in range(300):
+        v = base + rng.standard_normal(768).astype(f32) * f32(2e-5)
+        rows[100 + j * 100] = v / np.linalg.norm(v)
+    ix = _build(cqs, rows)
+    q = O.fast_unit_rows(32, 768, seed=42)
+    q[0] = base
+    q[1] = rows[100]
+    _check_batch_equals_single(ix, q, 20)
+    ix.close()
+
+
+def test_batch_edge_cases(cqs):
+    rows = O.fast_unit_rows(5000, 768, seed=51)
+    ix = _build(cqs, rows)
+    q = O.fast_unit_rows(16, 768, seed=52)
+    q[3, 10] = np.nan                                  # malformed query inside a batch -> empty
+    r, s, n = ix.search_batch_rows(q, 20)
+    assert n[3] == 0 and all(n[i] == 20 for i in range(16) if i != 3)
+    r, s, n = ix.search_batch_rows(q[:4], 20)           # nq < 8 -> single-query loop
+    assert n[0] == 20 and n[3] == 0
+    r, s, n = ix.search_batch_rows(q, 0)                # k = 0
+    assert (n == 0).all()
+    none = np.zeros(5000, bool)
+    r, s, n = ix.search_batch_rows(q, 20, O.mask_to_bitset(none))
+    assert (n == 0).all()
+    few = np.zeros(5000, bool); few[[5, 77, 4000]] = True
+    r, s, n = ix.search_batch_rows(q, 20, O.mask_to_bitset(few))
+    assert all(n[i] == 3 for i in range(16) if i != 3)
+    assert set(r[0, :3].tolist()) == {5, 77, 4000}
+    ix.close()
+    ix32 = _build(cqs, rows, storage="f32")             # f32 storage: loop of exact scans
+    _check_batch_equals_single(ix32, q[:3].copy(), 20)
+    ix32.close()
+
+
+def test_batch_other_dims(cqs):
+    for dim in (1024, 384, 128):
+        rows = O.fast_unit_rows(30_000, dim, seed=dim)
+        ix = _build(cqs, rows)
+        q = O.fast_unit_rows(40, dim, seed=dim + 1)
+        _check_batch_equals_single(ix, q, 20)
+        ix.close()
