@@ -106,6 +106,7 @@ struct cqs_b200_index {
   uint64_t n_rows = 0, reserved = 0, rows_per_shard = 0;
   float last_kernel_ms = 0.f;
   uint32_t last_batch_reruns = 0;  // queries the batched path sent to the exact kernel (cumulative)
+  float last_batch_ms = 0.f;       // device time of the most recent tensor-core batch pipeline
   std::vector<Shard> shards;
 };
 
@@ -590,6 +591,7 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   CK(ix, cudaMemcpyAsync(flags.data(), s.d_bflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaStreamSynchronize(s.stream));
   CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  ix->last_batch_ms = ix->last_kernel_ms;
   for (uint32_t i = 0; i < nq; ++i) {
     out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
     if (flags[i] && !bad[i]) rerun->push_back(i);
@@ -935,6 +937,7 @@ int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) {
   cudaSetDevice(ix->shards[0].device);
   return cudaMemcpy(out, ix->shards[0].d_bflags, 4 * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
 }
+float cqs_b200_debug_last_batch_ms(cqs_b200_index* ix) { return ix ? ix->last_batch_ms : 0.f; }
 float cqs_b200_debug_max_row_norm(cqs_b200_index* ix) { return ix && !ix->shards.empty() ? ix->shards[0].max_row_norm : -1.f; }
 // copies the trace stamps of shard 0
 int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) {

@@ -140,7 +140,14 @@ struct BatchParams {
   uint32_t* cnt;          // [nq_pad]
   uint32_t* overflow;     // [nq_pad]
   uint32_t cap;
+  // sparse rounds: candidates go to per-(query, CTA) sub-pools so that no global
+  // atomic sits on the epilogue's path (a query is owned by exactly one thread of a CTA)
+  ckey_t* sub;            // [nq_pad][grid][kSub]
+  uint8_t* subcnt;        // [grid][nq_pad]
+  uint32_t nq_pad;
 };
+constexpr uint32_t kSub = 64;        // slots per (query, CTA) sub-pool and round
+constexpr uint32_t kMaxGridB = 160;  // sub-pool stride bound (SMs)
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
 // 4..7 = epilogue (warp % 4 selects the TMEM lane quarter = 32 queries).
@@ -154,8 +161,10 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   __shared__ __align__(8) uint64_t s_tfull[kAccStages], s_tempty[kAccStages];
   __shared__ uint32_t s_tmem_base;
+  __shared__ uint8_t s_subcnt[kBatchMaxQ];
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < kBatchMaxQ; i += kBatchThreads) s_subcnt[i] = 0;
   const uint64_t n_chunks = (p.row_end - p.row_begin + kBN - 1) / kBN;
   const uint64_t n_items = n_chunks * p.n_qt;
 
@@ -255,6 +264,8 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kBN;
       ckey_t* my_cand = p.cand + (size_t)q * p.cap;
+      ckey_t* my_sub = p.sub + ((size_t)q * gridDim.x + blockIdx.x) * kSub;
+      uint32_t my_cnt = active ? s_subcnt[q] : 0;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < kBN; c0 += 32) {
         uint32_t v[32];
@@ -286,13 +297,13 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               bool ok = key > thr_key;
               if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
               if (ok) {
-                const uint32_t slot = atomicAdd(p.cnt + q, 1u);
-                if (slot < p.cap) my_cand[slot] = key; else p.overflow[q] = 1;
+                if (my_cnt < kSub) my_sub[my_cnt++] = key; else p.overflow[q] = 1;
               }
             }
           }
         }
       }
+      if (active) s_subcnt[q] = (uint8_t)my_cnt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
@@ -300,6 +311,13 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         acc = 0;
         aph ^= 1;
       }
+    }
+  }
+  if (warp >= 4 && !p.dense) {
+    // publish this CTA's sub-pool fill levels (each thread owns its queries)
+    for (uint32_t qt = 0; qt < p.n_qt; ++qt) {
+      const uint32_t q = qt * kBM + (warp & 3) * 32 + lane;
+      p.subcnt[(size_t)blockIdx.x * p.nq_pad + q] = s_subcnt[q];
     }
   }
   tc_fence_before();
@@ -344,7 +362,9 @@ constexpr uint32_t kUpdThreads = 256;
 constexpr uint32_t kUpdCap = 4096;
 __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, uint32_t* cnt,
                                                                  ckey_t* thr, uint32_t cap,
-                                                                 uint32_t kprime) {
+                                                                 uint32_t kprime, const ckey_t* sub,
+                                                                 const uint8_t* subcnt,
+                                                                 uint32_t sub_grid, uint32_t nq_pad) {
   __shared__ ckey_t s_buf[kUpdCap];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
@@ -361,6 +381,20 @@ __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, u
     for (uint32_t i = base + tid; i < end; i += kUpdThreads) {
       const ckey_t key = pool[i];
       if (key > t) tk.push(key);
+    }
+    tk.compact(kprime);
+  }
+  // this round's sub-pools, `per` of them between compactions (per * kSub <= step)
+  const uint32_t per = step / kSub;
+  for (uint32_t c0 = 0; c0 < sub_grid; c0 += per) {
+    const ckey_t t = s_thr;
+    const uint32_t c1 = min(sub_grid, c0 + per);
+    for (uint32_t i = tid; i < (c1 - c0) * kSub; i += kUpdThreads) {
+      const uint32_t c = c0 + i / kSub, j = i % kSub;
+      if (j < subcnt[(size_t)c * nq_pad + q]) {
+        const ckey_t key = sub[((size_t)q * sub_grid + c) * kSub + j];
+        if (key > t) tk.push(key);
+      }
     }
     tk.compact(kprime);
   }
@@ -544,6 +578,8 @@ size_t batch_scratch_bytes(uint32_t nq_pad, uint32_t ld) {
   b += (size_t)nq_pad * ld * 2;                 // bf16 queries
   b += (size_t)nq_pad * kBatchCap * 8;          // candidate pools
   b += (size_t)nq_pad * (8 + 4 + 4 + 4 + 4);    // thr, cnt, overflow, qnorm, flags
+  b += (size_t)nq_pad * kMaxGridB * kSub * 8;   // sub-pools
+  b += (size_t)nq_pad * kMaxGridB;              // sub-pool fill levels
   return b + 4096;
 }
 
@@ -567,6 +603,12 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   uint32_t* overflow = (uint32_t*)base;
   base += (size_t)nq_pad * 4;
   float* qnorm = (float*)base;
+  base += (size_t)nq_pad * 4;
+  base = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+  ckey_t* sub = (ckey_t*)base;
+  base += (size_t)nq_pad * kMaxGridB * kSub * 8;
+  uint8_t* subcnt = base;
+  if (num_sms > (int)kMaxGridB) num_sms = kMaxGridB;
 
   CUtensorMap tmQ, tmR;
   if (!make_tmap(&tmQ, q16, nq_pad, ld, kBM) || !make_tmap(&tmR, a.d_rows, a.n_rows, ld, kBN))
@@ -590,6 +632,9 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   p.cnt = cnt;
   p.overflow = overflow;
   p.cap = kBatchCap;
+  p.sub = sub;
+  p.subcnt = subcnt;
+  p.nq_pad = nq_pad;
   uint64_t begin = 0, end = r0;
   int round = 0;
   while (begin < a.n_rows) {
@@ -599,7 +644,8 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
     const uint64_t items = ((end - begin + kBN - 1) / kBN) * p.n_qt;
     const int grid = (int)(items < (uint64_t)num_sms ? items : (uint64_t)num_sms);
     scan_batch_kernel<<<grid, kBatchThreads, kBatchSmem, st>>>(tmQ, tmR, p);
-    update_thr_kernel<<<nq_pad, kUpdThreads, 0, st>>>(cand, cnt, thr, kBatchCap, kprime);
+    update_thr_kernel<<<nq_pad, kUpdThreads, 0, st>>>(cand, cnt, thr, kBatchCap, kprime, sub, subcnt,
+                                                      p.dense ? 0u : (uint32_t)grid, nq_pad);
     launches += 2;
     begin = end;
     end = (end * 9 < a.n_rows) ? end * 9 : a.n_rows;

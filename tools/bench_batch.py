@@ -24,11 +24,13 @@ rng = np.random.default_rng(0)
 q = rng.standard_normal((nq, 768)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
 lib.cqs_b200_debug_batch_reruns.restype = C.c_uint32
 lib.cqs_b200_debug_batch_reruns.argtypes = [C.c_void_p]
+lib.cqs_b200_debug_last_batch_ms.restype = C.c_float
+lib.cqs_b200_debug_last_batch_ms.argtypes = [C.c_void_p]
 for it in range(4):
     t0 = time.perf_counter()
     r, s, nn = ix.search_batch_rows(q, k)
     dt = time.perf_counter() - t0
-    kms = ix.last_kernel_ms()
+    kms = lib.cqs_b200_debug_last_batch_ms(ix._h)
     flops = 2.0 * nq * n * 768
     print(f"iter {it}: e2e {dt*1e3:8.2f} ms ({nq/dt:9.0f} q/s)  device {kms:8.2f} ms ({nq/kms*1e3:9.0f} q/s, "
           f"{flops/kms/1e9:7.1f} TFLOP/s)  reruns so far {lib.cqs_b200_debug_batch_reruns(ix._h)}")
