@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcqs_b200.so")
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_POISONED, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 METRIC_COSINE, METRIC_DOT = 0, 1
-STORAGE_F32, STORAGE_BF16 = 0, 1
+STORAGE_F32, STORAGE_BF16, STORAGE_BF16_F32 = 0, 1, 2
 MAX_K = 1024
 
 u64p, u32p, f32p, u8p, i32p = (C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_float),

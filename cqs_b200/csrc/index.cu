@@ -42,6 +42,7 @@ struct Shard {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   uint8_t* d_rows = nullptr;
+  uint8_t* d_rows16 = nullptr;  // STORAGE_BF16_F32: bf16 shadow of the f32 master rows
   uint64_t n_rows = 0, cap_rows = 0;
   uint64_t first_row = 0;  // offset of this shard's row 0 inside the index
   float* d_stage = nullptr;  // staging for row ingest
@@ -98,7 +99,8 @@ constexpr size_t kHostOutBytes = kMaxK * (8 + 4 + 4 + 4 + 1) + 64;
 struct cqs_b200_index {
   std::mutex mu;
   uint32_t dim = 0;
-  RowLayout layout{};
+  RowLayout layout{};    // master rows (what single-query scans read)
+  RowLayout layout16{};  // bf16 shadow (STORAGE_BF16_F32 only)
   int metric = 0, storage = 0;
   bool finalized = false;
   std::atomic<int> poisoned{0};
@@ -129,7 +131,7 @@ static size_t row_bytes(const cqs_b200_index* ix) {
 static void free_shard(Shard& s) {
   cudaSetDevice(s.device);
   if (s.stream) cudaStreamSynchronize(s.stream);
-  cudaFree(s.d_rows); cudaFree(s.d_stage); cudaFree(s.d_query); cudaFree(s.d_bitset);
+  cudaFree(s.d_rows); cudaFree(s.d_rows16); cudaFree(s.d_stage); cudaFree(s.d_query); cudaFree(s.d_bitset);
   cudaFree(s.d_partial); cudaFree(s.d_partial_cnt); cudaFree(s.d_done);
   cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
   cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
@@ -197,9 +199,17 @@ static int grow_shard(cqs_b200_index* ix, Shard& s, uint64_t want_rows) {
   size_t rb = row_bytes(ix);
   CK(ix, cudaMalloc((void**)&nd, cap * rb));
   if (s.n_rows) CK(ix, cudaMemcpyAsync(nd, s.d_rows, s.n_rows * rb, cudaMemcpyDeviceToDevice, s.stream));
+  uint8_t* nd16 = nullptr;
+  if (ix->storage == CQS_B200_STORAGE_BF16_F32) {
+    const size_t rb16 = (size_t)ix->layout16.ld * 2;
+    CK(ix, cudaMalloc((void**)&nd16, cap * rb16));
+    if (s.n_rows) CK(ix, cudaMemcpyAsync(nd16, s.d_rows16, s.n_rows * rb16, cudaMemcpyDeviceToDevice, s.stream));
+  }
   CK(ix, cudaStreamSynchronize(s.stream));
   cudaFree(s.d_rows);
+  cudaFree(s.d_rows16);
   s.d_rows = nd;
+  s.d_rows16 = nd16;
   s.cap_rows = cap;
   return 0;
 }
@@ -213,11 +223,14 @@ int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, 
   if (n_dev < 1 || n_dev > 64) return fail(CQS_B200_ERR_INVALID, "n_dev must be in 1..64");
   if (metric != CQS_B200_METRIC_COSINE && metric != CQS_B200_METRIC_DOT)
     return fail(CQS_B200_ERR_INVALID, "unknown metric %d", metric);
-  if (storage != CQS_B200_STORAGE_F32 && storage != CQS_B200_STORAGE_BF16)
+  if (storage != CQS_B200_STORAGE_F32 && storage != CQS_B200_STORAGE_BF16 &&
+      storage != CQS_B200_STORAGE_BF16_F32)
     return fail(CQS_B200_ERR_INVALID, "unknown storage %d", storage);
-  RowLayout lay;
-  if (!choose_layout(dim, storage, &lay))
+  RowLayout lay, lay16{};
+  if (!choose_layout(dim, storage == CQS_B200_STORAGE_BF16 ? 1 : 0, &lay))
     return fail(CQS_B200_ERR_INVALID, "unsupported dim %u (1..2048)", dim);
+  if (storage == CQS_B200_STORAGE_BF16_F32 && (!choose_layout(dim, 1, &lay16) || lay16.ld != lay.ld))
+    return fail(CQS_B200_ERR_UNSUPPORTED, "no common row stride for dim %u", dim);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -229,6 +242,7 @@ int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, 
   if (!ix) return fail(CQS_B200_ERR_OOM, "host allocation failed");
   ix->dim = dim;
   ix->layout = lay;
+  ix->layout16 = lay16;
   ix->metric = metric;
   ix->storage = storage;
   ix->shards.resize(n_dev);
@@ -312,11 +326,13 @@ static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, b
     int rc = grow_shard(ix, s, local + take);
     if (rc) return rc;
     const float* src = rows + done * ix->dim;
-    if (direct) {
+    const bool shadow = ix->storage == CQS_B200_STORAGE_BF16_F32;
+    if (direct && !shadow) {
       CK(ix, cudaMemcpyAsync(s.d_rows + local * rb, src, take * rb,
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s.stream));
     } else if (on_device) {
       CK(ix, launch_convert_rows(src, ix->dim, take, s.d_rows, local, ix->layout, s.stream));
+      if (shadow) CK(ix, launch_convert_rows(src, ix->dim, take, s.d_rows16, local, ix->layout16, s.stream));
     } else {
       const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / (sizeof(float) * ix->dim));
       if (s.stage_rows < std::min(chunk, take)) {
@@ -330,6 +346,8 @@ static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, b
         CK(ix, cudaMemcpyAsync(s.d_stage, src + c * ix->dim, m * sizeof(float) * ix->dim,
                                cudaMemcpyHostToDevice, s.stream));
         CK(ix, launch_convert_rows(s.d_stage, ix->dim, m, s.d_rows, local + c, ix->layout, s.stream));
+        if (shadow)
+          CK(ix, launch_convert_rows(s.d_stage, ix->dim, m, s.d_rows16, local + c, ix->layout16, s.stream));
         CK(ix, cudaStreamSynchronize(s.stream));
       }
     }
@@ -364,7 +382,7 @@ int cqs_b200_finalize(cqs_b200_index* ix) {
       CK(ix, cudaMalloc((void**)&s.d_bitset, std::max<uint64_t>(words, 1) * 4));
       s.bitset_words = words;
     }
-    if (ix->layout.mode != 0 && s.n_rows) {
+    if (ix->storage != CQS_B200_STORAGE_F32 && s.n_rows) {
       // exactness bound of the batched tensor-core path needs max |row|
       if (!s.d_maxnorm) CK(ix, cudaMalloc((void**)&s.d_maxnorm, sizeof(float)));
       CK(ix, launch_max_row_norm(s.d_rows, s.n_rows, ix->layout, s.d_maxnorm, s.stream));
@@ -576,7 +594,14 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
     d_bits = s.d_bitset;
   }
   BatchArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_queries = s.d_bq; a.nq = nq;
+  const bool shadow = ix->storage == CQS_B200_STORAGE_BF16_F32;
+  a.d_rows = shadow ? s.d_rows16 : s.d_rows;
+  a.layout = shadow ? ix->layout16 : ix->layout;
+  a.d_exact_rows = s.d_rows;
+  a.exact_layout = ix->layout;
+  // bf16 rounding of the query (2^-9) [+ of the rows (2^-9) and the cross term] + fp32 accumulation
+  a.err_factor = shadow ? 0.0041656494140625f : 0.0020751953125f;
+  a.n_rows = s.n_rows; a.d_queries = s.d_bq; a.nq = nq;
   a.k = k; a.d_bitset = d_bits; a.row_base = ix->row_base + s.first_row;
   a.max_row_norm = s.max_row_norm; a.d_scratch = s.d_bscratch;
   a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
@@ -609,7 +634,7 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
   if (k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u exceeds max_k=%u", k, kMaxK);
   for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
   if (k == 0 || ix->n_rows == 0 || nq == 0) return CQS_B200_OK;
-  const bool tensor_path = ix->storage == CQS_B200_STORAGE_BF16 && ix->shards.size() == 1 &&
+  const bool tensor_path = ix->storage != CQS_B200_STORAGE_F32 && ix->shards.size() == 1 &&
                            nq >= 8 && ix->n_rows < (1ull << 31);
   if (!tensor_path) {
     for (uint32_t i = 0; i < nq; ++i) {
@@ -924,7 +949,7 @@ uint32_t cqs_b200_dim(const cqs_b200_index* ix) { return ix ? ix->dim : 0; }
 uint32_t cqs_b200_max_k(const cqs_b200_index*) { return kMaxK; }
 int cqs_b200_is_poisoned(const cqs_b200_index* ix) { return ix ? ix->poisoned.load() : 0; }
 int cqs_b200_scores_are_cosine(const cqs_b200_index* ix) {
-  return ix && ix->storage == CQS_B200_STORAGE_F32 && ix->metric == CQS_B200_METRIC_COSINE;
+  return ix && ix->storage != CQS_B200_STORAGE_BF16 && ix->metric == CQS_B200_METRIC_COSINE;
 }
 const char* cqs_b200_name(void) { return "B200"; }
 const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }

@@ -65,9 +65,12 @@ constexpr uint32_t kBatchMaxQ = 1024;        // queries per launch_scan_batch ca
 constexpr uint32_t kBatchCap = 20480;        // candidate slots per query pool
 constexpr uint32_t kBatchDenseRows = 18944;  // round 0 (74 chunks of 256 rows)
 struct BatchArgs {
-  const void* d_rows;        // bf16 [n_rows][ld]
+  const void* d_rows;        // bf16 [n_rows][ld]: what the tensor cores scan
   uint64_t n_rows;           // < 2^31
   RowLayout layout;          // mode 1 or 2 (bf16)
+  const void* d_exact_rows;  // rows the candidates are re-scored on (== d_rows, or the f32 master)
+  RowLayout exact_layout;    // same ld as `layout`
+  float err_factor;          // |tensor score - exact score| <= err_factor * |q| * max|row|
   const float* d_queries;    // f32 [nq][ld], zero padded beyond dim
   uint32_t nq;               // <= kBatchMaxQ
   uint32_t k;

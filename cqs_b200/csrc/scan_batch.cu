@@ -414,12 +414,18 @@ template <int MODE>
 __device__ __forceinline__ float exact_row_dot(const uint8_t* row, const float* q, uint32_t nv,
                                                uint32_t lane) {
   constexpr int E = (MODE == 1) ? 8 : 4;
-  constexpr int BYTES = (MODE == 1) ? 16 : 8;
+  constexpr int BYTES = (MODE == 2) ? 8 : 16;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (uint32_t v = 0; v < nv; ++v) {
     const uint8_t* rp = row + ((size_t)v * 32 + lane) * BYTES;
     const float* qp = q + ((size_t)v * 32 + lane) * E;
-    if (MODE == 1) {
+    if (MODE == 0) {
+      const float4 x = *reinterpret_cast<const float4*>(rp);
+      acc[0] = fmaf(x.x, qp[0], acc[0]);
+      acc[1] = fmaf(x.y, qp[1], acc[1]);
+      acc[2] = fmaf(x.z, qp[2], acc[2]);
+      acc[3] = fmaf(x.w, qp[3], acc[3]);
+    } else if (MODE == 1) {
       const uint4 x = *reinterpret_cast<const uint4*>(rp);
       const uint32_t r[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -454,9 +460,10 @@ __global__ void __launch_bounds__(256) rescore_kernel(const uint8_t* __restrict_
   for (uint32_t j = warp; j < n; j += 8) {
     const ckey_t key = pool[j];
     const uint32_t r = key_row(key);
-    const uint8_t* row = rows + (size_t)r * ld * 2;
-    const float s = (mode == 1) ? exact_row_dot<1>(row, qp, nv, lane)
-                                : exact_row_dot<2>(row, qp, nv, lane);
+    const uint8_t* row = rows + (size_t)r * ld * (mode == 0 ? 4 : 2);
+    const float s = (mode == 0)   ? exact_row_dot<0>(row, qp, nv, lane)
+                    : (mode == 1) ? exact_row_dot<1>(row, qp, nv, lane)
+                                  : exact_row_dot<2>(row, qp, nv, lane);
     // exact keys go to the second half of the pool ([cap/2, cap/2 + n)); a non-finite
     // exact score is dropped like in the single-query kernel
     if (lane == 0) pool[cap / 2 + j] = finite_bits(__float_as_uint(s)) ? make_key(s, r) : 0;
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const uint8_t* __restrict_
 // ---- final selection + exactness check ---------------------------------------------------
 __global__ void __launch_bounds__(kUpdThreads) final_select_kernel(
     const ckey_t* cand, const uint32_t* cnt, const ckey_t* thr, const uint32_t* overflow,
-    const float* qnorm, float max_row_norm, uint32_t cap, uint32_t kprime, uint32_t k,
+    const float* qnorm, float max_row_norm, float err_factor, uint32_t cap, uint32_t kprime, uint32_t k,
     uint64_t row_base, float* out_scores, uint64_t* out_rows, uint32_t* out_n, uint32_t* flags) {
   __shared__ ckey_t s_buf[kUpdCap];
   __shared__ uint32_t s_cnt;
@@ -491,14 +498,15 @@ __global__ void __launch_bounds__(kUpdThreads) final_select_kernel(
   if (tid == 0) {
     out_n[q] = m;
     // Rows outside the pool have approx score <= the pool's cut-off; |approx - exact| <= E
-    // with E = (2^-9 + 2^-13) * |q| * max|row| (bf16 rounding of the query + fp32
-    // accumulation).  If the k-th exact score clears cut-off + E nothing was missed.
+    // with E = err_factor * |q| * max|row| (bf16 rounding of the query — and of the rows
+    // when they shadow an f32 master — plus fp32 accumulation).  If the k-th exact score
+    // clears cut-off + E nothing was missed.
     // flag codes: 1 = pool overflowed, 2 = too few exact survivors, 3 = margin not proven
     uint32_t flag = overflow[q] ? 1u : 0u;
     const ckey_t t = thr[q];
     if (t != 0 && !flag) {
       const float cut = key_score(t);
-      const float E = 0.0020751953125f * qnorm[q] * max_row_norm;
+      const float E = err_factor * qnorm[q] * max_row_norm;
       if (m < k) flag = 2;  // the pool was full yet fewer than k exact survivors: be safe
       else if (!(key_score(s_buf[k - 1]) > cut + E)) flag = 3;
     }
@@ -585,7 +593,7 @@ size_t batch_scratch_bytes(uint32_t nq_pad, uint32_t ld) {
 
 cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) {
   if (a.nq == 0 || a.k == 0 || a.k > kMaxK || a.n_rows == 0 || a.n_rows >= (1ull << 31) ||
-      a.layout.mode == 0 || a.nq > kBatchMaxQ)
+      a.layout.mode == 0 || a.nq > kBatchMaxQ || a.exact_layout.ld != a.layout.ld)
     return cudaErrorInvalidValue;
   const uint32_t nq_pad = (a.nq + kBM - 1) / kBM * kBM;
   const uint32_t ld = a.layout.ld;
@@ -651,10 +659,10 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
     end = (end * 9 < a.n_rows) ? end * 9 : a.n_rows;
     ++round;
   }
-  rescore_kernel<<<a.nq, 256, 0, st>>>((const uint8_t*)a.d_rows, ld, a.layout.mode, a.layout.nv,
-                                       a.d_queries, cand, cnt, kBatchCap, kprime);
+  rescore_kernel<<<a.nq, 256, 0, st>>>((const uint8_t*)a.d_exact_rows, ld, a.exact_layout.mode,
+                                       a.exact_layout.nv, a.d_queries, cand, cnt, kBatchCap, kprime);
   final_select_kernel<<<a.nq, kUpdThreads, 0, st>>>(cand, cnt, thr, overflow, qnorm,
-                                                    a.max_row_norm, kBatchCap, kprime, a.k,
+                                                    a.max_row_norm, a.err_factor, kBatchCap, kprime, a.k,
                                                     a.row_base, a.d_out_scores, a.d_out_rows,
                                                     a.d_out_n, a.d_flags);
   launches += 2;

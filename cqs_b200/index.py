@@ -39,7 +39,8 @@ class B200Index:
         arr = (C.c_int * len(devs))(*devs)
         check(lib.cqs_b200_create(arr, len(devs), self._dim,
                                   capi.METRIC_COSINE if metric == "cosine" else capi.METRIC_DOT,
-                                  capi.STORAGE_F32 if storage == "f32" else capi.STORAGE_BF16,
+                                  {"f32": capi.STORAGE_F32, "bf16": capi.STORAGE_BF16,
+                                   "bf16+f32": capi.STORAGE_BF16_F32}[storage],
                                   C.byref(self._h)))
         self.id_map: list[str] = []
         self.row_base = int(row_base)

@@ -45,6 +45,9 @@ extern "C" {
 #define CQS_B200_METRIC_DOT 1       /* DistanceMetric::DotProduct             */
 #define CQS_B200_STORAGE_F32 0      /* rows kept as f32 (BLOB layout, src/store/helpers/embeddings.rs:14-41) */
 #define CQS_B200_STORAGE_BF16 1     /* rows rounded (RNE) to bf16; the rounded matrix IS the corpus */
+#define CQS_B200_STORAGE_BF16_F32 2 /* f32 master rows (every result is exact f32, as STORAGE_F32) plus a
+                                       bf16 shadow copy that only feeds the tensor-core candidate scan of
+                                       cqs_b200_search_batch; candidates are re-scored on the f32 rows */
 
 #define CQS_B200_MAX_K 1024u        /* VectorIndex::max_k()  src/index.rs:217  */
 
