@@ -1,0 +1,127 @@
+"""N > 1 path.  CPU: world_size-2 gloo test of the host-side logic (partition,
+all-gather plumbing, merge rule) with the oracle standing in for the per-shard
+scan.  GPU: the same corpus split into shards inside ONE process (emulating the
+ranks), per-shard device top-k, concatenation = the all-gather result, merge
+kernel — must equal the unsharded answer."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import cqs_oracle as O
+
+f32 = np.float32
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, n, k, out):
+    import torch.distributed as dist
+    import torch
+    from cqs_b200.sharded import shard_range, merge_topk_host
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows = O.fast_unit_rows(n, 64, seed=3)
+    rows[10] = rows[n - 5]                                   # a cross-shard exact tie
+    queries = O.fast_unit_rows(6, 64, seed=4)
+    queries[0] = rows[10]
+    row0, nl = shard_range(n, world, rank)
+    sc = np.full((6, k), -np.inf, f32)
+    rw = np.full((6, k), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    for qi in range(6):
+        r, s = O.brute_force_search(rows[row0:row0 + nl], queries[qi], k)   # stand-in for the shard scan
+        sc[qi, :r.shape[0]] = s
+        rw[qi, :r.shape[0]] = (r + row0).astype(np.uint64)
+    g_sc = [torch.empty((6, k), dtype=torch.float32) for _ in range(world)]
+    g_rw = [torch.empty((6, k), dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(g_sc, torch.from_numpy(sc))
+    dist.all_gather(g_rw, torch.from_numpy(rw.view(np.int64)))
+    ok = True
+    for qi in range(6):
+        s, r = merge_topk_host(np.stack([t[qi].numpy() for t in g_sc]),
+                               np.stack([t[qi].numpy().view(np.uint64) for t in g_rw]), k)
+        er, es = O.brute_force_search(rows, queries[qi], k)
+        ok &= r.astype(np.int64).tolist() == er.tolist()
+        ok &= np.array_equal(s.view(np.uint32), es.view(np.uint32))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_partition_gather_merge():
+    import torch.multiprocessing as mp
+    from cqs_b200.sharded import shard_range
+    assert shard_range(10, 3, 0) == (0, 4) and shard_range(10, 3, 2) == (8, 2) and shard_range(3, 8, 7) == (3, 0)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 5003, 20, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
+
+
+def test_merge_topk_host_rule():
+    from cqs_b200.sharded import merge_topk_host
+    sc = np.array([[0.5, 0.4, -np.inf], [0.5, 0.45, 0.1]], f32)
+    rw = np.array([[9, 2, 2**64 - 1], [3, 7, 8]], np.uint64)
+    s, r = merge_topk_host(sc, rw, 4)
+    assert r.tolist() == [3, 9, 7, 2] and s.tolist() == [0.5, 0.5, f32(0.45), f32(0.4)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_emulated_shards_device_merge_equals_unsharded(storage):
+    import ctypes as C
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    from cqs_b200.sharded import shard_range
+    n, dim, k, G, Q = 50_003, 768, 20, 4, 8
+    rows = O.fast_unit_rows(n, dim, seed=71)
+    rows[17] = rows[n - 3]                                   # cross-shard tie
+    queries = O.fast_unit_rows(Q, dim, seed=72)
+    queries[0] = rows[17]
+    whole = cqs_b200.B200Index(dim, storage=storage)
+    whole.append(None, rows); whole.finalize()
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    d_q = torch.from_numpy(queries).to(dev)
+    g_sc = torch.empty((G, Q, k), dtype=torch.float32, device=dev)
+    g_rw = torch.empty((G, Q, k), dtype=torch.int64, device=dev)
+    g_n = torch.empty((G, Q), dtype=torch.int32, device=dev)
+    shards = []
+    with torch.cuda.stream(stream):
+        sp = C.c_void_p(stream.cuda_stream)
+        for g in range(G):
+            row0, nl = shard_range(n, G, g)
+            ix = cqs_b200.B200Index(dim, storage=storage, row_base=row0)
+            ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+            shards.append(ix)
+            for qi in range(Q):
+                check(lib.cqs_b200_search_device(ix._h, C.c_void_p(d_q.data_ptr() + qi * dim * 4), k, None,
+                                                 C.c_void_p(g_sc[g, qi].data_ptr()), C.c_void_p(g_rw[g, qi].data_ptr()),
+                                                 C.c_void_p(g_n[g, qi].data_ptr()), sp))
+        m_sc = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        m_rw = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        m_n = torch.empty((Q,), dtype=torch.int32, device=dev)
+        check(lib.cqs_b200_merge_topk_device(0, C.c_void_p(g_sc.data_ptr()), C.c_void_p(g_rw.data_ptr()), G, Q, k,
+                                             C.c_void_p(m_sc.data_ptr()), C.c_void_p(m_rw.data_ptr()),
+                                             C.c_void_p(m_n.data_ptr()), sp))
+    stream.synchronize()
+    for qi in range(Q):
+        a, b = whole.search_rows(queries[qi], k)
+        assert int(m_n[qi]) == k
+        assert m_rw[qi].cpu().numpy().view(np.uint64).tolist() == a.tolist()
+        assert np.array_equal(m_sc[qi].cpu().numpy().view(np.uint32), b.view(np.uint32))
+    assert m_rw[0, :2].cpu().tolist() == [17, n - 3]
+    for ix in shards + [whole]:
+        ix.close()
