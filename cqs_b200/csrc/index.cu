@@ -67,6 +67,8 @@ struct Shard {
   uint32_t* d_sp_done = nullptr;
   uint32_t* d_q_tok = nullptr;
   float* d_q_w = nullptr;
+  uint32_t* d_bounds = nullptr;   // sparse pass-1 scratch, grown on demand
+  size_t bounds_bytes = 0;
   // fused output
   uint64_t* d_f_rows = nullptr;
   float* d_f_fused = nullptr;
@@ -136,7 +138,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
   cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
   cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
-  cudaFree(s.d_q_tok); cudaFree(s.d_q_w);
+  cudaFree(s.d_q_tok); cudaFree(s.d_q_w); cudaFree(s.d_bounds);
   cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
@@ -723,7 +725,17 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
                          uint32_t q_nnz, uint32_t k, const uint32_t* d_bits) {
   CK(ix, cudaMemcpyAsync(s.d_q_tok, q_tok, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, s.stream));
   CK(ix, cudaMemcpyAsync(s.d_q_w, q_w, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, s.stream));
+  const size_t need = sparse_bounds_bytes(s.n_rows, q_nnz);
+  if (need > s.bounds_bytes) {
+    CK(ix, cudaStreamSynchronize(s.stream));
+    cudaFree(s.d_bounds);
+    s.d_bounds = nullptr;
+    s.bounds_bytes = 0;
+    CK(ix, cudaMalloc((void**)&s.d_bounds, need + need / 2));
+    s.bounds_bytes = need + need / 2;
+  }
   SparseArgs a;
+  a.d_bounds = s.d_bounds;
   a.sp = s.sparse; a.n_docs = s.n_rows; a.d_q_tok = s.d_q_tok; a.d_q_w = s.d_q_w; a.q_nnz = q_nnz;
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;

@@ -104,6 +104,7 @@ struct SparseArgs {
   const uint32_t* d_q_tok;  // [q_nnz] (query order)
   const float* d_q_w;
   uint32_t q_nnz;
+  uint32_t* d_bounds;       // scratch, sparse_bounds_bytes(n_docs, q_nnz)
   const uint32_t* d_bitset;
   uint32_t k;
   uint64_t row_base;
@@ -114,7 +115,8 @@ struct SparseArgs {
   uint64_t* d_out_rows;
   uint32_t* d_out_n;
 };
-constexpr uint32_t kSparseDocsPerBlock = 4096;
+constexpr uint32_t kSparseDocsPerBlock = 256;   // docs owned by one warp at a time
+size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz);
 cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
 
 struct FuseArgs {

@@ -17,22 +17,76 @@
 // [tptr[t], tptr[t+1]) hold (doc, weight) sorted by doc ascending — the order
 // SpladeIndex::build produces (index.rs:197-203).  A query touches only
 // sum_t |postings(t)| * 8 bytes, versus the whole 8*nnz bytes of a doc-major
-// scan.  Docs are processed in ranges of 4096: a CTA owns a range, keeps the
-// 4096 f32 accumulators in shared memory, stages the slices of every query
-// token that fall in its range, then applies the tokens IN QUERY ORDER (the
-// reference's accumulation order, index.rs:251-259) with one barrier per
-// token.  Candidates go through the same shared-memory top-k accumulator as
-// the dense scan; the last CTA merges.
+// scan.  Docs are processed in blocks of 256 owned by one warp (accumulators in
+// shared memory); a first pass streams the doc ids of the touched lists once to
+// find where every block starts in every query token's list, the second applies
+// the tokens IN QUERY ORDER (the reference's accumulation order,
+// index.rs:251-259).  Candidates go through the same shared-memory top-k
+// accumulator as the dense scan; the last CTA merges.
 #include "common.cuh"
 #include "internal.h"
 
 namespace cqs {
 
-constexpr int kSpThreads = 512;
-constexpr uint32_t kSpCap = 8192;      // top-k accumulator slots
-constexpr uint32_t kSpStage = 8192;    // staged posting entries
-constexpr uint32_t kSpMaxQ = 1024;     // max query nnz
-constexpr uint32_t kDPB = kSparseDocsPerBlock;
+constexpr int kSpThreads = 256;          // 8 warps; light enough to share an SM with the dense scan CTA
+constexpr int kSpWarps = kSpThreads / 32;
+constexpr uint32_t kSpCap = 4096;        // top-k accumulator slots
+constexpr uint32_t kSpMaxQ = 1024;       // max query nnz
+constexpr uint32_t kSpBlock = kSparseDocsPerBlock;  // docs owned by one warp at a time (256)
+
+// ---- pass 1: where does every 256-doc block start inside every query token's list? ----
+// bounds[i][j] = number of postings of query token i with doc < j*256 (j = 0..n_blocks).
+// Found by streaming the doc ids of the touched lists once (no dependent binary-search
+// chains): the thread that sees the first posting of a block writes the offsets of that
+// block and of the empty blocks before it.  bounds is zero-filled beforehand (empty lists).
+struct BoundsParams {
+  const uint64_t* tptr;
+  const uint32_t* doc;
+  uint32_t vocab;
+  const uint32_t* q_tok;
+  uint32_t q_nnz;
+  uint32_t n_blocks;
+  uint32_t* bounds;  // [q_nnz][n_blocks + 1]
+};
+constexpr uint32_t kBoundsChunk = 2048;  // postings per CTA work unit
+__global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p) {
+  __shared__ uint64_t s_base[kSpMaxQ];
+  __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // chunks before token i
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
+    const uint32_t t = __ldg(p.q_tok + i);
+    uint64_t b0 = 0, b1 = 0;
+    if (t < p.vocab) { b0 = __ldg(p.tptr + t); b1 = __ldg(p.tptr + t + 1); }
+    s_base[i] = b0;
+    s_prefix[i + 1] = (b1 - b0 + kBoundsChunk - 1) / kBoundsChunk;  // chunk count, scanned below
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s_prefix[0] = 0;
+    for (uint32_t i = 0; i < p.q_nnz; ++i) s_prefix[i + 1] += s_prefix[i];
+  }
+  __syncthreads();
+  const uint64_t n_chunks = s_prefix[p.q_nnz];
+  for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    uint32_t lo = 0, hi = p.q_nnz;  // token owning chunk c: last i with prefix[i] <= c
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (s_prefix[mid] <= c) lo = mid; else hi = mid;
+    }
+    const uint32_t i = lo, t = __ldg(p.q_tok + i);
+    const uint64_t base = s_base[i];
+    const uint32_t len = (uint32_t)(__ldg(p.tptr + t + 1) - base);
+    const uint32_t e0 = (uint32_t)(c - s_prefix[i]) * kBoundsChunk;
+    uint32_t* row = p.bounds + (size_t)i * (p.n_blocks + 1);
+    for (uint32_t e = e0 + tid; e < min(len, e0 + kBoundsChunk); e += blockDim.x) {
+      const uint32_t blk = __ldg(p.doc + base + e) / kSpBlock;
+      const int prev = (e == 0) ? -1 : (int)(__ldg(p.doc + base + e - 1) / kSpBlock);
+      for (int j = prev + 1; j <= (int)blk; ++j) row[j] = e;       // first posting at or after block j
+      if (e == len - 1)
+        for (uint32_t j = blk + 1; j <= p.n_blocks; ++j) row[j] = len;  // blocks after the last posting
+    }
+  }
+}
 
 struct SparseParams {
   const uint64_t* tptr;
@@ -43,6 +97,8 @@ struct SparseParams {
   const uint32_t* q_tok;
   const float* q_w;
   uint32_t q_nnz;
+  const uint32_t* bounds;
+  uint32_t n_blocks;
   const uint32_t* bitset;
   uint32_t k;
   uint64_t row_base;
@@ -54,110 +110,157 @@ struct SparseParams {
   uint32_t* out_n;
 };
 
+constexpr uint32_t kSpStage = 1024;      // postings staged per warp between apply phases
+
 struct SpSmem {
-  ckey_t buf[kSpCap];            // 64 KB
-  uint2 stage[kSpStage];        // 64 KB: (local doc, weight bits)
-  float acc[kDPB];              // 16 KB
-  uint8_t touched[kDPB];        //  4 KB
-  uint64_t lo[kSpMaxQ];         //  8 KB  slice start of token i in this range
-  uint32_t len[kSpMaxQ];        //  4 KB  slice length
-  uint32_t off[kSpMaxQ + 1];    //  4 KB  staging offsets of the current batch
-  uint32_t pos[kMaxGrid];       //  4 KB
+  ckey_t buf[kSpCap];                    // 32 KB
+  uint2 stage[kSpWarps][kSpStage];       // 64 KB  (local doc, weight bits)
+  float acc[kSpWarps][kSpBlock];         //  8 KB
+  uint8_t touched[kSpWarps][kSpBlock];   //  2 KB
+  uint32_t off[kSpWarps][36];            //  staging offsets of the tokens of the current group
+  uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
+  float qw[kSpMaxQ];                     //  4 KB
+  uint32_t pos[kMaxGrid];                //  4 KB
   ckey_t thr;
   uint32_t cnt;
   uint32_t last;
-  uint32_t batch_end;
 };
 
-__device__ __forceinline__ uint64_t lower_bound_doc(const uint32_t* doc, uint64_t lo, uint64_t hi,
-                                                    uint64_t target) {
-  while (lo < hi) {
-    uint64_t mid = lo + ((hi - lo) >> 1);
-    if ((uint64_t)__ldg(doc + mid) < target) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-__global__ void __launch_bounds__(kSpThreads, 1) sparse_search_kernel(const SparseParams p) {
+// ---- pass 2: accumulate + select -------------------------------------------------------
+// A warp owns a 256-doc block: its accumulators sit in shared memory.  Query tokens are
+// taken in groups whose slices (the part of each token's posting list that falls in the
+// block) fit a 1024-entry staging buffer: the group's postings are fetched with many
+// independent loads in flight, then applied IN QUERY ORDER (the reference's accumulation
+// order, index.rs:251-259): within one token the docs are distinct, so the lanes update
+//   acc[doc] = acc[doc] + qw*dw   (separate f32 multiply and add)
+// without conflicts, and only a __syncwarp separates tokens.  Touched docs that pass the
+// filter go to the CTA's top-k accumulator.
+__global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpSmem& s = *reinterpret_cast<SpSmem*>(smem_raw);
-  const uint32_t tid = threadIdx.x;
-  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{threadIdx.x, kSpThreads, 0}};
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}};
   tk.init();
+  for (uint32_t i = tid; i < p.q_nnz; i += kSpThreads) {
+    const uint32_t t = __ldg(p.q_tok + i);
+    s.base[i] = (t < p.vocab) ? __ldg(p.tptr + t) : 0;
+    s.qw[i] = __ldg(p.q_w + i);
+  }
   __syncthreads();
   const uint32_t k = p.k;
-  const uint64_t n_ranges = (p.n_docs + kDPB - 1) / kDPB;
-  for (uint64_t range = blockIdx.x; range < n_ranges; range += gridDim.x) {
-    const uint64_t d0 = range * kDPB;
-    const uint64_t d1 = min(p.n_docs, d0 + kDPB);
-    const uint32_t nd = (uint32_t)(d1 - d0);
-    for (uint32_t i = tid; i < kDPB; i += kSpThreads) {
-      s.acc[i] = 0.f;
-      s.touched[i] = 0;
-    }
-    // slice of every query token's posting list that falls in [d0, d1)
-    for (uint32_t i = tid; i < p.q_nnz; i += kSpThreads) {
-      uint32_t t = __ldg(p.q_tok + i);
-      uint64_t a = 0, b = 0;
-      if (t < p.vocab) {
-        uint64_t b0 = __ldg(p.tptr + t), b1 = __ldg(p.tptr + t + 1);
-        a = lower_bound_doc(p.doc, b0, b1, d0);
-        b = lower_bound_doc(p.doc, a, b1, d1);
+  const uint32_t stride = p.n_blocks + 1;
+  const uint32_t n_steps = (p.n_blocks + kSpWarps - 1) / kSpWarps;
+  float* acc = s.acc[warp];
+  uint8_t* touched = s.touched[warp];
+  uint2* stage = s.stage[warp];
+  uint32_t* off = s.off[warp];
+  for (uint32_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
+    const uint32_t blk = step * kSpWarps + warp;
+    const ckey_t thr = s.thr;
+    if (blk < p.n_blocks) {
+      const uint32_t d0 = blk * kSpBlock;
+#pragma unroll
+      for (uint32_t i = lane; i < kSpBlock; i += 32) {
+        acc[i] = 0.f;
+        touched[i] = 0;
       }
-      s.lo[i] = a;
-      s.len[i] = (uint32_t)(b - a);
+      for (uint32_t i0 = 0; i0 < p.q_nnz; i0 += 32) {
+        // slice [lo, hi) of 32 query tokens at once (one token per lane)
+        uint32_t lo = 0, hi = 0;
+        if (i0 + lane < p.q_nnz) {
+          const uint32_t* row = p.bounds + (size_t)(i0 + lane) * stride + blk;
+          lo = __ldg(row);
+          hi = __ldg(row + 1);
+        }
+        const uint32_t len = hi - lo;           // <= 256 (a doc lists a token once)
+        uint32_t incl = len;                    // inclusive warp scan of the slice lengths
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (uint32_t)o) incl += v;
+        }
+        uint32_t done_tok = 0;                  // tokens of this 32-group already applied
+        uint32_t consumed = 0;                  // postings of this 32-group already applied
+        const uint32_t n_tok = min(32u, p.q_nnz - i0);
+        while (done_tok < n_tok) {
+          // group = maximal run of tokens from done_tok whose postings fit the staging buffer
+          const uint32_t fits = __ballot_sync(0xffffffffu, lane >= done_tok && lane < n_tok &&
+                                                               incl - consumed <= kSpStage);
+          const uint32_t g1 = done_tok + __popc(fits);        // tokens [done_tok, g1)
+          __syncwarp();
+          if (lane >= done_tok && lane < g1) off[lane - done_tok + 1] = incl - consumed;
+          if (lane == 0) off[0] = 0;
+          __syncwarp();
+          const uint32_t g_n = g1 - done_tok;
+          const uint32_t total = off[g_n];
+          // fetch: flat posting index -> (token, offset); 8 postings per lane in flight
+          for (uint32_t f0 = 0; f0 < total; f0 += 32 * 8) {
+            uint32_t dd[8];
+            float ww[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t f = f0 + u * 32 + lane;
+              dd[u] = 0xFFFFFFFFu;
+              ww[u] = 0.f;
+              if (f < total) {
+                uint32_t a = 0, b = g_n;        // token t with off[t] <= f < off[t+1]
+                while (b - a > 1) {
+                  const uint32_t m = (a + b) >> 1;
+                  if (off[m] <= f) a = m; else b = m;
+                }
+                dd[u] = a;                      // token index inside the group, resolved after the loop
+                ww[u] = __uint_as_float(f - off[a]);
+              }
+            }
+            // resolve addresses (needs the slice start of the owning token, held by another lane)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t f = f0 + u * 32 + lane;
+              const uint32_t tsel = (f < total) ? dd[u] : 0;
+              const uint32_t tok_lo = __shfl_sync(0xffffffffu, lo, done_tok + tsel);
+              if (f < total) {
+                const uint64_t e = s.base[i0 + done_tok + tsel] + tok_lo + __float_as_uint(ww[u]);
+                dd[u] = __ldg(p.doc + e) - d0;
+                ww[u] = __ldg(p.w + e);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint32_t f = f0 + u * 32 + lane;
+              if (f < total) stage[f] = make_uint2(dd[u], __float_as_uint(ww[u]));
+            }
+          }
+          __syncwarp();
+          // apply the group's tokens in query order
+          for (uint32_t t = 0; t < g_n; ++t) {
+            const float qw = s.qw[i0 + done_tok + t];
+            const uint32_t e1 = off[t + 1];
+            for (uint32_t e = off[t] + lane; e < e1; e += 32) {
+              const uint2 ent = stage[e];
+              // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
+              acc[ent.x] = __fadd_rn(acc[ent.x], __fmul_rn(qw, __uint_as_float(ent.y)));
+              touched[ent.x] = 1;
+            }
+            __syncwarp();
+          }
+          consumed += total;
+          done_tok = g1;
+        }
+      }
+      // candidates: touched docs that pass the filter, finite score (candidate.rs:275)
+      for (uint32_t d = lane; d < kSpBlock; d += 32) {
+        const uint64_t r = (uint64_t)d0 + d;
+        if (!touched[d] || r >= p.n_docs) continue;
+        if (p.bitset && !((__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u)) continue;
+        const float sc = acc[d];
+        if (!finite_bits(__float_as_uint(sc))) continue;
+        const ckey_t key = make_key(sc, (uint32_t)r);
+        if (key > thr) tk.push(key);
+      }
     }
     __syncthreads();
-    uint32_t i0 = 0;
-    while (i0 < p.q_nnz) {
-      // batch = maximal run of tokens whose slices fit the staging buffer
-      if (tid == 0) {
-        uint32_t o = 0, i = i0;
-        s.off[0] = 0;
-        while (i < p.q_nnz && o + s.len[i] <= kSpStage) {
-          o += s.len[i];
-          ++i;
-          s.off[i - i0] = o;
-        }
-        s.batch_end = i;  // a single slice never exceeds kDPB <= kSpStage, so i > i0
-      }
-      __syncthreads();
-      const uint32_t i1 = s.batch_end;
-      for (uint32_t i = i0; i < i1; ++i) {
-        const uint64_t lo = s.lo[i];
-        const uint32_t len = s.len[i], o = s.off[i - i0];
-        for (uint32_t e = tid; e < len; e += kSpThreads)
-          s.stage[o + e] = make_uint2((uint32_t)(__ldg(p.doc + lo + e) - d0),
-                                      __float_as_uint(__ldg(p.w + lo + e)));
-      }
-      __syncthreads();
-      for (uint32_t i = i0; i < i1; ++i) {
-        const float qw = __ldg(p.q_w + i);
-        const uint32_t len = s.len[i], o = s.off[i - i0];
-        for (uint32_t e = tid; e < len; e += kSpThreads) {
-          uint2 ent = s.stage[o + e];
-          // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight  (index.rs:259)
-          s.acc[ent.x] = __fadd_rn(s.acc[ent.x], __fmul_rn(qw, __uint_as_float(ent.y)));
-          s.touched[ent.x] = 1;
-        }
-        __syncthreads();
-      }
-      i0 = i1;
-    }
-    // candidates: touched docs that pass the filter, finite score (candidate.rs:275)
-    ckey_t thr = s.thr;
-    for (uint32_t d = tid; d < nd; d += kSpThreads) {
-      if (!s.touched[d]) continue;
-      uint64_t r = d0 + d;
-      if (p.bitset && !((__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u)) continue;
-      float sc = s.acc[d];
-      if (!finite_bits(__float_as_uint(sc))) continue;
-      ckey_t key = make_key(sc, (uint32_t)r);
-      if (key > thr) tk.push(key);
-    }
-    __syncthreads();
-    // at most kDPB pushes per range: compact when the next range could overflow
-    if (s.cnt + kDPB > kSpCap || (s.thr == 0 && s.cnt >= k)) tk.compact(k);
+    // at most kSpWarps*kSpBlock = 2048 pushes per step
+    if (s.cnt + kSpWarps * kSpBlock > kSpCap || (s.thr == 0 && s.cnt >= k)) tk.compact(k);
     __syncthreads();
   }
   tk.compact(k);
@@ -179,27 +282,38 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_search_kernel(const Spar
   if (tid == 0) *p.done = 0;
 }
 
+size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz) {
+  const uint64_t n_blocks = (n_docs + kSpBlock - 1) / kSpBlock;
+  return (size_t)q_nnz * (n_blocks + 1) * sizeof(uint32_t);
+}
+
 cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   if (a.n_docs == 0 || a.k == 0 || a.k > kMaxK || a.q_nnz == 0 || a.q_nnz > kSpMaxQ ||
-      a.n_docs > 0xFFFFFFFFull)
+      a.n_docs > 0xFFFFFFFFull || !a.d_bounds)
     return cudaErrorInvalidValue;
-  SparseParams p;
-  p.tptr = a.sp.d_tptr; p.doc = a.sp.d_doc; p.w = a.sp.d_w; p.vocab = a.sp.vocab;
-  p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
-  p.bitset = a.d_bitset; p.k = a.k; p.row_base = a.row_base;
-  p.partial = a.d_partial; p.partial_cnt = a.d_partial_cnt; p.done = a.d_done;
-  p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
-  uint64_t n_ranges = (a.n_docs + kDPB - 1) / kDPB;
+  const uint32_t n_blocks = (uint32_t)((a.n_docs + kSpBlock - 1) / kSpBlock);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = (int)(n_ranges < (uint64_t)sms ? n_ranges : (uint64_t)sms);
-  cudaError_t e = cudaFuncSetAttribute(sparse_search_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(SpSmem));
+  cudaError_t e = cudaMemsetAsync(a.d_bounds, 0, sparse_bounds_bytes(a.n_docs, a.q_nnz), st);
+  if (e != cudaSuccess) return e;
+  BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds};
+  sparse_bounds_kernel<<<sms * 4, 256, 0, st>>>(bp);
+  SparseParams p;
+  p.tptr = a.sp.d_tptr; p.doc = a.sp.d_doc; p.w = a.sp.d_w; p.vocab = a.sp.vocab;
+  p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
+  p.bounds = a.d_bounds; p.n_blocks = n_blocks;
+  p.bitset = a.d_bitset; p.k = a.k; p.row_base = a.row_base;
+  p.partial = a.d_partial; p.partial_cnt = a.d_partial_cnt; p.done = a.d_done;
+  p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
+  const uint32_t n_steps = (n_blocks + kSpWarps - 1) / kSpWarps;
+  int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
+  if (grid > (int)kMaxGrid) grid = kMaxGrid;
+  e = cudaFuncSetAttribute(sparse_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(SpSmem));
   if (e != cudaSuccess) return e;
   sparse_search_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
-  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  g_kernel_launches.fetch_add(2, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
