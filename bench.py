@@ -46,39 +46,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (one streaming
+    `nvidia-smi -lms 100` process, as in the profiling recipe)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
         self._idx = gpu_index
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._proc = None
+        self._t = None
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        for line in self._proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) < 6:
+                continue
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self._idx)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
                 self.samples.append(float(parts[0]))
                 self.max_mhz = float(parts[1])
-                for nm, v in zip(names, parts[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+            except ValueError:
+                continue
+            for nm, v in zip(self.NAMES, parts[2:]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def __enter__(self):
-        self._t.start()
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                           "-lms", "100", "-i", str(self._idx)], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+            time.sleep(0.25)   # let the first sample land before the timed region starts
+        except OSError:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self._proc is not None:
+            time.sleep(0.12)
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            if self._t is not None:
+                self._t.join(timeout=5)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
@@ -237,13 +253,14 @@ def main():
     barrier()
     launches0 = lib.cqs_b200_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record(stream)
-        for s in range(args.steps):
-            step_device(args.warmup + s)
-        e1.record(stream)
-        barrier()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    barrier()
+    e0.record(stream)
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record(stream)
+    barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.cqs_b200_kernel_launches() - launches0
     if world > 1:
@@ -288,6 +305,7 @@ def main():
         step_e2e(args.warmup + s)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clk.__exit__()
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

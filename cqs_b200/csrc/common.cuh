@@ -147,6 +147,7 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
 }
 
 constexpr uint32_t kRankSortMax = 512;  // compact() uses a rank sort up to this many keys
+constexpr uint32_t kSelBuckets = 2048;  // histogram resolution of select()
 
 // Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
 // Any thread may push() a key that beats the current threshold; the group calls
@@ -158,6 +159,7 @@ struct TopK {
   ckey_t* thr;     // shared: k-th best key so far (0 while fewer than k)
   uint32_t cap;
   Group g;
+  uint32_t* hist = nullptr;  // shared [kSelBuckets + 96] words, needed by select()
 
   __device__ __forceinline__ void init() {
     if (g.tid == 0) {
@@ -200,6 +202,112 @@ struct TopK {
     }
     g.sync();
   }
+
+  // Collective partial selection for the streaming phase: shrinks the buffer to a SUPERSET
+  // of the k best keys (unsorted, at most cap/2 of them) and raises the threshold to a
+  // valid lower bound of the k-th best — with one histogram pass instead of a sort.
+  // Keys live in registers (ITEMS per thread, ITEMS * nthr >= cap) while the buffer is
+  // rewritten.  Buckets are linear in key space between the current min and max.
+  template <int ITEMS>
+  __device__ __forceinline__ void select(uint32_t k) {
+    g.sync();
+    const uint32_t n = min(*cnt, cap);
+    if (n <= kRankSortMax || n <= k || hist == nullptr) {
+      compact(k);
+      return;
+    }
+    const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
+    ckey_t r[ITEMS];
+    ckey_t lo = ~0ull, hi = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint32_t i = j * g.nthr + g.tid;
+      r[j] = (i < n) ? buf[i] : 0;
+      if (i < n) {
+        lo = r[j] < lo ? r[j] : lo;
+        hi = r[j] > hi ? r[j] : hi;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const ckey_t a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = a < lo ? a : lo;
+      hi = b > hi ? b : hi;
+    }
+    ckey_t* aux64 = reinterpret_cast<ckey_t*>(hist + kSelBuckets);  // [2 * 16] keys
+    uint32_t* aux32 = hist + kSelBuckets + 64;                      // [16] words
+    if (lane == 0) {
+      aux64[warp] = lo;
+      aux64[16 + warp] = hi;
+    }
+    for (uint32_t i = g.tid; i < kSelBuckets; i += g.nthr) hist[i] = 0;
+    g.sync();
+    for (uint32_t w = 0; w < nwarps; ++w) {
+      lo = aux64[w] < lo ? aux64[w] : lo;
+      hi = aux64[16 + w] > hi ? aux64[16 + w] : hi;
+    }
+    const int bits = 64 - __clzll((long long)((hi - lo) | 1ull));
+    const int sh = bits > 11 ? bits - 11 : 0;  // (key - lo) >> sh < 2048
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if ((uint32_t)(j * g.nthr + g.tid) < n) atomicAdd(&hist[(uint32_t)((r[j] - lo) >> sh)], 1u);
+    g.sync();
+    // cumulative counts from the TOP bucket down: thread t owns buckets
+    // [top - per*(t+1) + 1, top - per*t], per = kSelBuckets / nthr
+    const uint32_t per = kSelBuckets / g.nthr;
+    const uint32_t b_hi = kSelBuckets - 1 - per * g.tid;  // highest bucket of this thread
+    uint32_t local = 0;
+    for (uint32_t j = 0; j < per; ++j) local += hist[b_hi - j];
+    uint32_t incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += v;
+    }
+    if (lane == 31) aux32[warp] = incl;
+    g.sync();
+    uint32_t before = incl - local;  // keys in buckets above this thread's segment
+    for (uint32_t w = 0; w < warp; ++w) before += aux32[w];
+    g.sync();
+    if (before < k && k <= before + local) {  // exactly one thread: the k-th best falls in its segment
+      uint32_t acc = before;
+      for (uint32_t j = 0; j < per; ++j) {
+        const uint32_t h = hist[b_hi - j];
+        if (acc + h >= k) {
+          aux32[0] = b_hi - j;   // b*: bucket holding the k-th best
+          aux32[1] = acc + h;    // keys in buckets >= b*
+          break;
+        }
+        acc += h;
+      }
+    }
+    g.sync();
+    const uint32_t bstar = aux32[0], n_keep = aux32[1];
+    if (n_keep > (cap >> 1)) {  // pathological ties: fall back to the exact sort (buffer untouched so far)
+      compact(k);
+      return;
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if ((uint32_t)(j * g.nthr + g.tid) < n && (uint32_t)((r[j] - lo) >> sh) >= bstar) ++mine;
+    uint32_t inc2 = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= (uint32_t)o) inc2 += v;
+    }
+    g.sync();
+    if (lane == 31) aux32[2 + warp] = inc2;
+    g.sync();
+    uint32_t off = inc2 - mine;
+    for (uint32_t w = 0; w < warp; ++w) off += aux32[2 + w];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if ((uint32_t)(j * g.nthr + g.tid) < n && (uint32_t)((r[j] - lo) >> sh) >= bstar) buf[off++] = r[j];
+    if (g.tid == 0) {
+      *cnt = n_keep;
+      *thr = lo + ((ckey_t)bstar << sh) - 1;  // every kept key is > thr; thr >= the previous threshold
+    }
+    g.sync();
+  }
 };
 
 constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the partial-list scratch
@@ -208,17 +316,20 @@ constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the par
 // the sparse kernels).  All G lists (the caller's own included) are read back
 // from the partial-list scratch in L2.  Collective over tk.g.
 //
-//  1. bound: with m = ceil(k/G), S = the first m keys of every list has >= k
-//     members whenever k candidates exist at all, so the k-th largest key of S is
-//     a lower bound T0 of the global k-th best.  S (<= k + G keys) is loaded with
-//     independent L2 loads and T0 found by rank counting.  For k <= G this leaves
-//     ~k survivors out of G*k candidates.
+//  1. bound: for a column m (the m-th key of every list) the ceil(k/m)-th largest
+//     column value v has at least ceil(k/m) lists with >= m keys >= v, i.e. >= k keys
+//     >= v overall: v is a lower bound of the global k-th best.  Two columns are
+//     evaluated (the first power of two m with ceil(k/m) <= G, and 2m; rank counting
+//     over G values each) and the better bound kept.  For k <= G column 1 alone
+//     leaves ~k survivors out of G*k candidates.
 //  2. rounds: in round r every still-active list exposes its window
-//     [r*b, (r+1)*b) and all window slots are examined in parallel; keys above the
-//     threshold are pushed; a list retires at its first key <= threshold (lists
-//     are sorted) or when exhausted.  b*G <= cap - k, so the accumulator cannot
-//     overflow between compactions.  s_pos[l] = keys list l still offers.
-//  3. emit: (score desc, row asc); unused slots = (-inf, UINT64_MAX).
+//     [r*b, (r+1)*b) and all window slots are examined in parallel (independent L2
+//     loads); keys above the threshold are pushed; a list retires at its first key
+//     <= threshold (lists are sorted) or when exhausted.  The accumulator is only
+//     re-selected when the next round could overflow it.  s_pos[l] = keys list l
+//     still offers.
+//  3. final exact sort, emit (score desc, row asc); unused slots = (-inf, UINT64_MAX).
+template <int ITEMS>
 __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_pos, uint32_t k,
                                                         const ckey_t* partial,
                                                         const uint32_t* partial_cnt, uint32_t G,
@@ -232,29 +343,44 @@ __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_po
     *tk.thr = 0;
   }
   tk.g.sync();
-  // ---- 1. lower bound from the list heads ----
-  const uint32_t m = (k + G - 1) / G;
-  const uint32_t sn = G * m;  // <= k + G - 1 <= cap / 2
-  ckey_t* S = tk.buf + (tk.cap >> 1);
-  for (uint32_t t = tid; t < sn; t += T) {
-    const uint32_t l = t / m, pos = t - l * m;
-    S[t] = (pos < s_pos[l]) ? __ldcg(partial + (size_t)l * kPartialStride + pos) : 0;
+  // ---- 1. column bounds (two columns: the first m with ceil(k/m) <= G, and 2m) ----
+  {
+    ckey_t* col = tk.buf + (tk.cap >> 1);  // [2][G] scratch (2G <= 2*kMaxGrid <= cap/2)
+    uint32_t m0 = 1;
+    while ((k + m0 - 1) / m0 > G) m0 <<= 1;
+    const uint32_t ms[2] = {m0, 2 * m0};
+    for (uint32_t l = tid; l < G; l += T) {
+      const uint32_t len = s_pos[l];
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2)
+        col[c2 * G + l] = (ms[c2] <= len && ms[c2] <= k)
+                              ? __ldcg(partial + (size_t)l * kPartialStride + (ms[c2] - 1)) : 0;
+    }
+    tk.g.sync();
+    for (uint32_t t = tid; t < 2 * G; t += T) {
+      const uint32_t c2 = t / G;
+      const ckey_t mine = col[t];
+      if (mine == 0) continue;
+      const uint32_t j = (k + ms[c2] - 1) / ms[c2];  // need the j-th largest of this column
+      const ckey_t* cc = col + c2 * G;
+      uint32_t rank = 0;
+      for (uint32_t i = 0; i < G; ++i) rank += (cc[i] > mine) ? 1u : 0u;  // keys are unique
+      if (rank == j - 1) atomicMax(tk.thr, mine - 1);  // keys >= v pass "key > thr"
+    }
+    tk.g.sync();
   }
-  tk.g.sync();
-  for (uint32_t t = tid; t < sn; t += T) {
-    const ckey_t mine = S[t];
-    if (mine == 0) continue;
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < sn; ++j) rank += (S[j] > mine) ? 1u : 0u;
-    if (rank == k - 1) *tk.thr = mine - 1;  // keys >= the k-th largest of S pass "key > thr"
-  }
-  tk.g.sync();
   // ---- 2. rounds ----
-  uint32_t b = (tk.cap / 2 - k) / G;  // the upper half of buf is scratch for compact()
+  uint32_t b = (tk.cap / 2) / G;  // at most cap/2 pushes per round
   if (b == 0) b = 1;
-  if (b > kPartialStride) b = kPartialStride;
+  if (b > 64) b = 64;
   constexpr int kMlp = 8;  // independent L2 loads in flight per thread
   for (uint32_t r = 0;; ++r) {
+    if (*tk.cnt + G * b > tk.cap) {  // uniform: cnt only changes between barriers
+      const ckey_t before = *tk.thr;
+      tk.template select<ITEMS>(k);
+      if (tid == 0 && before > *tk.thr) *tk.thr = before;
+      tk.g.sync();
+    }
     const ckey_t thr = *tk.thr;
     const uint32_t lo = r * b, total = G * b;
     bool more = false;
@@ -286,17 +412,8 @@ __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_po
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[5]));
       trace[7] = *tk.cnt;
     }
-    {
-      // compact() would replace the head bound by the k-th best of what was pushed so
-      // far; both are valid lower bounds, keep the larger one.
-      const ckey_t before = *tk.thr;
-      tk.compact(k);
-      if (tid == 0 && before > *tk.thr) *tk.thr = before;
-      tk.g.sync();
-    }
-    if (trace && tid == 0 && r == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
     if (!any_more) break;
-    // retire lists whose window ended at or below the (old) threshold, or that are exhausted
+    // retire lists whose window ended at or below the threshold, or that are exhausted
     for (uint32_t l = tid; l < G; l += T) {
       const uint32_t len = s_pos[l], last = lo + b - 1;
       if (len == 0) continue;
@@ -304,6 +421,8 @@ __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_po
     }
     tk.g.sync();
   }
+  tk.compact(k);
+  if (trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
   uint32_t n = *tk.cnt;
   for (uint32_t i = tid; i < k; i += T) {
     if (i < n) {

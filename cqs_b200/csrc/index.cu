@@ -143,7 +143,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
   cudaFree(s.d_bout_n); cudaFree(s.d_bflags); cudaFree(s.d_maxnorm);
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
   if (s.h_query) cudaFreeHost(s.h_query);
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
@@ -690,7 +690,7 @@ int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uin
   }
   for (uint32_t t = 0; t < vocab; ++t) tptr[t + 1] += tptr[t];
   std::vector<uint32_t> pdoc(nnz);
-  std::vector<float> pw(nnz);
+  std::vector<uint2> ppost(nnz);
   {
     std::vector<uint64_t> cur(tptr.begin(), tptr.end() - 1);
     for (uint64_t d = 0; d < n; ++d)
@@ -702,19 +702,21 @@ int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uin
         if (pos > tptr[tok[e]] && pdoc[pos - 1] == (uint32_t)d)
           return fail(CQS_B200_ERR_INVALID, "doc %llu lists token %u twice", (unsigned long long)d, tok[e]);
         pdoc[pos] = (uint32_t)d;
-        pw[pos] = w[e];
+        uint32_t wbits;
+        memcpy(&wbits, &w[e], 4);
+        ppost[pos] = make_uint2((uint32_t)d, wbits);
       }
   }
   CK(ix, cudaSetDevice(s.device));
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_w);
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
   s.sparse = SparseDev();
   CK(ix, cudaMalloc((void**)&s.sparse.d_tptr, sizeof(uint64_t) * ((size_t)vocab + 1)));
   CK(ix, cudaMalloc((void**)&s.sparse.d_doc, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1)));
-  CK(ix, cudaMalloc((void**)&s.sparse.d_w, sizeof(float) * std::max<uint64_t>(nnz, 1)));
+  CK(ix, cudaMalloc((void**)&s.sparse.d_post, sizeof(uint2) * std::max<uint64_t>(nnz, 1)));
   CK(ix, cudaMemcpy(s.sparse.d_tptr, tptr.data(), sizeof(uint64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice));
   if (nnz) {
     CK(ix, cudaMemcpy(s.sparse.d_doc, pdoc.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
-    CK(ix, cudaMemcpy(s.sparse.d_w, pw.data(), sizeof(float) * nnz, cudaMemcpyHostToDevice));
+    CK(ix, cudaMemcpy(s.sparse.d_post, ppost.data(), sizeof(uint2) * nnz, cudaMemcpyHostToDevice));
   }
   s.sparse.vocab = vocab;
   s.sparse.nnz = nnz;
@@ -736,6 +738,7 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
   }
   SparseArgs a;
   a.d_bounds = s.d_bounds;
+  a.d_trace = s.d_trace;
   a.sp = s.sparse; a.n_docs = s.n_rows; a.d_q_tok = s.d_q_tok; a.d_q_w = s.d_q_w; a.q_nnz = q_nnz;
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;
@@ -874,6 +877,13 @@ int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* den
     return fail(CQS_B200_ERR_INVALID, "NULL pool");
   uint32_t cap = std::min(pool_k, n_dense + n_sparse);
   if (cap == 0) return CQS_B200_OK;
+  {
+    // the fusion sort packs (row - min_row) into 32 bits
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t j = 0; j < n_dense; ++j) if (dense_rows[j] != ~0ull) { lo = std::min(lo, dense_rows[j]); hi = std::max(hi, dense_rows[j]); }
+    for (uint32_t j = 0; j < n_sparse; ++j) if (sparse_rows[j] != ~0ull) { lo = std::min(lo, sparse_rows[j]); hi = std::max(hi, sparse_rows[j]); }
+    if (hi > lo && hi - lo > 0xFFFFFFFEull) return fail(CQS_B200_ERR_UNSUPPORTED, "row ids span more than 2^32");
+  }
   cqs_b200_index* none = nullptr;
   CK(none, cudaSetDevice(device));
   // one scratch allocation: [dense rows | sparse rows | dense sc | sparse sc | counts | outputs]

@@ -93,8 +93,8 @@ cudaError_t launch_max_row_norm(const void* d_rows, uint64_t n_rows, RowLayout l
 struct SparseDev {
   // token-major postings (CSC): for token t, entries [tptr[t], tptr[t+1]) sorted by doc asc
   uint64_t* d_tptr = nullptr;   // [vocab+1]
-  uint32_t* d_doc = nullptr;    // [nnz]
-  float* d_w = nullptr;         // [nnz]
+  uint32_t* d_doc = nullptr;    // [nnz] doc ids alone (bounds pass)
+  void* d_post = nullptr;       // [nnz] (doc, weight bits) pairs (accumulate pass)
   uint32_t vocab = 0;
   uint64_t nnz = 0;
 };
@@ -105,6 +105,7 @@ struct SparseArgs {
   const float* d_q_w;
   uint32_t q_nnz;
   uint32_t* d_bounds;       // scratch, sparse_bounds_bytes(n_docs, q_nnz)
+  void* d_trace = nullptr;  // optional [kMaxGrid][8] u64 stamps (CQS_B200_TRACE=1)
   const uint32_t* d_bitset;
   uint32_t k;
   uint64_t row_base;
@@ -115,7 +116,7 @@ struct SparseArgs {
   uint64_t* d_out_rows;
   uint32_t* d_out_n;
 };
-constexpr uint32_t kSparseDocsPerBlock = 256;   // docs owned by one warp at a time
+constexpr uint32_t kSparseDocsPerBlock = 64;    // docs owned by one warp at a time
 size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz);
 cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
 

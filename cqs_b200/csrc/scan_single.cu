@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   __shared__ ckey_t s_thr;
   __shared__ uint32_t s_last;
   __shared__ uint32_t s_pos[kMaxGrid];
+  __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
 
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t n = p.n_rows;
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
 
   // ===== consumer warps =====
   const uint32_t ctid = threadIdx.x - 32, warp = ctid >> 5;
-  TopK tk{s_buf, &s_cnt, &s_thr, kCap, Group{ctid, kConsumers, 1}};
+  TopK tk{s_buf, &s_cnt, &s_thr, kCap, Group{ctid, kConsumers, 1}, s_hist};
   tk.init();
   float q[NV * E];
 #pragma unroll
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
         need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
       }
       if (tk.g.any(need)) {
-        tk.compact(k);
+        tk.template select<kCap / kConsumers>(k);
         thr = s_thr;
       }
     }
@@ -358,9 +359,9 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   TRACE(3);
   if (!s_last) return;
   __threadfence();
-  merge_partials_and_emit(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x, p.row_base,
-                          p.out_scores, p.out_rows, p.out_n,
-                          p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+  merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
+                                             p.row_base, p.out_scores, p.out_rows, p.out_n,
+                                             p.trace ? p.trace + blockIdx.x * 8 : nullptr);
   TRACE(4);
   if (ctid == 0) {
     p.done[0] = 0;

@@ -14,7 +14,8 @@
 // f32 restatement of the reference — no atomics on floating-point data anywhere.
 //
 // Sparse layout in HBM: token-major postings (CSC).  For token t the entries
-// [tptr[t], tptr[t+1]) hold (doc, weight) sorted by doc ascending — the order
+// [tptr[t], tptr[t+1]) hold (doc, weight) pairs (8-byte AoS, plus a doc-only copy
+// for the bounds pass) sorted by doc ascending — the order
 // SpladeIndex::build produces (index.rs:197-203).  A query touches only
 // sum_t |postings(t)| * 8 bytes, versus the whole 8*nnz bytes of a doc-major
 // scan.  Docs are processed in blocks of 256 owned by one warp (accumulators in
@@ -28,7 +29,7 @@
 
 namespace cqs {
 
-constexpr int kSpThreads = 256;          // 8 warps; light enough to share an SM with the dense scan CTA
+constexpr int kSpThreads = 512;          // 16 warps, 2 CTAs per SM
 constexpr int kSpWarps = kSpThreads / 32;
 constexpr uint32_t kSpCap = 4096;        // top-k accumulator slots
 constexpr uint32_t kSpMaxQ = 1024;       // max query nnz
@@ -48,17 +49,26 @@ struct BoundsParams {
   uint32_t n_blocks;
   uint32_t* bounds;  // [q_nnz][n_blocks + 1]
 };
-constexpr uint32_t kBoundsChunk = 2048;  // postings per CTA work unit
+constexpr uint32_t kBoundsChunk = 8192;  // postings per streaming work unit
+constexpr uint32_t kBoundsShort = 2048;  // lists up to this long are binary-searched per block instead
 __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p) {
   __shared__ uint64_t s_base[kSpMaxQ];
-  __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // chunks before token i
+  __shared__ uint32_t s_len[kSpMaxQ];
+  __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // work units before token i
   const uint32_t tid = threadIdx.x;
+  const uint32_t search_units = (p.n_blocks + 1 + 255) / 256;  // 256 block boundaries per unit
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
     uint64_t b0 = 0, b1 = 0;
     if (t < p.vocab) { b0 = __ldg(p.tptr + t); b1 = __ldg(p.tptr + t + 1); }
+    const uint64_t len = b1 - b0;
     s_base[i] = b0;
-    s_prefix[i + 1] = (b1 - b0 + kBoundsChunk - 1) / kBoundsChunk;  // chunk count, scanned below
+    s_len[i] = (uint32_t)len;
+    // long lists are streamed (a thread that sees the first posting of a block writes the
+    // offsets of that block and of the empty blocks before it); short lists would leave
+    // long serial fills to a few threads, so every block boundary is binary-searched.
+    s_prefix[i + 1] = len == 0 ? 0 : (len <= kBoundsShort ? search_units
+                                                         : (len + kBoundsChunk - 1) / kBoundsChunk);
   }
   __syncthreads();
   if (tid == 0) {
@@ -66,32 +76,63 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
     for (uint32_t i = 0; i < p.q_nnz; ++i) s_prefix[i + 1] += s_prefix[i];
   }
   __syncthreads();
-  const uint64_t n_chunks = s_prefix[p.q_nnz];
-  for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    uint32_t lo = 0, hi = p.q_nnz;  // token owning chunk c: last i with prefix[i] <= c
+  const uint64_t n_units = s_prefix[p.q_nnz];
+  for (uint64_t c = blockIdx.x; c < n_units; c += gridDim.x) {
+    uint32_t lo = 0, hi = p.q_nnz;  // token owning unit c: last i with prefix[i] <= c
     while (hi - lo > 1) {
       uint32_t mid = (lo + hi) >> 1;
       if (s_prefix[mid] <= c) lo = mid; else hi = mid;
     }
-    const uint32_t i = lo, t = __ldg(p.q_tok + i);
+    const uint32_t i = lo;
     const uint64_t base = s_base[i];
-    const uint32_t len = (uint32_t)(__ldg(p.tptr + t + 1) - base);
-    const uint32_t e0 = (uint32_t)(c - s_prefix[i]) * kBoundsChunk;
+    const uint32_t len = s_len[i];
+    const uint32_t unit = (uint32_t)(c - s_prefix[i]);
     uint32_t* row = p.bounds + (size_t)i * (p.n_blocks + 1);
-    for (uint32_t e = e0 + tid; e < min(len, e0 + kBoundsChunk); e += blockDim.x) {
-      const uint32_t blk = __ldg(p.doc + base + e) / kSpBlock;
-      const int prev = (e == 0) ? -1 : (int)(__ldg(p.doc + base + e - 1) / kSpBlock);
-      for (int j = prev + 1; j <= (int)blk; ++j) row[j] = e;       // first posting at or after block j
-      if (e == len - 1)
-        for (uint32_t j = blk + 1; j <= p.n_blocks; ++j) row[j] = len;  // blocks after the last posting
+    if (len <= kBoundsShort) {
+      const uint32_t j = unit * 256 + tid;  // block boundary
+      if (j <= p.n_blocks) {
+        const uint64_t target = (uint64_t)j * kSpBlock;
+        uint32_t a = 0, b = len;  // first posting with doc >= target
+        while (a < b) {
+          const uint32_t m = (a + b) >> 1;
+          if ((uint64_t)__ldg(p.doc + base + m) < target) a = m + 1; else b = m;
+        }
+        row[j] = a;
+      }
+      continue;
+    }
+    const uint32_t e0 = unit * kBoundsChunk;
+    const uint32_t e_end = min(len, e0 + kBoundsChunk);
+    const uint32_t lane = tid & 31;
+    constexpr int kU = 8;  // independent loads in flight per thread
+    for (uint32_t eb = e0; eb < e_end; eb += 256 * kU) {
+      uint32_t cur[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t e = eb + u * 256 + tid;
+        cur[u] = (e < e_end) ? __ldg(p.doc + base + e) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const uint32_t e = eb + u * 256 + tid;
+        // block of the previous posting: the neighbouring lane holds it, lane 0 re-reads it
+        uint32_t prv = __shfl_up_sync(0xffffffffu, cur[u], 1);
+        if (lane == 0 && e > 0 && e < e_end) prv = __ldg(p.doc + base + e - 1);
+        if (e >= e_end) continue;
+        const uint32_t blk = cur[u] / kSpBlock;
+        const int prev = (e == 0) ? -1 : (int)(prv / kSpBlock);
+        if (prev != (int)blk)
+          for (int j = prev + 1; j <= (int)blk; ++j) row[j] = e;     // first posting at or after block j
+        if (e == len - 1)
+          for (uint32_t j = blk + 1; j <= p.n_blocks; ++j) row[j] = len;  // blocks after the last posting
+      }
     }
   }
 }
 
 struct SparseParams {
   const uint64_t* tptr;
-  const uint32_t* doc;
-  const float* w;
+  const uint2* post;      // (doc, weight bits) pairs, token-major
   uint32_t vocab;
   uint64_t n_docs;
   const uint32_t* q_tok;
@@ -108,38 +149,38 @@ struct SparseParams {
   float* out_scores;
   uint64_t* out_rows;
   uint32_t* out_n;
+  unsigned long long* trace;  // optional [grid][8] stamps (development aid)
 };
-
-constexpr uint32_t kSpStage = 1024;      // postings staged per warp between apply phases
+#define SPTRACE(slot) do { if (p.trace && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[blockIdx.x * 8 + (slot)] = t_; } } while (0)
 
 struct SpSmem {
   ckey_t buf[kSpCap];                    // 32 KB
-  uint2 stage[kSpWarps][kSpStage];       // 64 KB  (local doc, weight bits)
-  float acc[kSpWarps][kSpBlock];         //  8 KB
-  uint8_t touched[kSpWarps][kSpBlock];   //  2 KB
-  uint32_t off[kSpWarps][36];            //  staging offsets of the tokens of the current group
+  float acc[kSpWarps][kSpBlock];         //  4 KB
+  uint8_t touched[kSpWarps][kSpBlock];   //  1 KB
   uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
   float qw[kSpMaxQ];                     //  4 KB
   uint32_t pos[kMaxGrid];                //  4 KB
+  uint32_t hist[kSelBuckets + 96];       //  8 KB  select() histogram
   ckey_t thr;
   uint32_t cnt;
   uint32_t last;
 };
 
 // ---- pass 2: accumulate + select -------------------------------------------------------
-// A warp owns a 256-doc block: its accumulators sit in shared memory.  Query tokens are
-// taken in groups whose slices (the part of each token's posting list that falls in the
-// block) fit a 1024-entry staging buffer: the group's postings are fetched with many
-// independent loads in flight, then applied IN QUERY ORDER (the reference's accumulation
-// order, index.rs:251-259): within one token the docs are distinct, so the lanes update
+// A warp owns a 64-doc block: its accumulators sit in shared memory.  For a batch of 8
+// query tokens the block's slices of their posting lists (<= 64 postings each, a doc lists
+// a token once) are fetched into registers with all loads in flight, then applied IN
+// QUERY ORDER (the reference's accumulation order, index.rs:251-259): within one token
+// the docs are distinct, so the lanes update
 //   acc[doc] = acc[doc] + qw*dw   (separate f32 multiply and add)
 // without conflicts, and only a __syncwarp separates tokens.  Touched docs that pass the
 // filter go to the CTA's top-k accumulator.
-__global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseParams p) {
+constexpr int kSpBatch = 8;
+__global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const SparseParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpSmem& s = *reinterpret_cast<SpSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}};
+  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}, s.hist};
   tk.init();
   for (uint32_t i = tid; i < p.q_nnz; i += kSpThreads) {
     const uint32_t t = __ldg(p.q_tok + i);
@@ -147,13 +188,12 @@ __global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseP
     s.qw[i] = __ldg(p.q_w + i);
   }
   __syncthreads();
+  SPTRACE(0);
   const uint32_t k = p.k;
   const uint32_t stride = p.n_blocks + 1;
   const uint32_t n_steps = (p.n_blocks + kSpWarps - 1) / kSpWarps;
   float* acc = s.acc[warp];
   uint8_t* touched = s.touched[warp];
-  uint2* stage = s.stage[warp];
-  uint32_t* off = s.off[warp];
   for (uint32_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
     const uint32_t blk = step * kSpWarps + warp;
     const ckey_t thr = s.thr;
@@ -172,81 +212,39 @@ __global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseP
           lo = __ldg(row);
           hi = __ldg(row + 1);
         }
-        const uint32_t len = hi - lo;           // <= 256 (a doc lists a token once)
-        uint32_t incl = len;                    // inclusive warp scan of the slice lengths
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= (uint32_t)o) incl += v;
-        }
-        uint32_t done_tok = 0;                  // tokens of this 32-group already applied
-        uint32_t consumed = 0;                  // postings of this 32-group already applied
         const uint32_t n_tok = min(32u, p.q_nnz - i0);
-        while (done_tok < n_tok) {
-          // group = maximal run of tokens from done_tok whose postings fit the staging buffer
-          const uint32_t fits = __ballot_sync(0xffffffffu, lane >= done_tok && lane < n_tok &&
-                                                               incl - consumed <= kSpStage);
-          const uint32_t g1 = done_tok + __popc(fits);        // tokens [done_tok, g1)
-          __syncwarp();
-          if (lane >= done_tok && lane < g1) off[lane - done_tok + 1] = incl - consumed;
-          if (lane == 0) off[0] = 0;
-          __syncwarp();
-          const uint32_t g_n = g1 - done_tok;
-          const uint32_t total = off[g_n];
-          // fetch: flat posting index -> (token, offset); 8 postings per lane in flight
-          for (uint32_t f0 = 0; f0 < total; f0 += 32 * 8) {
-            uint32_t dd[8];
-            float ww[8];
+        for (uint32_t j0 = 0; j0 < n_tok; j0 += kSpBatch) {
+          uint2 pp[kSpBatch][2];
+          uint32_t ln[kSpBatch];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t f = f0 + u * 32 + lane;
-              dd[u] = 0xFFFFFFFFu;
-              ww[u] = 0.f;
-              if (f < total) {
-                uint32_t a = 0, b = g_n;        // token t with off[t] <= f < off[t+1]
-                while (b - a > 1) {
-                  const uint32_t m = (a + b) >> 1;
-                  if (off[m] <= f) a = m; else b = m;
-                }
-                dd[u] = a;                      // token index inside the group, resolved after the loop
-                ww[u] = __uint_as_float(f - off[a]);
-              }
-            }
-            // resolve addresses (needs the slice start of the owning token, held by another lane)
+          for (int u = 0; u < kSpBatch; ++u) {
+            const uint32_t tl = __shfl_sync(0xffffffffu, lo, (j0 + u) & 31);
+            const uint32_t th = __shfl_sync(0xffffffffu, hi, (j0 + u) & 31);
+            ln[u] = (j0 + u < n_tok) ? th - tl : 0;   // <= 64
+            const uint64_t e = s.base[min(i0 + j0 + u, p.q_nnz - 1)] + tl + lane;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t f = f0 + u * 32 + lane;
-              const uint32_t tsel = (f < total) ? dd[u] : 0;
-              const uint32_t tok_lo = __shfl_sync(0xffffffffu, lo, done_tok + tsel);
-              if (f < total) {
-                const uint64_t e = s.base[i0 + done_tok + tsel] + tok_lo + __float_as_uint(ww[u]);
-                dd[u] = __ldg(p.doc + e) - d0;
-                ww[u] = __ldg(p.w + e);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t f = f0 + u * 32 + lane;
-              if (f < total) stage[f] = make_uint2(dd[u], __float_as_uint(ww[u]));
+            for (int h = 0; h < 2; ++h) {
+              pp[u][h] = make_uint2(0u, 0u);
+              if (lane + 32 * h < ln[u]) pp[u][h] = __ldg(p.post + e + 32 * h);
             }
           }
-          __syncwarp();
-          // apply the group's tokens in query order
-          for (uint32_t t = 0; t < g_n; ++t) {
-            const float qw = s.qw[i0 + done_tok + t];
-            const uint32_t e1 = off[t + 1];
-            for (uint32_t e = off[t] + lane; e < e1; e += 32) {
-              const uint2 ent = stage[e];
-              // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
-              acc[ent.x] = __fadd_rn(acc[ent.x], __fmul_rn(qw, __uint_as_float(ent.y)));
-              touched[ent.x] = 1;
-            }
+#pragma unroll
+          for (int u = 0; u < kSpBatch; ++u) {
+            if (ln[u] == 0) continue;  // warp-uniform
+            const float qw = s.qw[i0 + j0 + u];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (lane + 32 * h < ln[u]) {
+                const uint32_t d = pp[u][h].x - d0;
+                // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
+                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][h].y)));
+                touched[d] = 1;
+              }
             __syncwarp();
           }
-          consumed += total;
-          done_tok = g1;
         }
       }
+      __syncwarp();
       // candidates: touched docs that pass the filter, finite score (candidate.rs:275)
       for (uint32_t d = lane; d < kSpBlock; d += 32) {
         const uint64_t r = (uint64_t)d0 + d;
@@ -259,11 +257,16 @@ __global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseP
       }
     }
     __syncthreads();
-    // at most kSpWarps*kSpBlock = 2048 pushes per step
-    if (s.cnt + kSpWarps * kSpBlock > kSpCap || (s.thr == 0 && s.cnt >= k)) tk.compact(k);
+    if (step == blockIdx.x) SPTRACE(1);
+    // at most kSpWarps*kSpBlock = 1024 pushes per step
+    if (s.cnt + kSpWarps * kSpBlock > kSpCap || (s.thr == 0 && s.cnt >= k))
+      tk.template select<kSpCap / kSpThreads>(k);
     __syncthreads();
+    if (step == blockIdx.x) SPTRACE(2);
   }
+  SPTRACE(3);
   tk.compact(k);
+  SPTRACE(4);
   const uint32_t mycnt = s.cnt;
   for (uint32_t i = tid; i < mycnt; i += kSpThreads)
     p.partial[(size_t)blockIdx.x * kMaxK + i] = s.buf[i];
@@ -277,8 +280,9 @@ __global__ void __launch_bounds__(kSpThreads) sparse_search_kernel(const SparseP
   __syncthreads();
   if (!s.last) return;
   __threadfence();
-  merge_partials_and_emit(tk, s.pos, k, p.partial, p.partial_cnt, gridDim.x, p.row_base,
-                          p.out_scores, p.out_rows, p.out_n);
+  merge_partials_and_emit<kSpCap / kSpThreads>(tk, s.pos, k, p.partial, p.partial_cnt, gridDim.x,
+                                               p.row_base, p.out_scores, p.out_rows, p.out_n);
+  SPTRACE(5);
   if (tid == 0) *p.done = 0;
 }
 
@@ -298,14 +302,15 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(a.d_bounds, 0, sparse_bounds_bytes(a.n_docs, a.q_nnz), st);
   if (e != cudaSuccess) return e;
   BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds};
-  sparse_bounds_kernel<<<sms * 4, 256, 0, st>>>(bp);
+  sparse_bounds_kernel<<<sms * 6, 256, 0, st>>>(bp);
   SparseParams p;
-  p.tptr = a.sp.d_tptr; p.doc = a.sp.d_doc; p.w = a.sp.d_w; p.vocab = a.sp.vocab;
+  p.tptr = a.sp.d_tptr; p.post = (const uint2*)a.sp.d_post; p.vocab = a.sp.vocab;
   p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
   p.bounds = a.d_bounds; p.n_blocks = n_blocks;
   p.bitset = a.d_bitset; p.k = a.k; p.row_base = a.row_base;
   p.partial = a.d_partial; p.partial_cnt = a.d_partial_cnt; p.done = a.d_done;
   p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
+  p.trace = (unsigned long long*)a.d_trace;
   const uint32_t n_steps = (n_blocks + kSpWarps - 1) / kSpWarps;
   int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
   if (grid > (int)kMaxGrid) grid = kMaxGrid;
@@ -320,123 +325,117 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------
 // alpha fusion (src/search/query.rs:914-1005), one CTA, pools <= 1024 each.
 // ---------------------------------------------------------------------------
-constexpr uint32_t kFuseMax = kMaxK;       // per pool
-constexpr uint32_t kFuseN = 2 * kFuseMax;  // union upper bound (power of two)
+// The reference builds two HashMaps (id -> dense score, id -> normalised sparse score; a
+// later duplicate overwrites), walks the union in insertion order and sorts by
+// (fused desc, id asc).  Here: one open-addressing table in shared memory keyed by row
+// ("last index wins" via atomicMax on (index, score bits)), one pass over the table to
+// form (fused, row) keys, the register/shuffle block sort, and a table lookup per output
+// row for the per-leg values.  Every f32 step keeps the reference's operation order.
+constexpr uint32_t kFuseMax = kMaxK;           // per pool
+constexpr uint32_t kFuseSlots = 4096;          // >= 2 * (2 * kFuseMax) entries' worth of slots
+constexpr uint32_t kFuseThreads = 1024;
+constexpr uint64_t kFuseEmpty = ~0ull;
 
 struct FuseSmem {
-  uint64_t drow[kFuseMax];
-  uint64_t srow[kFuseMax];
-  float dsc[kFuseMax];
-  float ssc[kFuseMax];
-  uint64_t key[kFuseN];   // (1<<32 | ordered fused) or 0 when empty
-  uint64_t row[kFuseN];
-  uint32_t src[kFuseN];   // payload: dense idx | sparse idx<<12 | flags<<24
-  float red[32];
+  unsigned long long hrow[kFuseSlots];   // 32 KB
+  unsigned long long hd[kFuseSlots];     // (index + 1) << 32 | dense score bits, 0 = not in the dense pool
+  unsigned long long hs[kFuseSlots];     // same for the raw sparse score
+  ckey_t keys[2 * kFuseMax];             // 16 KB
+  unsigned long long row_min;
+  uint32_t n_union;
   float max_sparse;
 };
 
-__device__ __forceinline__ float f32_max_rust(float a, float b) {
-  // f32::max: if one operand is NaN the other is returned
-  return fmaxf(a, b);
+__device__ __forceinline__ uint32_t fuse_hash(uint64_t row) {
+  return (uint32_t)((row * 0x9E3779B97F4A7C15ull) >> 52);  // 12 bits
+}
+__device__ __forceinline__ uint32_t fuse_find(const FuseSmem& s, uint64_t row) {
+  uint32_t slot = fuse_hash(row);
+  while (s.hrow[slot] != row) slot = (slot + 1) & (kFuseSlots - 1);
+  return slot;
+}
+__device__ __forceinline__ uint32_t fuse_insert(FuseSmem& s, uint64_t row) {
+  uint32_t slot = fuse_hash(row);
+  while (true) {
+    const unsigned long long prev = atomicCAS(&s.hrow[slot], kFuseEmpty, row);
+    if (prev == kFuseEmpty || prev == row) return slot;
+    slot = (slot + 1) & (kFuseSlots - 1);
+  }
 }
 
-__global__ void __launch_bounds__(1024, 1) fuse_pools_kernel(const FuseArgs a) {
+__global__ void __launch_bounds__(kFuseThreads, 1) fuse_pools_kernel(const FuseArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   FuseSmem& s = *reinterpret_cast<FuseSmem*>(smem_raw);
-  const uint32_t tid = threadIdx.x, T = blockDim.x;
+  const uint32_t tid = threadIdx.x, T = kFuseThreads;
   const uint32_t nd = min(*a.d_n_dense, kFuseMax), ns = min(*a.d_n_sparse, kFuseMax);
-  for (uint32_t i = tid; i < nd; i += T) { s.drow[i] = a.d_dense_rows[i]; s.dsc[i] = a.d_dense_scores[i]; }
-  for (uint32_t i = tid; i < ns; i += T) { s.srow[i] = a.d_sparse_rows[i]; s.ssc[i] = a.d_sparse_scores[i]; }
-  for (uint32_t i = tid; i < kFuseN; i += T) { s.key[i] = 0; s.row[i] = ~0ull; s.src[i] = 0; }
-  __syncthreads();
-  // max_sparse = iter().map(score).reduce(f32::max).unwrap_or(0.0)   (query.rs:914-919)
-  // (max is associative/commutative up to the sign of zero; NaN-ignoring)
+  for (uint32_t i = tid; i < kFuseSlots; i += T) {
+    s.hrow[i] = kFuseEmpty;
+    s.hd[i] = 0;
+    s.hs[i] = 0;
+  }
+  for (uint32_t i = tid; i < 2 * kFuseMax; i += T) s.keys[i] = 0;
+  if (tid == 0) {
+    s.row_min = ~0ull;
+    s.n_union = 0;
+  }
+  // max_sparse = iter().map(score).reduce(f32::max).unwrap_or(0.0)   (query.rs:914-919);
+  // f32::max ignores NaN, and max is order independent up to the sign of zero
   if (tid < 32) {
     float m = __uint_as_float(0x7FC00000u);  // NaN = identity of a NaN-ignoring max
-    for (uint32_t i = tid; i < ns; i += 32) m = f32_max_rust(m, s.ssc[i]);
-    for (int off = 16; off > 0; off >>= 1) m = f32_max_rust(m, __shfl_xor_sync(0xffffffffu, m, off));
+    for (uint32_t i = tid; i < ns; i += 32) m = fmaxf(m, a.d_sparse_scores[i]);
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (tid == 0) s.max_sparse = (ns == 0) ? 0.f : m;
+  }
+  __syncthreads();
+  // insert both pools: HashMap::insert semantics, a later duplicate overwrites
+  for (uint32_t i = tid; i < nd + ns; i += T) {
+    const bool dense = i < nd;
+    const uint32_t j = dense ? i : i - nd;
+    const uint64_t row = dense ? a.d_dense_rows[j] : a.d_sparse_rows[j];
+    if (row == kFuseEmpty) continue;
+    const uint32_t bits = __float_as_uint(dense ? a.d_dense_scores[j] : a.d_sparse_scores[j]);
+    const uint32_t slot = fuse_insert(s, row);
+    atomicMax(dense ? &s.hd[slot] : &s.hs[slot], ((unsigned long long)(j + 1) << 32) | bits);
+    atomicMin(&s.row_min, (unsigned long long)row);
   }
   __syncthreads();
   const float max_sparse = s.max_sparse;
   const float alpha = a.alpha;
-  // one thread per union slot: slots [0,nd) dense entries, [nd, nd+ns) sparse-only entries
-  for (uint32_t i = tid; i < nd + ns; i += T) {
-    float d = 0.f, sraw = 0.f, sn = 0.f;
-    uint64_t row;
-    uint32_t flags = 0;
-    bool emit = true;
-    if (i < nd) {
-      row = s.drow[i];
-      // HashMap::insert: a later duplicate overwrites; emit only the last occurrence
-      for (uint32_t j = i + 1; j < nd; ++j) if (s.drow[j] == row) { emit = false; break; }
-      d = s.dsc[i];
-      flags = 1;
-      for (uint32_t j = 0; j < ns; ++j) if (s.srow[j] == row) { sraw = s.ssc[j]; flags = 3; }
-    } else {
-      uint32_t j0 = i - nd;
-      row = s.srow[j0];
-      for (uint32_t j = j0 + 1; j < ns; ++j) if (s.srow[j] == row) { emit = false; break; }
-      for (uint32_t j = 0; j < nd && emit; ++j) if (s.drow[j] == row) emit = false;
-      sraw = s.ssc[j0];
-      flags = 2;
-    }
-    if (!emit) continue;
-    if (flags & 2) sn = (max_sparse > 0.f) ? __fdiv_rn(sraw, max_sparse) : 0.f;
+  const uint64_t row_min = s.row_min;
+  for (uint32_t slot = tid; slot < kFuseSlots; slot += T) {
+    const uint64_t row = s.hrow[slot];
+    if (row == kFuseEmpty) continue;
+    const unsigned long long pd = s.hd[slot], ps = s.hs[slot];
+    const float d = pd ? __uint_as_float((uint32_t)pd) : 0.f;          // unwrap_or(0.0)
+    float sn = 0.f;
+    if (ps) sn = (max_sparse > 0.f) ? __fdiv_rn(__uint_as_float((uint32_t)ps), max_sparse) : 0.f;
     float fused;
     if (alpha <= 0.f)
       fused = __fadd_rn(d, __fmul_rn(sn, 0.1f));
     else
       fused = __fadd_rn(__fmul_rn(alpha, d), __fmul_rn(__fsub_rn(1.0f, alpha), sn));
-    s.key[i] = (1ull << 32) | (uint64_t)ordered_u32(__float_as_uint(fused));
-    s.row[i] = row;
-    s.src[i] = i;
-    // stash per-leg values in the (now consumed) score arrays' slots via registers:
-    // we re-derive them at output time from src, so keep flags in the top bits.
-    s.src[i] |= flags << 24;
+    ckey_t key = ((ckey_t)ordered_u32(__float_as_uint(fused)) << 32) | (ckey_t)(~(uint32_t)(row - row_min));
+    if (key == 0) key = 1;
+    s.keys[atomicAdd(&s.n_union, 1u)] = key;
   }
   __syncthreads();
   // sort (fused desc by total order, row asc)   (query.rs:1004)
-  const uint32_t P = next_pow2(max(nd + ns, 1u));
-  for (uint32_t size = 2; size <= P; size <<= 1)
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t i = tid; i < (P >> 1); i += T) {
-        uint32_t pos = 2 * i - (i & (stride - 1));
-        uint64_t ka = s.key[pos], kb = s.key[pos + stride];
-        uint64_t ra = s.row[pos], rb = s.row[pos + stride];
-        bool b_first = kb > ka || (kb == ka && rb < ra);
-        bool dir = ((pos & size) == 0);
-        if (b_first == dir) {
-          uint32_t sa = s.src[pos], sb = s.src[pos + stride];
-          s.key[pos] = kb; s.row[pos] = rb; s.src[pos] = sb;
-          s.key[pos + stride] = ka; s.row[pos + stride] = ra; s.src[pos + stride] = sa;
-        }
-      }
-      __syncthreads();
-    }
-  __shared__ uint32_t s_n;
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < a.pool_k && i < P; i += T) {
-    if (s.key[i] == 0) continue;
-    uint32_t src = s.src[i] & 0xFFFFFFu, flags = s.src[i] >> 24;
-    uint64_t row = s.row[i];
-    float d = 0.f, sraw = 0.f;
-    if (src < nd) {
-      d = s.dsc[src];
-      if (flags & 2) for (uint32_t j = 0; j < ns; ++j) if (s.srow[j] == row) sraw = s.ssc[j];
-    } else {
-      sraw = s.ssc[src - nd];
-    }
+  const uint32_t n_union = s.n_union;
+  const uint32_t P = max(next_pow2(n_union), kSortChunk);
+  block_sort_desc(Group{tid, T, 0}, s.keys, P);
+  const uint32_t n_out = min(n_union, a.pool_k);
+  for (uint32_t i = tid; i < n_out; i += T) {
+    const ckey_t key = s.keys[i];
+    const uint64_t row = row_min + (uint64_t)(~(uint32_t)key);
+    const uint32_t slot = fuse_find(s, row);
+    const unsigned long long pd = s.hd[slot], ps = s.hs[slot];
     a.d_out_rows[i] = row;
-    a.d_out_fused[i] = __uint_as_float(unordered_u32((uint32_t)s.key[i]));
-    a.d_out_dense[i] = d;
-    a.d_out_sparse_raw[i] = sraw;
-    a.d_out_present[i] = (uint8_t)flags;
-    atomicAdd(&s_n, 1u);
+    a.d_out_fused[i] = __uint_as_float(unordered_u32((uint32_t)(key >> 32)));
+    a.d_out_dense[i] = pd ? __uint_as_float((uint32_t)pd) : 0.f;
+    a.d_out_sparse_raw[i] = ps ? __uint_as_float((uint32_t)ps) : 0.f;
+    a.d_out_present[i] = (uint8_t)((pd ? 1 : 0) | (ps ? 2 : 0));
   }
-  __syncthreads();
-  if (tid == 0) *a.d_out_n = s_n;
+  if (tid == 0) *a.d_out_n = n_out;
 }
 
 cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t st) {
@@ -444,7 +443,7 @@ cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t st) {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(FuseSmem));
   if (e != cudaSuccess) return e;
-  fuse_pools_kernel<<<1, 1024, sizeof(FuseSmem), st>>>(a);
+  fuse_pools_kernel<<<1, kFuseThreads, sizeof(FuseSmem), st>>>(a);
   g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
