@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcqs_b200.so")
+LIB_PATH = os.environ.get("CQS_B200_LIB") or os.path.join(_HERE, "libcqs_b200.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_POISONED, ERR_OOM, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -32,6 +32,9 @@ SIGNATURES = {
     "cqs_b200_reopen": (C.c_int, [vp]),
     "cqs_b200_destroy": (None, [vp]),
     "cqs_b200_search": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, vp]),
+    "cqs_b200_set_row_meta": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "cqs_b200_set_row_signals": (C.c_int, [vp, vp, vp, C.c_uint64]),
+    "cqs_b200_search_filtered": (C.c_int, [vp, vp, C.c_uint32, C.c_float, vp, vp, C.c_int, vp, vp, vp]),
     "cqs_b200_search_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_sparse_attach": (C.c_int, [vp, vp, vp, vp, C.c_uint32]),
     "cqs_b200_search_sparse": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),

@@ -89,6 +89,11 @@ struct Shard {
   uint32_t* d_bflags = nullptr;   // [kBatchMaxQ]
   float* d_maxnorm = nullptr;     // [1]
   float max_row_norm = 0.f;
+  // structured filter / per-row signals (cqs_b200_set_row_meta / _signals)
+  uint8_t* d_ctype = nullptr;
+  uint8_t* d_lang = nullptr;
+  float* d_note_boost = nullptr;
+  float* d_importance = nullptr;
   SparseDev sparse;
 };
 
@@ -109,6 +114,7 @@ struct cqs_b200_index {
   uint64_t row_base = 0;
   uint64_t n_rows = 0, reserved = 0, rows_per_shard = 0;
   float last_kernel_ms = 0.f;
+  float max_note_boost = 1.f, max_importance = 1.f;
   uint32_t last_batch_reruns = 0;  // queries the batched path sent to the exact kernel (cumulative)
   float last_batch_ms = 0.f;       // device time of the most recent tensor-core batch pipeline
   std::vector<Shard> shards;
@@ -143,6 +149,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
   cudaFree(s.d_bout_n); cudaFree(s.d_bflags); cudaFree(s.d_maxnorm);
+  cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
   cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
   if (s.h_query) cudaFreeHost(s.h_query);
   if (s.h_out) cudaFreeHost(s.h_out);
@@ -425,7 +432,7 @@ static uint32_t host_ordered(float f) {
 // Upload query + (slice of) bitset to a shard and launch the dense scan into the
 // shard's dense pool buffers.  Asynchronous on s.stream.
 static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
-                        const uint32_t* bitset) {
+                        const uint32_t* bitset, const ScanSignals* sig = nullptr) {
   CK(ix, cudaSetDevice(s.device));
   memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
   memcpy(s.h_query, query, sizeof(float) * ix->dim);
@@ -444,6 +451,7 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
   a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
   a.d_trace = s.d_trace;
+  a.signals = sig;
   CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
   CK(ix, cudaEventRecord(s.ev1, s.stream));
@@ -457,8 +465,11 @@ static int check_searchable(cqs_b200_index* ix) {
   return 0;
 }
 
-int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
-                    uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+// sig_template (nullable): structured filter / signal fold; the per-shard device arrays are
+// filled in here.
+static int search_impl(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
+                       const ScanSignals* sig_template, uint64_t* out_rows, float* out_scores,
+                       uint32_t* out_n) {
   if (out_n) *out_n = 0;
   int rc = check_searchable(ix);
   if (rc) return rc;
@@ -472,7 +483,16 @@ int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const ui
   for (auto& s : ix->shards)
     if (s.n_rows) live.push_back(&s);
   for (Shard* s : live) {
-    rc = launch_dense(ix, *s, query, k, bitset);
+    ScanSignals sig;
+    if (sig_template) {
+      sig = *sig_template;
+      sig.d_ctype = s->d_ctype;
+      sig.d_lang = s->d_lang;
+      sig.d_note_boost = sig.pipeline ? s->d_note_boost : nullptr;
+      sig.d_importance = (sig.pipeline && sig_template->d_importance) ? s->d_importance : nullptr;
+      if (!sig.d_importance) sig.max_importance = 1.f;
+    }
+    rc = launch_dense(ix, *s, query, k, bitset, sig_template ? &sig : nullptr);
     if (rc) return rc;
     float* hs = (float*)s->h_out;
     uint64_t* hr = (uint64_t*)(s->h_out + sizeof(float) * kMaxK);
@@ -516,6 +536,96 @@ int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const ui
   }
   *out_n = n;
   return CQS_B200_OK;
+}
+
+int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
+                    uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+  return search_impl(ix, query, k, bitset, nullptr, out_rows, out_scores, out_n);
+}
+
+static int upload_rows_u8(cqs_b200_index* ix, uint8_t* Shard::*field, const uint8_t* src, uint64_t n) {
+  for (auto& s : ix->shards) {
+    CK(ix, cudaSetDevice(s.device));
+    cudaFree(s.*field);
+    s.*field = nullptr;
+    if (!src || s.n_rows == 0) continue;
+    CK(ix, cudaMalloc((void**)&(s.*field), s.n_rows));
+    CK(ix, cudaMemcpy(s.*field, src + s.first_row, s.n_rows, cudaMemcpyHostToDevice));
+  }
+  (void)n;
+  return CQS_B200_OK;
+}
+static int upload_rows_f32(cqs_b200_index* ix, float* Shard::*field, const float* src) {
+  for (auto& s : ix->shards) {
+    CK(ix, cudaSetDevice(s.device));
+    cudaFree(s.*field);
+    s.*field = nullptr;
+    if (!src || s.n_rows == 0) continue;
+    CK(ix, cudaMalloc((void**)&(s.*field), s.n_rows * sizeof(float)));
+    CK(ix, cudaMemcpy(s.*field, src + s.first_row, s.n_rows * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return CQS_B200_OK;
+}
+
+int cqs_b200_set_row_meta(cqs_b200_index* ix, const uint8_t* chunk_type, const uint8_t* lang,
+                          uint64_t n_rows) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
+  if (n_rows != ix->n_rows) return fail(CQS_B200_ERR_INVALID, "n_rows != len");
+  if ((chunk_type == nullptr) != (lang == nullptr))
+    return fail(CQS_B200_ERR_INVALID, "chunk_type and lang must both be given or both be NULL");
+  int rc = upload_rows_u8(ix, &Shard::d_ctype, chunk_type, n_rows);
+  if (rc) return rc;
+  return upload_rows_u8(ix, &Shard::d_lang, lang, n_rows);
+}
+
+int cqs_b200_set_row_signals(cqs_b200_index* ix, const float* note_boost, const float* importance,
+                             uint64_t n_rows) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
+  if (n_rows != ix->n_rows) return fail(CQS_B200_ERR_INVALID, "n_rows != len");
+  float mb = 1.f, mi = 1.f;
+  for (uint64_t r = 0; r < n_rows; ++r) {
+    if (note_boost) {
+      if (!(note_boost[r] >= 0.f) || !isfinite(note_boost[r]))
+        return fail(CQS_B200_ERR_INVALID, "note_boost[%llu] must be finite and >= 0", (unsigned long long)r);
+      mb = std::max(mb, note_boost[r]);
+    }
+    if (importance) {
+      if (!(importance[r] >= 0.f) || !isfinite(importance[r]))
+        return fail(CQS_B200_ERR_INVALID, "importance[%llu] must be finite and >= 0", (unsigned long long)r);
+      mi = std::max(mi, importance[r]);
+    }
+  }
+  ix->max_note_boost = mb;
+  ix->max_importance = mi;
+  int rc = upload_rows_f32(ix, &Shard::d_note_boost, note_boost);
+  if (rc) return rc;
+  return upload_rows_f32(ix, &Shard::d_importance, importance);
+}
+
+int cqs_b200_search_filtered(cqs_b200_index* ix, const float* query, uint32_t limit,
+                             float threshold, const uint64_t* type_mask, const uint64_t* lang_mask,
+                             int enable_demotion, uint64_t* out_rows, float* out_scores,
+                             uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  const bool have_meta = !ix->shards.empty() && ix->shards[0].d_ctype != nullptr;
+  if ((type_mask || lang_mask) && !have_meta && ix->n_rows)
+    return fail(CQS_B200_ERR_INVALID, "type/language filter requested but cqs_b200_set_row_meta was not called");
+  ScanSignals sig;
+  if (type_mask) memcpy(sig.type_mask, type_mask, 32);
+  if (lang_mask) memcpy(sig.lang_mask, lang_mask, 32);
+  sig.pipeline = 1;
+  sig.threshold = threshold;
+  sig.max_note_boost = ix->max_note_boost;
+  sig.max_importance = ix->max_importance;
+  // non-null marker: search_impl substitutes the per-shard array when demotion is on
+  sig.d_importance = enable_demotion ? reinterpret_cast<const float*>(1) : nullptr;
+  int rc = search_impl(ix, query, limit, nullptr, &sig, out_rows, out_scores, out_n);
+  return rc;
 }
 
 int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,

@@ -27,6 +27,21 @@ struct RowLayout {
 // Returns false when dim is unsupported (0 or > 2048).
 bool choose_layout(uint32_t dim, int storage, RowLayout* out);
 
+// Optional structured filter + per-row score signals: the string-free part of
+// Store::search_filtered (src/search/query.rs:348-510, candidate.rs:420-562) on device.
+struct ScanSignals {
+  const uint8_t* d_ctype = nullptr;   // per-row chunk-type code (nullable = no type filter)
+  const uint8_t* d_lang = nullptr;    // per-row language code
+  uint64_t type_mask[4] = {~0ull, ~0ull, ~0ull, ~0ull};  // bit c set = code c passes
+  uint64_t lang_mask[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  const float* d_note_boost = nullptr;  // per-row 1 + sentiment*0.15 (nullable = 1.0)
+  const float* d_importance = nullptr;  // per-row 0.70 / 0.80 / 1.0 (nullable or demotion off = skipped)
+  float max_note_boost = 1.f;           // upper bounds used to skip rows that cannot qualify
+  float max_importance = 1.f;
+  float threshold = 0.f;                // ThresholdGate: keep score >= threshold
+  int pipeline = 0;                     // 1 = clamp / note boost / demotion / threshold fold
+};
+
 struct ScanArgs {
   const void* d_rows;       // [n_rows][ld] f32 or bf16
   uint64_t n_rows;          // <= 2^32 - 1
@@ -42,6 +57,7 @@ struct ScanArgs {
   uint64_t* d_out_rows;     // [k]
   uint32_t* d_out_n;        // [1]
   void* d_trace = nullptr;  // optional [kMaxGrid][8] u64 timestamps (CQS_B200_TRACE=1)
+  const ScanSignals* signals = nullptr;
 };
 // Kernel 1+3: single-query streaming scan with the top-k select fused in.
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);

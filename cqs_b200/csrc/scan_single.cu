@@ -87,6 +87,7 @@ struct ScanParams {
   uint64_t* out_rows;
   uint32_t* out_n;
   unsigned long long* trace;  // optional [grid][8] globaltimer stamps (development aid)
+  ScanSignals sig;            // structured filter + per-row signals (sig.pipeline / sig.d_ctype gate them)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -294,7 +295,30 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
       const uint32_t bits = __float_as_uint(mine);
       bool ok = finite_bits(bits);
       if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
-      if (ok) mykey = make_key(mine, (uint32_t)r);
+      float sc = mine;
+      if (ok && (p.sig.pipeline || p.sig.d_ctype)) {
+        // Store::search_filtered on device: SQL-style type/language filter, then the
+        // score fold base = clamp(cos,0,1); max(base,0)*note_boost; *importance; >= threshold
+        // (candidate.rs:420-562) applied BEFORE the top-k, in the reference's op order.
+        const float base = p.sig.pipeline ? fminf(fmaxf(mine, 0.f), 1.f) : mine;
+        // cheap upper bound first: a row that cannot beat the current k-th key needs no loads
+        const float ub = p.sig.pipeline
+                             ? __fmul_rn(__fmul_rn(base, p.sig.max_note_boost), p.sig.max_importance)
+                             : mine;
+        ok = make_key(ub, 0u) > (SMALLK ? wthr : thr);
+        if (ok && p.sig.d_ctype) {
+          const uint32_t ct = __ldg(p.sig.d_ctype + r), lg = __ldg(p.sig.d_lang + r);
+          ok = ((p.sig.type_mask[ct >> 6] >> (ct & 63)) & 1ull) && ((p.sig.lang_mask[lg >> 6] >> (lg & 63)) & 1ull);
+        }
+        if (ok && p.sig.pipeline) {
+          sc = base;
+          if (p.sig.d_note_boost) sc = __fmul_rn(fmaxf(sc, 0.f), __ldg(p.sig.d_note_boost + r));
+          else sc = fmaxf(sc, 0.f);
+          if (p.sig.d_importance) sc = __fmul_rn(sc, __ldg(p.sig.d_importance + r));
+          ok = sc >= p.sig.threshold;
+        }
+      }
+      if (ok) mykey = make_key(sc, (uint32_t)r);
     }
     if (SMALLK) {
 #pragma unroll
@@ -443,6 +467,7 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.out_rows = a.d_out_rows;
   p.out_n = a.d_out_n;
   p.trace = (unsigned long long*)a.d_trace;
+  if (a.signals) p.sig = *a.signals;
   switch (a.layout.mode) {
     case 0: return launch_mode<0>(p, a.layout.nv, num_sms, st);
     case 1: return launch_mode<1>(p, a.layout.nv, num_sms, st);

@@ -166,6 +166,42 @@ class B200Index:
         except capi.B200Error:
             return []
 
+    # ---- Store::search_filtered on device (src/search/query.rs:316-510) -------------
+    def set_row_meta(self, chunk_type, lang) -> None:
+        ct = None if chunk_type is None else np.ascontiguousarray(chunk_type, dtype=np.uint8)
+        lg = None if lang is None else np.ascontiguousarray(lang, dtype=np.uint8)
+        check(lib.cqs_b200_set_row_meta(self._h, ptr(ct), ptr(lg), len(self)))
+
+    def set_row_signals(self, note_boost=None, importance=None) -> None:
+        nb = None if note_boost is None else np.ascontiguousarray(note_boost, dtype=np.float32)
+        im = None if importance is None else np.ascontiguousarray(importance, dtype=np.float32)
+        check(lib.cqs_b200_set_row_signals(self._h, ptr(nb), ptr(im), len(self)))
+
+    @staticmethod
+    def _mask256(codes):
+        if codes is None:
+            return None
+        m = np.zeros(4, np.uint64)
+        for c in codes:
+            m[int(c) >> 6] |= np.uint64(1) << np.uint64(int(c) & 63)
+        return m
+
+    def search_filtered_rows(self, query, limit: int, threshold: float = 0.0, include_types=None,
+                             languages=None, enable_demotion: bool = True):
+        """search_filtered(query, filter, limit, threshold) with SearchFilter::default()-style
+        signals (no name matcher / glob): returns (rows, folded scores)."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self._dim:
+            return np.empty(0, np.uint64), np.empty(0, np.float32)
+        kk = max(int(limit), 0)
+        rows = np.empty(max(kk, 1), np.uint64)
+        scores = np.empty(max(kk, 1), np.float32)
+        n = C.c_uint32(0)
+        tm, lm = self._mask256(include_types), self._mask256(languages)
+        check(lib.cqs_b200_search_filtered(self._h, ptr(q), kk, float(threshold), ptr(tm), ptr(lm),
+                                           int(bool(enable_demotion)), ptr(rows), ptr(scores), C.byref(n)))
+        return rows[: n.value].copy(), scores[: n.value].copy()
+
     # ---- inherent (no trait counterpart) ---------------------------------------
     def search_batch_rows(self, queries: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
         q = np.ascontiguousarray(queries, dtype=np.float32)

@@ -87,6 +87,29 @@ void cqs_b200_destroy(cqs_b200_index* ix); /* syncs all streams first (src/cagra
 int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
                     uint64_t* out_rows, float* out_scores, uint32_t* out_n);
 
+/* ---- Store::search_filtered on the device (src/search/query.rs:316-510) ----------------
+ * The brute-force callers (gather.rs:619, scout.rs:244, where_to_add.rs:167, onboard.rs:175,
+ * the worktree overlay) pass no index; their semantics are: SQL type/language filter, then
+ * per row  base = clamp(cos,0,1) -> max(base,0)*note_boost -> *importance (if demotion) ->
+ * keep iff score >= threshold  (apply_scoring_pipeline, candidate.rs:420-562, without the
+ * string-matching signals NameBlend/GlobGate, which SearchFilter::default() leaves off),
+ * all BEFORE the bounded heap (query.rs:469-481).
+ * Per-row inputs are uploaded once: chunk_type/language codes (u8, the caller's own
+ * enumeration) and the two multipliers (note boost = 1 + sentiment*0.15 from the note
+ * index, importance = chunk_importance(): 0.70 test / 0.80 private / 1.0).  NULL arrays
+ * mean "no filter" / "multiplier 1.0". */
+int cqs_b200_set_row_meta(cqs_b200_index* ix, const uint8_t* chunk_type, const uint8_t* lang,
+                          uint64_t n_rows);
+int cqs_b200_set_row_signals(cqs_b200_index* ix, const float* note_boost, const float* importance,
+                             uint64_t n_rows);
+/* type_mask / lang_mask: 256-bit sets (4 x u64), bit c set = code c passes; NULL = all pass.
+ * Output: top-`limit` (score desc, row asc) of the rows that pass filter and threshold, with
+ * the FOLDED score (what search_filtered puts in its heap). */
+int cqs_b200_search_filtered(cqs_b200_index* ix, const float* query, uint32_t limit,
+                             float threshold, const uint64_t* type_mask, const uint64_t* lang_mask,
+                             int enable_demotion, uint64_t* out_rows, float* out_scores,
+                             uint32_t* out_n);
+
 /* nq independent queries (no trait counterpart — exposed as an inherent
  * B200Index::search_batch).  queries: f32[nq][dim]; outputs
  * [nq][k] with out_n[nq].  With bf16 storage and nq >= 64 this runs the

@@ -184,6 +184,34 @@ def brute_force_search(rows: np.ndarray, query: np.ndarray, k: int, mask=None):
     return topk_rows(dense_scores(rows, query), k, mask)
 
 
+def search_filtered(rows, query, limit, threshold=0.0, chunk_type=None, lang=None, include_types=None,
+                    languages=None, note_boost=None, importance=None, enable_demotion=True):
+    """Store::search_filtered_with_notes (src/search/query.rs:348-510) with
+    SearchFilter::default()-style signals (no name matcher, no glob): SQL type/language
+    filter, then per row score_candidate = cosine -> apply_scoring_pipeline
+    (candidate.rs:538-578), then the bounded heap — the pipeline runs BEFORE the heap
+    (query.rs:469-481).  Returns (rows, folded scores)."""
+    rows = np.asarray(rows)
+    query = np.asarray(query, dtype=np.float32)
+    n = rows.shape[0]
+    if limit == 0 or n == 0 or query.shape[0] != rows.shape[1] or not np.all(np.isfinite(query)):
+        return np.empty(0, np.int64), np.empty(0, np.float32)
+    ok = np.ones(n, bool)
+    if include_types is not None:
+        ok &= np.isin(np.asarray(chunk_type), list(include_types))
+    if languages is not None:
+        ok &= np.isin(np.asarray(lang), list(languages))
+    cos = dense_scores(rows, query)
+    folded = np.full(n, np.nan, np.float32)
+    for r in np.nonzero(ok & np.isfinite(cos))[0]:
+        s = apply_scoring_pipeline(cos[r], note_boost=1.0 if note_boost is None else note_boost[r],
+                                   importance=(None if (importance is None or not enable_demotion) else importance[r]),
+                                   threshold=threshold)
+        if s is not None:
+            folded[r] = s
+    return topk_rows(folded, limit)
+
+
 def bitset_to_mask(bitset: np.ndarray, n: int) -> np.ndarray:
     """Host filter bitset convention, bit i%32 of word i/32 (src/cagra.rs:747-757)."""
     bits = np.unpackbits(np.asarray(bitset, dtype="<u4").view(np.uint8), bitorder="little")

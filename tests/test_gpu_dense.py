@@ -261,3 +261,46 @@ def test_config2_full_size_1m_f32(cqs):
     assert (g_rows % 7 == 0).all() and g_rows[0] == 77
     assert ix.last_kernel_ms() > 0
     ix.close()
+
+
+def test_search_filtered_on_device_matches_reference_semantics(cqs):
+    """Store::search_filtered (src/search/query.rs:348-510) with default signals: type/language
+    filter, clamp -> note boost -> demotion -> threshold, all before the heap."""
+    rng = np.random.default_rng(17)
+    n, dim = 30_000, 768
+    rows = O.fast_unit_rows(n, dim, seed=17, clustered=True)
+    ctype = rng.integers(0, 12, n).astype(np.uint8)
+    lang = rng.integers(0, 70, n).astype(np.uint8)          # > 64 codes: second mask word
+    note = np.ones(n, f32); note[rng.random(n) < 0.05] = f32(1.15); note[rng.random(n) < 0.05] = f32(0.85)
+    imp = np.ones(n, f32); imp[rng.random(n) < 0.2] = f32(0.70); imp[rng.random(n) < 0.1] = f32(0.80)
+    ix = cqs.B200Index(dim)
+    ix.append(None, rows); ix.finalize()
+    ix.set_row_meta(ctype, lang)
+    ix.set_row_signals(note, imp)
+    for trial in range(6):
+        q = rows[int(rng.integers(0, n))] + rng.standard_normal(dim).astype(f32) * f32(0.03)
+        q = (q / np.linalg.norm(q)).astype(f32)
+        types = None if trial % 3 == 0 else [1, 4, 7]
+        langs = None if trial % 2 == 0 else [0, 3, 65, 69]
+        thr = [0.0, 0.3, 0.5][trial % 3]
+        demote = trial != 4
+        for limit in (5, 20, 100):
+            g_rows, g_sc = ix.search_filtered_rows(q, limit, thr, types, langs, demote)
+            o_rows, o_sc = O.search_filtered(rows, q, limit, thr, ctype, lang, types, langs, note, imp, demote)
+            assert g_rows.shape[0] == o_rows.shape[0]
+            assert np.allclose(g_sc, o_sc, rtol=2e-5, atol=1e-7)
+            if not np.array_equal(g_rows.astype(np.int64), o_rows):      # only near-ties may differ
+                diff = np.nonzero(g_rows.astype(np.int64) != o_rows)[0]
+                for i in diff:
+                    assert abs(float(g_sc[i]) - float(o_sc[i])) <= 2e-5 * abs(float(o_sc[i])) + 1e-7
+            if types is not None:
+                assert np.isin(ctype[g_rows.astype(np.int64)], types).all()
+            if langs is not None:
+                assert np.isin(lang[g_rows.astype(np.int64)], langs).all()
+            assert (g_sc >= thr).all()
+    # plain search is unaffected by the uploaded signals
+    a, b = ix.search_rows(q, 10)
+    full = O.dense_scores(rows, q)
+    o_rows, o_sc = O.topk_rows(full, 10)
+    assert_topk_parity(a, b, o_rows, o_sc, full)
+    ix.close()
