@@ -35,6 +35,8 @@ SIGNATURES = {
     "cqs_b200_set_row_meta": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "cqs_b200_set_row_signals": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "cqs_b200_search_filtered": (C.c_int, [vp, vp, C.c_uint32, C.c_float, vp, vp, C.c_int, vp, vp, vp]),
+    "cqs_b200_search_typed": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, vp, vp]),
+    "cqs_b200_rrf_fuse": (C.c_int, [C.c_int, vp, vp, C.c_uint32, C.c_float, C.c_uint32, vp, vp, vp]),
     "cqs_b200_search_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_sparse_attach": (C.c_int, [vp, vp, vp, vp, C.c_uint32]),
     "cqs_b200_search_sparse": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),

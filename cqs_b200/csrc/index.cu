@@ -1046,6 +1046,62 @@ int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* den
   return rc;
 }
 
+int cqs_b200_rrf_fuse(int device, const uint64_t* ids, const uint32_t* list_len, uint32_t n_lists,
+                      float k, uint32_t limit, uint64_t* out_ids, float* out_scores, uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  if (!out_ids || !out_scores || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (n_lists == 0 || limit == 0) return CQS_B200_OK;
+  if (!ids || !list_len) return fail(CQS_B200_ERR_INVALID, "NULL lists");
+  std::vector<uint32_t> off(n_lists + 1, 0);
+  for (uint32_t l = 0; l < n_lists; ++l) off[l + 1] = off[l] + list_len[l];
+  const uint32_t total = off[n_lists];
+  if (total == 0) return CQS_B200_OK;
+  if (total > kRrfMaxEntries) return fail(CQS_B200_ERR_INVALID, "more than %u ids in total", kRrfMaxEntries);
+  uint64_t lo = ~0ull, hi = 0;
+  for (uint32_t j = 0; j < total; ++j) if (ids[j] != ~0ull) { lo = std::min(lo, ids[j]); hi = std::max(hi, ids[j]); }
+  if (hi > lo && hi - lo > 0xFFFFFFFEull) return fail(CQS_B200_ERR_UNSUPPORTED, "ids span more than 2^32");
+  cqs_b200_index* none = nullptr;
+  CK(none, cudaSetDevice(device));
+  const uint32_t cap = std::min(limit, total);
+  uint8_t* d = nullptr;
+  const size_t bytes = 8 * (size_t)total + 4 * (n_lists + 1) + 16 + (8 + 4) * (size_t)cap + 64;
+  CK(none, cudaMalloc((void**)&d, bytes));
+  uint64_t* d_ids = (uint64_t*)d;
+  uint64_t* d_out = d_ids + total;
+  float* d_sc = (float*)(d_out + cap);
+  uint32_t* d_off = (uint32_t*)(d_sc + cap);
+  uint32_t* d_n = d_off + n_lists + 1;
+  auto body = [&]() -> int {
+    CK(none, cudaMemcpy(d_ids, ids, 8 * (size_t)total, cudaMemcpyHostToDevice));
+    CK(none, cudaMemcpy(d_off, off.data(), 4 * (n_lists + 1), cudaMemcpyHostToDevice));
+    CK(none, launch_rrf_fuse(d_ids, d_off, n_lists, k, cap, d_out, d_sc, d_n, 0));
+    uint32_t n = 0;
+    CK(none, cudaMemcpy(&n, d_n, 4, cudaMemcpyDeviceToHost));
+    n = std::min(n, cap);
+    CK(none, cudaMemcpy(out_ids, d_out, 8 * (size_t)n, cudaMemcpyDeviceToHost));
+    CK(none, cudaMemcpy(out_scores, d_sc, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    *out_n = n;
+    return CQS_B200_OK;
+  };
+  int rc = body();
+  cudaFree(d);
+  return rc;
+}
+
+int cqs_b200_search_typed(cqs_b200_index* ix, const float* query, uint32_t k, const uint64_t* type_mask,
+                          const uint64_t* lang_mask, uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (!type_mask && !lang_mask) return search_impl(ix, query, k, nullptr, nullptr, out_rows, out_scores, out_n);
+  if (ix->n_rows && (ix->shards.empty() || !ix->shards[0].d_ctype))
+    return fail(CQS_B200_ERR_INVALID, "type/language filter requested but cqs_b200_set_row_meta was not called");
+  ScanSignals sig;
+  if (type_mask) memcpy(sig.type_mask, type_mask, 32);
+  if (lang_mask) memcpy(sig.lang_mask, lang_mask, 32);
+  sig.pipeline = 0;  // raw cosine, filter only
+  return search_impl(ix, query, k, nullptr, &sig, out_rows, out_scores, out_n);
+}
+
 int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, uint32_t dim,
                              const float* queries, uint32_t nq, float threshold, int32_t* out_cat,
                              float* out_margin) {

@@ -145,6 +145,11 @@ struct FuseArgs {
 };
 cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t stream);
 
+constexpr uint32_t kRrfMaxEntries = 2048;  // total ids over all lists of one rrf_fuse call
+cudaError_t launch_rrf_fuse(const uint64_t* d_ids, const uint32_t* d_list_off, uint32_t n_lists, float k,
+                            uint32_t limit, uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_n,
+                            cudaStream_t stream);
+
 cudaError_t launch_route_centroids(const float* d_centroids, uint32_t n_c, uint32_t dim,
                                    const float* d_queries, uint32_t nq, float threshold,
                                    int32_t* d_out_cat, float* d_out_margin, cudaStream_t stream);

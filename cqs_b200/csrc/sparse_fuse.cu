@@ -449,6 +449,120 @@ cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------
+// rrf_fuse_n (src/search/scoring/fusion.rs:36-68), one CTA.
+// ---------------------------------------------------------------------------
+// score[id] = sum over lists IN LIST ORDER of 1/(K + rank + 1) (f32; rank = 0-based position
+// of the FIRST occurrence of id in that list), then the bounded heap: top-`limit` by
+// (score desc, id asc).  Lists are processed one after the other (two barriers each) so
+// the f32 additions happen in the reference's order; within a list every id is owned by
+// the thread holding its first occurrence.
+constexpr uint32_t kRrfMaxTotal = 2048;   // total entries over all lists
+constexpr uint32_t kRrfSlots = 4096;
+struct RrfSmem {
+  unsigned long long hrow[kRrfSlots];   // 32 KB
+  uint32_t hfirst[kRrfSlots];           // first rank of the id in the CURRENT list
+  float hscore[kRrfSlots];
+  ckey_t keys[kRrfMaxTotal];            // 16 KB
+  unsigned long long row_min;
+  uint32_t n_union;
+};
+struct RrfParams {
+  const uint64_t* ids;        // concatenated lists
+  const uint32_t* list_off;   // [n_lists + 1]
+  uint32_t n_lists;
+  float k;
+  uint32_t limit;
+  uint64_t* out_ids;
+  float* out_scores;
+  uint32_t* out_n;
+};
+__global__ void __launch_bounds__(1024, 1) rrf_fuse_kernel(const RrfParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  RrfSmem& s = *reinterpret_cast<RrfSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x, T = 1024;
+  for (uint32_t i = tid; i < kRrfSlots; i += T) {
+    s.hrow[i] = kFuseEmpty;
+    s.hfirst[i] = 0xFFFFFFFFu;
+    s.hscore[i] = 0.f;
+  }
+  for (uint32_t i = tid; i < kRrfMaxTotal; i += T) s.keys[i] = 0;
+  if (tid == 0) {
+    s.row_min = ~0ull;
+    s.n_union = 0;
+  }
+  __syncthreads();
+  auto insert = [&](uint64_t row) {
+    uint32_t slot = fuse_hash(row);
+    while (true) {
+      const unsigned long long prev = atomicCAS(&s.hrow[slot], kFuseEmpty, row);
+      if (prev == kFuseEmpty || prev == row) return slot;
+      slot = (slot + 1) & (kRrfSlots - 1);
+    }
+  };
+  for (uint32_t l = 0; l < p.n_lists; ++l) {
+    const uint32_t b = p.list_off[l], e = p.list_off[l + 1];
+    for (uint32_t r = tid; r < e - b; r += T) {          // first occurrence per id
+      const uint64_t row = p.ids[b + r];
+      if (row == kFuseEmpty) continue;
+      const uint32_t slot = insert(row);
+      atomicMin(&s.hfirst[slot], r);
+      atomicMin(&s.row_min, (unsigned long long)row);
+    }
+    __syncthreads();
+    for (uint32_t r = tid; r < e - b; r += T) {
+      const uint64_t row = p.ids[b + r];
+      if (row == kFuseEmpty) continue;
+      uint32_t slot = fuse_hash(row);
+      while (s.hrow[slot] != row) slot = (slot + 1) & (kRrfSlots - 1);
+      if (s.hfirst[slot] == r) {
+        // contribution = 1.0 / (k + rank as f32 + 1.0);  *entry += contribution
+        const float c = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(p.k, (float)r), 1.0f));
+        s.hscore[slot] = __fadd_rn(s.hscore[slot], c);
+      }
+    }
+    __syncthreads();
+    for (uint32_t r = tid; r < e - b; r += T) {          // reset the per-list first-rank marks
+      const uint64_t row = p.ids[b + r];
+      if (row == kFuseEmpty) continue;
+      uint32_t slot = fuse_hash(row);
+      while (s.hrow[slot] != row) slot = (slot + 1) & (kRrfSlots - 1);
+      s.hfirst[slot] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+  }
+  const uint64_t row_min = s.row_min;
+  for (uint32_t slot = tid; slot < kRrfSlots; slot += T) {
+    const uint64_t row = s.hrow[slot];
+    if (row == kFuseEmpty) continue;
+    const float sc = s.hscore[slot];
+    if (!finite_bits(__float_as_uint(sc))) continue;     // BoundedScoreHeap drops non-finite
+    ckey_t key = ((ckey_t)ordered_u32(__float_as_uint(sc)) << 32) | (ckey_t)(~(uint32_t)(row - row_min));
+    s.keys[atomicAdd(&s.n_union, 1u)] = key;
+  }
+  __syncthreads();
+  const uint32_t n_union = s.n_union;
+  block_sort_desc(Group{tid, T, 0}, s.keys, max(next_pow2(n_union), kSortChunk));
+  const uint32_t n_out = min(n_union, p.limit);
+  for (uint32_t i = tid; i < n_out; i += T) {
+    p.out_ids[i] = row_min + (uint64_t)(~(uint32_t)s.keys[i]);
+    p.out_scores[i] = __uint_as_float(unordered_u32((uint32_t)(s.keys[i] >> 32)));
+  }
+  if (tid == 0) *p.out_n = n_out;
+}
+
+cudaError_t launch_rrf_fuse(const uint64_t* d_ids, const uint32_t* d_list_off, uint32_t n_lists, float k,
+                            uint32_t limit, uint64_t* d_out_ids, float* d_out_scores, uint32_t* d_out_n,
+                            cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RrfSmem));
+  if (e != cudaSuccess) return e;
+  RrfParams p{d_ids, d_list_off, n_lists, k, limit, d_out_ids, d_out_scores, d_out_n};
+  rrf_fuse_kernel<<<1, 1024, sizeof(RrfSmem), st>>>(p);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // centroid routing (src/search/router.rs:1415-1444)
 // ---------------------------------------------------------------------------
 // score[q][c] = sequential f32 sum_i e_i * c_i (Iterator::sum over a.zip(b).map(a*b)).

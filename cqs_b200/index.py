@@ -202,6 +202,19 @@ class B200Index:
                                            int(bool(enable_demotion)), ptr(rows), ptr(scores), C.byref(n)))
         return rows[: n.value].copy(), scores[: n.value].copy()
 
+    def search_typed_rows(self, query, k: int, include_types=None, languages=None):
+        """search_with_filter for an include_types / languages predicate, tested on device."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self._dim:
+            return np.empty(0, np.uint64), np.empty(0, np.float32)
+        kk = max(int(k), 0)
+        rows = np.empty(max(kk, 1), np.uint64)
+        scores = np.empty(max(kk, 1), np.float32)
+        n = C.c_uint32(0)
+        tm, lm = self._mask256(include_types), self._mask256(languages)
+        check(lib.cqs_b200_search_typed(self._h, ptr(q), kk, ptr(tm), ptr(lm), ptr(rows), ptr(scores), C.byref(n)))
+        return rows[: n.value].copy(), scores[: n.value].copy()
+
     # ---- inherent (no trait counterpart) ---------------------------------------
     def search_batch_rows(self, queries: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
         q = np.ascontiguousarray(queries, dtype=np.float32)
@@ -250,6 +263,20 @@ class B200Index:
         m = n.value
         return dict(rows=rows[:m].copy(), fused=fused[:m].copy(), dense=dense[:m].copy(),
                     sparse_raw=sraw[:m].copy(), present=present[:m].copy())
+
+
+def rrf_fuse_n(ranked_lists, limit: int, k: float = 60.0, device: int = 0):
+    """rrf_fuse_n over lists of row ids (src/search/scoring/fusion.rs:36-68) -> (ids, scores)."""
+    lens = np.asarray([len(l) for l in ranked_lists], np.uint32)
+    ids = np.ascontiguousarray(np.concatenate([np.asarray(l, np.uint64) for l in ranked_lists])
+                               if len(ranked_lists) else np.empty(0, np.uint64))
+    cap = max(min(int(limit), int(lens.sum())), 1)
+    out_ids = np.empty(cap, np.uint64)
+    out_sc = np.empty(cap, np.float32)
+    n = C.c_uint32(0)
+    check(lib.cqs_b200_rrf_fuse(device, ptr(ids), ptr(lens), len(ranked_lists), float(k), int(limit),
+                                ptr(out_ids), ptr(out_sc), C.byref(n)))
+    return out_ids[: n.value].copy(), out_sc[: n.value].copy()
 
 
 def fuse_pools(dense_rows, dense_scores, sparse_rows, sparse_scores, alpha: float, pool_k: int, device: int = 0):

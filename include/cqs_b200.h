@@ -110,6 +110,21 @@ int cqs_b200_search_filtered(cqs_b200_index* ix, const float* query, uint32_t li
                              int enable_demotion, uint64_t* out_rows, float* out_scores,
                              uint32_t* out_n);
 
+/* VectorIndex::search_with_filter for the predicate search_hybrid_inner / the CLI build from
+ * include_types / languages (src/search/query.rs:867-878): the same exact scan with the
+ * type/language test done on the device from the uploaded row meta — no per-query host bitset
+ * (12.5 MB at 100M rows).  Raw cosine scores.  NULL masks = all pass. */
+int cqs_b200_search_typed(cqs_b200_index* ix, const float* query, uint32_t k,
+                          const uint64_t* type_mask, const uint64_t* lang_mask, uint64_t* out_rows,
+                          float* out_scores, uint32_t* out_n);
+
+/* ---- rrf_fuse_n  (src/search/scoring/fusion.rs:36-68) -------------------------------------
+ * ids: the ranked lists concatenated (row ids), list_len[n_lists]; k = the RRF constant (60,
+ * CQS_RRF_K).  score[id] = sum over lists in list order of 1/(k + rank + 1) with rank the
+ * 0-based first occurrence in that list; output top-`limit` (score desc, id asc). */
+int cqs_b200_rrf_fuse(int device, const uint64_t* ids, const uint32_t* list_len, uint32_t n_lists,
+                      float k, uint32_t limit, uint64_t* out_ids, float* out_scores, uint32_t* out_n);
+
 /* nq independent queries (no trait counterpart — exposed as an inherent
  * B200Index::search_batch).  queries: f32[nq][dim]; outputs
  * [nq][k] with out_n[nq].  With bf16 storage and nq >= 64 this runs the

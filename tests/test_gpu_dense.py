@@ -304,3 +304,44 @@ def test_search_filtered_on_device_matches_reference_semantics(cqs):
     o_rows, o_sc = O.topk_rows(full, 10)
     assert_topk_parity(a, b, o_rows, o_sc, full)
     ix.close()
+
+
+def test_search_typed_equals_bitset_filter(cqs):
+    rng = np.random.default_rng(23)
+    n, dim = 20_000, 768
+    rows = O.fast_unit_rows(n, dim, seed=23)
+    ctype = rng.integers(0, 9, n).astype(np.uint8)
+    lang = rng.integers(0, 5, n).astype(np.uint8)
+    ix = cqs.B200Index(dim)
+    ix.append(None, rows); ix.finalize()
+    with pytest.raises(cqs.B200Error):
+        ix.search_typed_rows(rows[0], 5, include_types=[1])              # meta not uploaded yet
+    ix.set_row_meta(ctype, lang)
+    q = O.fast_unit_rows(1, dim, seed=24)[0]
+    for types, langs in (([1, 2], None), (None, [3]), ([0, 8], [1, 4]), (None, None)):
+        mask = np.ones(n, bool)
+        if types is not None: mask &= np.isin(ctype, types)
+        if langs is not None: mask &= np.isin(lang, langs)
+        a = ix.search_typed_rows(q, 50, types, langs)
+        b = ix.search_rows(q, 50, O.mask_to_bitset(mask))
+        assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    ix.close()
+
+
+def test_extend_after_reopen(cqs):
+    """TieredIndex::extend analogue (src/tiered.rs:317-360): reopen, append, finalize."""
+    from cqs_b200.capi import lib, check
+    rows = O.fast_unit_rows(5000, 768, seed=33)
+    ix = cqs.B200Index(768)
+    ix.append(None, rows[:3000]); ix.finalize()
+    with pytest.raises(cqs.B200Error):
+        ix.append(None, rows[3000:])                                      # sealed
+    check(lib.cqs_b200_reopen(ix._h))
+    ix.append(None, rows[3000:]); ix.finalize()
+    q = rows[4500]
+    g_rows, g_sc = ix.search_rows(q, 10)
+    full = O.dense_scores(rows, q)
+    o_rows, o_sc = O.topk_rows(full, 10)
+    assert g_rows[0] == 4500
+    assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+    ix.close()

@@ -219,3 +219,26 @@ def test_centroid_routing_bit_exact(cqs):
     assert applied and cqs.apply_centroid_floor(cqs.resolve_splade_alpha(cat, env={}), applied) >= f32(0.7)
     cat, applied = reclassify_with_centroid("structural", qs[0], clf, env={})
     assert cat == "structural" and not applied
+
+
+# ---- a14 rrf_fuse_n (src/search/scoring/fusion.rs:208-331) ---------------------------------
+
+def test_rrf_fuse_reference_vectors_and_random(cqs):
+    from cqs_b200.index import rrf_fuse_n
+    ids, sc = rrf_fuse_n([[0, 1, 2, 3, 0, 4]], 10)                        # per-list dedup
+    assert abs(float(sc[ids.tolist().index(0)]) - 1.0 / 61.0) < 1e-6
+    ids, sc = rrf_fuse_n([[9, 1, 2], [9, 3], [9, 4]], 10)                  # cumulative overlap
+    by = dict(zip(ids.tolist(), sc.tolist()))
+    assert abs(by[9] - 3.0 / 61.0) < 1e-6 and abs(by[1] - 1.0 / 62.0) < 1e-6 and ids[0] == 9
+    ids, sc = rrf_fuse_n([[0, 1], [2, 3], [4, 5], [6, 7]], 3)              # limit, ties -> id asc
+    assert ids.tolist() == [0, 2, 4] and sc[0] >= sc[1] >= sc[2]
+    assert rrf_fuse_n([], 10)[0].shape[0] == 0
+    rng = np.random.default_rng(8)
+    for trial in range(5):
+        lists = [rng.choice(900, size=int(rng.integers(1, 500)), replace=True).tolist()
+                 for _ in range(int(rng.integers(1, 4)))]
+        limit = int(rng.integers(1, 300))
+        want = O.rrf_fuse_n(lists, limit)
+        ids, sc = rrf_fuse_n(lists, limit)
+        assert ids.tolist() == [i for i, _ in want]
+        assert np.array_equal(bits(sc), bits([s for _, s in want]))
