@@ -31,6 +31,8 @@ SIGNATURES = {
     "cqs_b200_finalize": (C.c_int, [vp]),
     "cqs_b200_reopen": (C.c_int, [vp]),
     "cqs_b200_destroy": (None, [vp]),
+    "cqs_b200_save": (C.c_int, [vp, C.c_char_p]),
+    "cqs_b200_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
     "cqs_b200_search": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_set_row_meta": (C.c_int, [vp, vp, vp, C.c_uint64]),
     "cqs_b200_set_row_signals": (C.c_int, [vp, vp, vp, C.c_uint64]),

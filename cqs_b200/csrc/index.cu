@@ -1130,6 +1130,135 @@ int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, u
   return rc;
 }
 
+// ---- persistence -----------------------------------------------------------------------
+
+namespace {
+struct FileHeader {
+  char magic[8];
+  uint32_t version, dim, storage, metric;
+  uint64_t n_rows, checksum, reserved[3];
+};
+static_assert(sizeof(FileHeader) == 64, "header must be 64 bytes");
+// 64-bit multiply-rotate checksum over 8-byte words (tail bytes zero padded)
+uint64_t checksum_update(uint64_t h, const uint8_t* p, size_t n) {
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    h = (h << 31) | (h >> 33);
+  }
+  if (i < n) {
+    uint64_t w = 0;
+    memcpy(&w, p + i, n - i);
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    h = (h << 31) | (h >> 33);
+  }
+  return h;
+}
+}  // namespace
+
+int cqs_b200_save(cqs_b200_index* ix, const char* path) {
+  if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(CQS_B200_ERR_INVALID, "cannot open %s for writing", tmp.c_str());
+  FileHeader hd{};
+  memcpy(hd.magic, "CQSB2001", 8);
+  hd.version = 1; hd.dim = ix->dim; hd.storage = (uint32_t)ix->storage; hd.metric = (uint32_t)ix->metric;
+  hd.n_rows = ix->n_rows;
+  const size_t esz = ix->layout.mode == 0 ? 4 : 2;
+  const size_t row_out = (size_t)ix->dim * esz, row_in = (size_t)ix->layout.ld * esz;
+  const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / row_out);
+  std::vector<uint8_t> buf(chunk * row_out);
+  uint64_t h = 0x243F6A8885A308D3ull;
+  bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+  for (auto& s : ix->shards) {
+    if (cudaSetDevice(s.device) != cudaSuccess) ok = false;
+    for (uint64_t r = 0; ok && r < s.n_rows; r += chunk) {
+      const uint64_t m = std::min(chunk, s.n_rows - r);
+      if (cudaMemcpy2D(buf.data(), row_out, s.d_rows + r * row_in, row_in, row_out, m,
+                       cudaMemcpyDeviceToHost) != cudaSuccess) {
+        ix->poisoned.store(1);
+        ok = false;
+        break;
+      }
+      h = checksum_update(h, buf.data(), m * row_out);
+      ok = fwrite(buf.data(), 1, m * row_out, f) == m * row_out;
+    }
+  }
+  hd.checksum = h;
+  ok = ok && fseek(f, 0, SEEK_SET) == 0 && fwrite(&hd, sizeof hd, 1, f) == 1;
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {
+    remove(tmp.c_str());
+    return fail(CQS_B200_ERR_INVALID, "writing %s failed", path);
+  }
+  return CQS_B200_OK;
+}
+
+int cqs_b200_load(const char* path, const int* device_ids, int n_dev, cqs_b200_index** out) {
+  if (!out) return fail(CQS_B200_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!path) return fail(CQS_B200_ERR_INVALID, "path is NULL");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(CQS_B200_ERR_INVALID, "cannot open %s", path);
+  FileHeader hd{};
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "CQSB2001", 8) != 0 || hd.version != 1 ||
+      hd.storage > 2 || hd.dim == 0 || hd.dim > 2048) {
+    fclose(f);
+    return fail(CQS_B200_ERR_INVALID, "%s: not a cqs_b200 index file (bad magic / header)", path);
+  }
+  const size_t esz = hd.storage == CQS_B200_STORAGE_BF16 ? 2 : 4;
+  const size_t row = (size_t)hd.dim * esz;
+  fseek(f, 0, SEEK_END);
+  const long fsize = ftell(f);
+  if (fsize < 0 || (uint64_t)fsize != sizeof hd + hd.n_rows * row) {
+    fclose(f);
+    return fail(CQS_B200_ERR_INVALID, "%s: size does not match the header (truncated?)", path);
+  }
+  fseek(f, sizeof hd, SEEK_SET);
+  cqs_b200_index* ix = nullptr;
+  int rc = cqs_b200_create(device_ids, n_dev, hd.dim, (int)hd.metric, (int)hd.storage, &ix);
+  if (rc) { fclose(f); return rc; }
+  rc = cqs_b200_reserve(ix, hd.n_rows);
+  const uint64_t chunk = std::max<uint64_t>(1, (64ull << 20) / row);
+  std::vector<uint8_t> buf(chunk * row);
+  std::vector<float> wide;
+  uint64_t h = 0x243F6A8885A308D3ull;
+  for (uint64_t r = 0; rc == 0 && r < hd.n_rows; r += chunk) {
+    const uint64_t m = std::min(chunk, hd.n_rows - r);
+    if (fread(buf.data(), 1, m * row, f) != m * row) { rc = fail(CQS_B200_ERR_INVALID, "%s: short read", path); break; }
+    h = checksum_update(h, buf.data(), m * row);
+    if (esz == 4) {
+      rc = cqs_b200_append_rows_f32(ix, (const float*)buf.data(), m);
+    } else {
+      // bf16 -> f32 is exact, and the device's RNE rounding of an exact bf16 value is the identity
+      wide.resize(m * hd.dim);
+      const uint16_t* b16 = (const uint16_t*)buf.data();
+      for (size_t i = 0; i < m * hd.dim; ++i) {
+        uint32_t u = (uint32_t)b16[i] << 16;
+        memcpy(&wide[i], &u, 4);
+      }
+      rc = cqs_b200_append_rows_f32(ix, wide.data(), m);
+    }
+  }
+  fclose(f);
+  if (rc == 0 && h != hd.checksum) rc = fail(CQS_B200_ERR_INVALID, "%s: checksum mismatch (corrupt file)", path);
+  if (rc == 0) rc = cqs_b200_finalize(ix);
+  if (rc) {
+    std::string msg = t_last_error;
+    cqs_b200_destroy(ix);
+    t_last_error = msg;
+    return rc;
+  }
+  *out = ix;
+  return CQS_B200_OK;
+}
+
 // ---- introspection ---------------------------------------------------------
 
 uint64_t cqs_b200_len(const cqs_b200_index* ix) { return ix ? ix->n_rows : 0; }

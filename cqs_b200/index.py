@@ -64,6 +64,44 @@ class B200Index:
         ix.finalize()
         return ix
 
+    # ---- persistence (src/cagra.rs:963-1652 analogue: blob + id sidecar) -----------------
+    def save(self, path: str) -> None:
+        import json
+        check(lib.cqs_b200_save(self._h, path.encode()))
+        with open(path + ".ids.json.tmp", "w") as f:
+            json.dump({"magic": "cqs-b200-ids-v1", "dim": self._dim, "chunk_count": len(self.id_map),
+                       "storage": self.storage, "id_map": self.id_map}, f)
+        import os
+        os.replace(path + ".ids.json.tmp", path + ".ids.json")
+
+    @classmethod
+    def load(cls, path: str, devices: Optional[Sequence[int]] = None) -> Optional["B200Index"]:
+        """None on any mismatch (caller rebuilds from the store, src/cagra.rs:1676-1802)."""
+        import json
+        devs = list(devices) if devices is not None else [0]
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        if lib.cqs_b200_load(path.encode(), arr, len(devs), C.byref(h)) != capi.OK:
+            return None
+        self = cls.__new__(cls)
+        self._h = h
+        self._dim = int(lib.cqs_b200_dim(h))
+        self.row_base = 0
+        self._bitset_cache = {}
+        self.id_map = []
+        self.storage = "?"
+        try:
+            with open(path + ".ids.json") as f:
+                meta = json.load(f)
+            if meta.get("magic") != "cqs-b200-ids-v1" or meta.get("chunk_count") != len(self):
+                raise ValueError("sidecar mismatch")
+            self.id_map = list(meta["id_map"])
+            self.storage = meta.get("storage", "?")
+        except (OSError, ValueError, KeyError):
+            self.close()
+            return None
+        return self
+
     def reserve(self, n: int) -> None:
         check(lib.cqs_b200_reserve(self._h, int(n)))
 

@@ -78,6 +78,16 @@ int cqs_b200_finalize(cqs_b200_index* ix);
 int cqs_b200_reopen(cqs_b200_index* ix);
 void cqs_b200_destroy(cqs_b200_index* ix); /* syncs all streams first (src/cagra.rs:289-301) */
 
+/* ---- persistence: the flat-matrix analogue of CagraIndex::save / load ---------------------
+ * (src/cagra.rs:963-1652: blob + sidecar with magic, dim, chunk_count, checksum; atomic
+ * temp + rename).  The file holds a 64-byte header (magic "CQSB2001", version, dim, storage,
+ * metric, n_rows, payload checksum) and the master rows un-padded in their storage dtype; the
+ * chunk-id sidecar stays with the caller exactly like CagraMeta's id_map.  Load verifies magic,
+ * sizes and checksum and returns CQS_B200_ERR_INVALID on any mismatch (the caller then
+ * rebuilds from the store, as src/cagra.rs:1676-1802 does). */
+int cqs_b200_save(cqs_b200_index* ix, const char* path);
+int cqs_b200_load(const char* path, const int* device_ids, int n_dev, cqs_b200_index** out);
+
 /* ---- VectorIndex::search / search_with_filter  (src/index.rs:146,167) ------
  * query: f32[dim].  bitset: NULL or ceil(len/32) words, bit (i%32) of word
  * (i/32) set = row i passes (src/cagra.rs:747-757).

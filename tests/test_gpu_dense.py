@@ -345,3 +345,32 @@ def test_extend_after_reopen(cqs):
     assert g_rows[0] == 4500
     assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
     ix.close()
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16", "bf16+f32"])
+def test_save_load_roundtrip_and_corruption(cqs, tmp_path, storage):
+    """Persistence conventions of src/cagra.rs:963-1652: checksummed blob + id sidecar,
+    atomic write; any mismatch -> None -> rebuild."""
+    n, dim = 4000, 768
+    emb = O.fast_unit_rows(n, dim, seed=44)
+    ids = [f"chunk_{i:05d}" for i in range(n)]
+    ix = cqs.B200Index.build(ids, emb, storage=storage)
+    path = str(tmp_path / "index.b200")
+    ix.save(path)
+    ix2 = cqs.B200Index.load(path)
+    assert ix2 is not None and len(ix2) == n and ix2.id_map == ix.id_map
+    for s in range(3):
+        q = O.fast_unit_rows(1, dim, seed=500 + s)[0]
+        a, b = ix.search_rows(q, 20)
+        c, d = ix2.search_rows(q, 20)
+        assert np.array_equal(a, c) and np.array_equal(bits(b), bits(d))
+    assert [r.id for r in ix2.search(emb[7], 3)][0] == "chunk_00007"
+    ix2.close()
+    raw = bytearray(open(path, "rb").read())
+    raw[64 + 12345] ^= 0x40                                     # flip one payload bit
+    open(path, "wb").write(bytes(raw))
+    assert cqs.B200Index.load(path) is None                     # checksum mismatch
+    open(path, "wb").write(bytes(raw[: len(raw) // 2]))
+    assert cqs.B200Index.load(path) is None                     # truncated
+    assert cqs.B200Index.load(str(tmp_path / "missing.b200")) is None
+    ix.close()
