@@ -384,8 +384,18 @@ __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, u
     }
     tk.compact(kprime);
   }
-  // this round's sub-pools, `per` of them between compactions (per * kSub <= step)
-  const uint32_t per = step / kSub;
+  // this round's sub-pools.  Usually everything fits at once (a few hundred keys per query
+  // and round); otherwise `per` sub-pools between compactions (per * kSub <= step).
+  __shared__ uint32_t s_total;
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  {
+    uint32_t mine = 0;
+    for (uint32_t c = tid; c < sub_grid; c += kUpdThreads) mine += subcnt[(size_t)c * nq_pad + q];
+    if (mine) atomicAdd(&s_total, mine);
+  }
+  __syncthreads();
+  const uint32_t per = (s_cnt + s_total <= kUpdCap / 2) ? sub_grid + 1 : step / kSub;
   for (uint32_t c0 = 0; c0 < sub_grid; c0 += per) {
     const ckey_t t = s_thr;
     const uint32_t c1 = min(sub_grid, c0 + per);
