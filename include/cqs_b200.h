@@ -137,10 +137,12 @@ int cqs_b200_rrf_fuse(int device, const uint64_t* ids, const uint32_t* list_len,
 
 /* nq independent queries (no trait counterpart — exposed as an inherent
  * B200Index::search_batch).  queries: f32[nq][dim]; outputs
- * [nq][k] with out_n[nq].  With bf16 storage and nq >= 64 this runs the
- * tcgen05 tile scan over bf16-rounded queries, over-fetches, and re-scores the
- * candidates with the f32 queries; results are identical to nq calls of
- * cqs_b200_search. */
+ * [nq][k] with out_n[nq].  With STORAGE_BF16 / STORAGE_BF16_F32 and nq >= 8 this
+ * runs the tcgen05 tile scan over bf16-rounded queries, over-fetches k' >= 64
+ * candidates per query, re-scores them with the f32 queries (on the f32 master rows
+ * when present) and falls back to the exact single-query scan for any query whose
+ * candidate pool cannot be proven complete; results are identical to nq calls of
+ * cqs_b200_search.  Other cases loop over cqs_b200_search. */
 int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
                           const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
                           uint32_t* out_n);
