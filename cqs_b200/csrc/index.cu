@@ -79,6 +79,12 @@ struct Shard {
   // pinned host mirror for results (sized for the fused output, the largest)
   uint8_t* h_out = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // The partial-list scratch, the tile counter and d_query are shared by every launch of this
+  // shard; launches may come on the shard's own stream or on a caller's stream
+  // (cqs_b200_search_device).  ev_last orders a launch after the previous one when the
+  // stream changes.
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
   unsigned long long* d_trace = nullptr;  // development aid (CQS_B200_TRACE=1)
   // batched tensor-core path (bf16 storage), allocated on first use
   float* d_bq = nullptr;          // [kBatchMaxQ][ld] padded f32 queries
@@ -155,6 +161,7 @@ static void free_shard(Shard& s) {
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.ev_last) cudaEventDestroy(s.ev_last);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Shard();
 }
@@ -192,6 +199,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaHostAlloc((void**)&s.h_out, kHostOutBytes, cudaHostAllocDefault));
   CK(ix, cudaEventCreate(&s.ev0));
   CK(ix, cudaEventCreate(&s.ev1));
+  CK(ix, cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
+  s.last_stream = s.stream;
   if (getenv("CQS_B200_TRACE")) {
     CK(ix, cudaMalloc((void**)&s.d_trace, sizeof(unsigned long long) * kMaxGrid * 8));
     CK(ix, cudaMemset(s.d_trace, 0, sizeof(unsigned long long) * kMaxGrid * 8));
@@ -431,9 +440,21 @@ static uint32_t host_ordered(float f) {
 
 // Upload query + (slice of) bitset to a shard and launch the dense scan into the
 // shard's dense pool buffers.  Asynchronous on s.stream.
+// Make `st` wait for the last launch that used this shard's scratch on another stream.
+static int order_after_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
+  if (s.last_stream != st) CK(ix, cudaStreamWaitEvent(st, s.ev_last, 0));
+  return 0;
+}
+static int mark_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
+  CK(ix, cudaEventRecord(s.ev_last, st));
+  s.last_stream = st;
+  return 0;
+}
+
 static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
                         const uint32_t* bitset, const ScanSignals* sig = nullptr) {
   CK(ix, cudaSetDevice(s.device));
+  if (int rc = order_after_last(ix, s, s.stream)) return rc;
   memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
   memcpy(s.h_query, query, sizeof(float) * ix->dim);
   CK(ix, cudaMemcpyAsync(s.d_query, s.h_query, sizeof(float) * ix->layout.ld,
@@ -455,7 +476,7 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
   CK(ix, cudaEventRecord(s.ev1, s.stream));
-  return 0;
+  return mark_last(ix, s, s.stream);
 }
 
 static int check_searchable(cqs_b200_index* ix) {
@@ -643,6 +664,7 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   if (s.n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty index");
   CK(ix, cudaSetDevice(s.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+  if (int rc2 = order_after_last(ix, s, st)) return rc2;
   const float* qp = d_query;
   if (ix->layout.ld != ix->dim) {
     // the query must be zero padded to the row stride: stage it through d_query
@@ -656,7 +678,7 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   CK(ix, launch_scan_single(a, s.num_sms, st));
-  return CQS_B200_OK;
+  return mark_last(ix, s, st);
 }
 
 int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t* d_rows,
@@ -718,9 +740,11 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   a.max_row_norm = s.max_row_norm; a.d_scratch = s.d_bscratch;
   a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
   a.d_flags = s.d_bflags;
+  if (int rc2 = order_after_last(ix, s, s.stream)) return rc2;
   CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_batch(a, s.num_sms, s.stream));
   CK(ix, cudaEventRecord(s.ev1, s.stream));
+  if (int rc2 = mark_last(ix, s, s.stream)) return rc2;
   std::vector<uint32_t> flags(nq), ns(nq);
   CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaMemcpyAsync(out_rows, s.d_bout_rows, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
