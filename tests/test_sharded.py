@@ -125,3 +125,69 @@ def test_emulated_shards_device_merge_equals_unsharded(storage):
     assert m_rw[0, :2].cpu().tolist() == [17, n - 3]
     for ix in shards + [whole]:
         ix.close()
+
+
+@pytest.mark.gpu
+def test_in_process_multi_device_index_equals_single():
+    """cqs_b200_create(device_ids, n_dev > 1): the form the single-process daemon would use —
+    contiguous row blocks per device, host merge.  Needs >= 2 GPUs (skipped otherwise)."""
+    import torch
+    import cqs_b200
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, dim = 30_011, 768
+    rows = O.fast_unit_rows(n, dim, seed=91)
+    rows[5] = rows[n - 2]
+    one = cqs_b200.B200Index(dim, devices=[0])
+    one.append(None, rows); one.finalize()
+    nd = min(torch.cuda.device_count(), 4)
+    multi = cqs_b200.B200Index(dim, devices=list(range(nd)))
+    multi.reserve(n)
+    multi.append(None, rows[:10_000]); multi.append(None, rows[10_000:])
+    multi.finalize()
+    assert len(multi) == n
+    rng = np.random.default_rng(0)
+    mask = rng.random(n) < 0.5
+    for qi in (5, 100, 29_999):
+        for k in (1, 20, 500):
+            a, b = one.search_rows(rows[qi], k)
+            c, d = multi.search_rows(rows[qi], k)
+            assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32))
+        a, b = one.search_rows(rows[qi], 20, O.mask_to_bitset(mask))
+        c, d = multi.search_rows(rows[qi], 20, O.mask_to_bitset(mask))
+        assert np.array_equal(a, c)
+    one.close(); multi.close()
+
+
+@pytest.mark.gpu
+def test_search_device_and_host_search_interleave_safely():
+    """Launches on a caller stream (search_device) and on the index's own stream share the
+    per-index scratch; the library must order them."""
+    import ctypes as C
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    n, dim, k = 200_000, 768, 20
+    rows = O.fast_unit_rows(n, dim, seed=93)
+    ix = cqs_b200.B200Index(dim)
+    ix.append(None, rows); ix.finalize()
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    qs = O.fast_unit_rows(16, dim, seed=94)
+    d_q = torch.from_numpy(qs).to(dev)
+    d_sc = torch.empty((16, k), dtype=torch.float32, device=dev)
+    d_rw = torch.empty((16, k), dtype=torch.int64, device=dev)
+    d_n = torch.empty((16,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    host = []
+    for i in range(16):
+        check(lib.cqs_b200_search_device(ix._h, C.c_void_p(d_q.data_ptr() + i * dim * 4), k, None,
+                                         C.c_void_p(d_sc[i].data_ptr()), C.c_void_p(d_rw[i].data_ptr()),
+                                         C.c_void_p(d_n[i].data_ptr()), C.c_void_p(st.cuda_stream)))
+        host.append(ix.search_rows(qs[15 - i], k))          # own stream, interleaved
+    st.synchronize()
+    for i in range(16):
+        a, b = ix.search_rows(qs[i], k)
+        assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
+        assert np.array_equal(host[15 - i][0], a)
+    ix.close()
