@@ -60,6 +60,7 @@ SIGNATURES = {
     "cqs_b200_last_error": (C.c_char_p, []),
     "cqs_b200_kernel_launches": (C.c_uint64, []),
     "cqs_b200_last_kernel_ms": (C.c_float, [vp]),
+    "cqs_b200_set_timing": (C.c_int, [vp, C.c_int]),
 }
 
 

@@ -77,7 +77,9 @@ struct Shard {
   uint8_t* d_f_present = nullptr;
   uint32_t* d_f_n = nullptr;
   // pinned host mirror for results (sized for the fused output, the largest)
-  uint8_t* h_out = nullptr;
+  uint8_t* h_out = nullptr;     // pinned + mapped: [scores kMaxK][rows kMaxK][n][flag] (+ fused layout)
+  uint8_t* d_hout = nullptr;    // device alias of h_out
+  uint32_t seq = 0;             // completion sequence number of the latency path
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // The partial-list scratch, the tile counter and d_query are shared by every launch of this
   // shard; launches may come on the shard's own stream or on a caller's stream
@@ -120,6 +122,7 @@ struct cqs_b200_index {
   uint64_t row_base = 0;
   uint64_t n_rows = 0, reserved = 0, rows_per_shard = 0;
   float last_kernel_ms = 0.f;
+  bool timing = false;   // record CUDA events around the dominant kernel (cqs_b200_set_timing)
   float max_note_boost = 1.f, max_importance = 1.f;
   uint32_t last_batch_reruns = 0;  // queries the batched path sent to the exact kernel (cumulative)
   float last_batch_ms = 0.f;       // device time of the most recent tensor-core batch pipeline
@@ -196,7 +199,9 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaMalloc((void**)&s.d_f_sraw, sizeof(float) * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_f_present, kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_f_n, sizeof(uint32_t)));
-  CK(ix, cudaHostAlloc((void**)&s.h_out, kHostOutBytes, cudaHostAllocDefault));
+  CK(ix, cudaHostAlloc((void**)&s.h_out, kHostOutBytes, cudaHostAllocMapped));
+  memset(s.h_out, 0, kHostOutBytes);
+  CK(ix, cudaHostGetDevicePointer((void**)&s.d_hout, s.h_out, 0));
   CK(ix, cudaEventCreate(&s.ev0));
   CK(ix, cudaEventCreate(&s.ev1));
   CK(ix, cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
@@ -451,8 +456,14 @@ static int mark_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
   return 0;
 }
 
+constexpr size_t kOffScores = 0, kOffRows = sizeof(float) * kMaxK,
+                 kOffN = (sizeof(float) + sizeof(uint64_t)) * kMaxK, kOffFlag = kOffN + 4;
+
+// to_host: the kernel writes the result into the host-mapped buffer and publishes a
+// completion word (the latency path of cqs_b200_search); otherwise into the device pool.
 static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
-                        const uint32_t* bitset, const ScanSignals* sig = nullptr) {
+                        const uint32_t* bitset, const ScanSignals* sig = nullptr,
+                        bool to_host = false) {
   CK(ix, cudaSetDevice(s.device));
   if (int rc = order_after_last(ix, s, s.stream)) return rc;
   memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
@@ -471,11 +482,19 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
   a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
+  if (to_host) {
+    a.d_out_scores = (float*)(s.d_hout + kOffScores);
+    a.d_out_rows = (uint64_t*)(s.d_hout + kOffRows);
+    a.d_out_n = (uint32_t*)(s.d_hout + kOffN);
+    a.d_host_flag = (uint32_t*)(s.d_hout + kOffFlag);
+    a.seq = ++s.seq;
+    if (a.seq == 0) a.seq = s.seq = 1;
+  }
   a.d_trace = s.d_trace;
   a.signals = sig;
-  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
-  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
   return mark_last(ix, s, s.stream);
 }
 
@@ -513,24 +532,40 @@ static int search_impl(cqs_b200_index* ix, const float* query, uint32_t k, const
       sig.d_importance = (sig.pipeline && sig_template->d_importance) ? s->d_importance : nullptr;
       if (!sig.d_importance) sig.max_importance = 1.f;
     }
-    rc = launch_dense(ix, *s, query, k, bitset, sig_template ? &sig : nullptr);
+    rc = launch_dense(ix, *s, query, k, bitset, sig_template ? &sig : nullptr, /*to_host=*/true);
     if (rc) return rc;
-    float* hs = (float*)s->h_out;
-    uint64_t* hr = (uint64_t*)(s->h_out + sizeof(float) * kMaxK);
-    uint32_t* hn = (uint32_t*)(s->h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
-    CK(ix, cudaMemcpyAsync(hs, s->d_out_scores, sizeof(float) * k, cudaMemcpyDeviceToHost, s->stream));
-    CK(ix, cudaMemcpyAsync(hr, s->d_out_rows, sizeof(uint64_t) * k, cudaMemcpyDeviceToHost, s->stream));
-    CK(ix, cudaMemcpyAsync(hn, s->d_out_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   }
   float kms = 0.f;
   for (Shard* s : live) {
-    CK(ix, cudaSetDevice(s->device));
-    CK(ix, cudaStreamSynchronize(s->stream));
-    float ms = 0.f;
-    CK(ix, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-    kms = std::max(kms, ms);
+    // poll the completion word the kernel writes into mapped host memory; fall back to the
+    // stream status every so often so a faulted kernel cannot hang the caller
+    volatile uint32_t* flag = (volatile uint32_t*)(s->h_out + kOffFlag);
+    for (uint64_t spin = 0; *flag != s->seq; ++spin) {
+      if ((spin & 0xFFF) == 0xFFF) {
+        CK(ix, cudaSetDevice(s->device));
+        cudaError_t e = cudaStreamQuery(s->stream);
+        if (e == cudaSuccess) {
+          if (*flag != s->seq) {
+            ix->poisoned.store(1);
+            return fail(CQS_B200_ERR_CUDA, "scan finished without publishing its result");
+          }
+          break;
+        }
+        if (e != cudaErrorNotReady) CK(ix, e);
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (ix->timing) {
+      CK(ix, cudaSetDevice(s->device));
+      CK(ix, cudaEventSynchronize(s->ev1));
+      float ms = 0.f;
+      CK(ix, cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+      kms = std::max(kms, ms);
+    }
   }
-  ix->last_kernel_ms = kms;
+  if (ix->timing) ix->last_kernel_ms = kms;
   if (live.size() == 1) {
     Shard* s = live[0];
     uint32_t n = *(uint32_t*)(s->h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
@@ -741,9 +776,9 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
   a.d_flags = s.d_bflags;
   if (int rc2 = order_after_last(ix, s, s.stream)) return rc2;
-  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_batch(a, s.num_sms, s.stream));
-  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
   if (int rc2 = mark_last(ix, s, s.stream)) return rc2;
   std::vector<uint32_t> flags(nq), ns(nq);
   CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
@@ -751,8 +786,10 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   CK(ix, cudaMemcpyAsync(ns.data(), s.d_bout_n, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaMemcpyAsync(flags.data(), s.d_bflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaStreamSynchronize(s.stream));
-  CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
-  ix->last_batch_ms = ix->last_kernel_ms;
+  if (ix->timing) {
+    CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+    ix->last_batch_ms = ix->last_kernel_ms;
+  }
   for (uint32_t i = 0; i < nq; ++i) {
     out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
     if (flags[i] && !bad[i]) rerun->push_back(i);
@@ -902,10 +939,10 @@ int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const floa
     CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
     d_bits = s.d_bitset;
   }
-  CK(ix, cudaEventRecord(s.ev0, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
   rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, k, d_bits);
   if (rc) return rc;
-  CK(ix, cudaEventRecord(s.ev1, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
   float* hs = (float*)s.h_out;
   uint64_t* hr = (uint64_t*)(s.h_out + sizeof(float) * kMaxK);
   uint32_t* hn = (uint32_t*)(s.h_out + (sizeof(float) + sizeof(uint64_t)) * kMaxK);
@@ -913,7 +950,7 @@ int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const floa
   CK(ix, cudaMemcpyAsync(hr, s.d_sp_rows, sizeof(uint64_t) * k, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaMemcpyAsync(hn, s.d_sp_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaStreamSynchronize(s.stream));
-  CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  if (ix->timing) CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
   uint32_t n = std::min(*hn, k);
   memcpy(out_scores, hs, sizeof(float) * n);
   memcpy(out_rows, hr, sizeof(uint64_t) * n);
@@ -994,7 +1031,7 @@ int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_
   rc = copy_fused_out(ix, s, pool_k, out_rows, out_fused, out_dense, out_sparse_raw, out_present,
                       out_n, s.stream);
   if (rc) return rc;
-  if (dense_ok) CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
+  if (dense_ok && ix->timing) CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
   return CQS_B200_OK;
 }
 
@@ -1296,6 +1333,12 @@ const char* cqs_b200_name(void) { return "B200"; }
 const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }
 uint64_t cqs_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 float cqs_b200_last_kernel_ms(cqs_b200_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
+int cqs_b200_set_timing(cqs_b200_index* ix, int enable) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  std::lock_guard<std::mutex> g(ix->mu);
+  ix->timing = enable != 0;
+  return CQS_B200_OK;
+}
 // development aids, not declared in the public header
 uint32_t cqs_b200_debug_batch_reruns(cqs_b200_index* ix) { return ix ? ix->last_batch_reruns : 0; }
 int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) {

@@ -58,6 +58,8 @@ struct ScanArgs {
   uint32_t* d_out_n;        // [1]
   void* d_trace = nullptr;  // optional [kMaxGrid][8] u64 timestamps (CQS_B200_TRACE=1)
   const ScanSignals* signals = nullptr;
+  uint32_t* d_host_flag = nullptr;  // device alias of a host-mapped completion word (nullable)
+  uint32_t seq = 0;                 // value written to it
 };
 // Kernel 1+3: single-query streaming scan with the top-k select fused in.
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);

@@ -88,6 +88,8 @@ struct ScanParams {
   uint32_t* out_n;
   unsigned long long* trace;  // optional [grid][8] globaltimer stamps (development aid)
   ScanSignals sig;            // structured filter + per-row signals (sig.pipeline / sig.d_ctype gate them)
+  uint32_t* host_flag;        // optional: host-mapped word that receives `seq` once the result is written
+  uint32_t seq;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -387,6 +389,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
                                              p.row_base, p.out_scores, p.out_rows, p.out_n,
                                              p.trace ? p.trace + blockIdx.x * 8 : nullptr);
   TRACE(4);
+  if (p.host_flag) {
+    // the result went straight into host-mapped memory: make it visible system-wide, then
+    // publish the completion word the host is polling (saves the D2H copies and the
+    // driver's stream-sync wake-up on the latency path)
+    __threadfence_system();
+    tk.g.sync();
+    if (ctid == 0) *reinterpret_cast<volatile uint32_t*>(p.host_flag) = p.seq;
+  }
   if (ctid == 0) {
     p.done[0] = 0;
     p.done[1] = 0;
@@ -468,6 +478,8 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.out_n = a.d_out_n;
   p.trace = (unsigned long long*)a.d_trace;
   if (a.signals) p.sig = *a.signals;
+  p.host_flag = a.d_host_flag;
+  p.seq = a.seq;
   switch (a.layout.mode) {
     case 0: return launch_mode<0>(p, a.layout.nv, num_sms, st);
     case 1: return launch_mode<1>(p, a.layout.nv, num_sms, st);

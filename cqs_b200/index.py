@@ -151,6 +151,9 @@ class B200Index:
     def index_scores_are_cosine(self) -> bool:
         return bool(lib.cqs_b200_scores_are_cosine(self._h))
 
+    def set_timing(self, enable: bool = True) -> None:
+        check(lib.cqs_b200_set_timing(self._h, int(enable)))
+
     def last_kernel_ms(self) -> float:
         return float(lib.cqs_b200_last_kernel_ms(self._h))
 

@@ -219,8 +219,11 @@ const char* cqs_b200_last_error(void);  /* thread-local */
 /* Number of CUDA kernels this library has launched in this process. */
 uint64_t cqs_b200_kernel_launches(void);
 /* Device time (ms) of the dominant kernel of the most recent search call on
- * this index, from CUDA events recorded on the launching stream. */
+ * this index, from CUDA events recorded on the launching stream.  The events are only
+ * recorded after cqs_b200_set_timing(ix, 1) (off by default: they cost a few microseconds
+ * on the single-query latency path). */
 float cqs_b200_last_kernel_ms(cqs_b200_index* ix);
+int cqs_b200_set_timing(cqs_b200_index* ix, int enable);
 
 #ifdef __cplusplus
 }

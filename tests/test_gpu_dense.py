@@ -243,6 +243,7 @@ def test_config2_full_size_1m_f32(cqs):
         ix.append(None, blk)
         blocks.append(blk)
     ix.finalize()
+    ix.set_timing(True)
     rows = np.concatenate(blocks)
     del blocks
     assert len(ix) == n

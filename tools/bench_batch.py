@@ -19,6 +19,7 @@ for b in range(0, n, 100_000):
     x /= x.norm(dim=1, keepdim=True)
     ix.append_device(x.data_ptr(), m)
 ix.finalize()
+ix.set_timing(True)
 del x; torch.cuda.empty_cache()
 rng = np.random.default_rng(0)
 q = rng.standard_normal((nq, 768)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)

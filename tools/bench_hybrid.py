@@ -18,6 +18,7 @@ for b in range(0, n, 100_000):
     x /= x.norm(dim=1, keepdim=True)
     ix.append_device(x.data_ptr(), m)
 ix.finalize()
+ix.set_timing(True)
 # sparse: Zipf(1.1) token ids, duplicates inside a doc removed, ascending; weights log1p(relu(N(.8,.5))) > .01
 t0 = time.time()
 p = 1.0 / torch.arange(1, vocab + 1, device=dev, dtype=torch.float64) ** 1.1

@@ -14,6 +14,7 @@ for b in range(0, n, 100_000):
     x /= x.norm(dim=1, keepdim=True)
     ix.append_device(x.data_ptr(), 100_000)
 ix.finalize()
+ix.set_timing(True)
 q = np.random.default_rng(0).standard_normal(768).astype(np.float32); q /= np.linalg.norm(q)
 lib.cqs_b200_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
 for k in (1, 20, 500):

@@ -10,6 +10,7 @@ dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(5)
 ix = cqs_b200.B200Index(8, storage="f32")
 ix.append(None, np.ones((n, 8), np.float32)); ix.finalize()
+ix.set_timing(True)
 p = 1.0 / torch.arange(1, vocab + 1, device=dev, dtype=torch.float64) ** 1.1
 cdf = torch.cumsum(p / p.sum(), 0).float()
 W = 320; indptr = [0]; toks = []; ws = []
