@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hnsw-rows", type=int, default=100_000,
+                    help="rows of the corpus the CPU HNSW baseline is built on (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -375,6 +377,30 @@ def main():
                                           C.byref(chk_n)))
                 agree += int(np.array_equal(chk_r, o_r[i]))
             line["cpu_baseline"]["ids_identical_queries"] = f"{agree}/{nb}"
+            if args.hnsw_rows > 0:
+                # the reference's default CPU index (HNSW, tier parameters of src/hnsw/mod.rs:104-112),
+                # restated in oracle/hnsw_baseline.c; approximate => speed baseline only, recall reported
+                hn = min(args.hnsw_rows, n_total)
+                t0 = time.perf_counter()
+                hn_index = CO.Hnsw(rows_h[:hn], threads=thr)
+                build_s = time.perf_counter() - t0
+                nqh = 200
+                ids1, _, n1, lat1 = hn_index.search(queries[:nqh], K, threads=1)
+                t0 = time.perf_counter()
+                hn_index.search(queries[:nqh * 4], K, threads=thr)
+                dt_all = time.perf_counter() - t0
+                exact_r, _, _ = CO.brute_force_batch(rows_h[:hn], queries[:nqh], K, use_f64=False, threads=thr)
+                hits = sum(len(set(exact_r[i].tolist()) & set(ids1[i, :n1[i]].tolist())) for i in range(nqh))
+                line["cpu_baseline"]["hnsw"] = {
+                    "rows": hn, "M": hn_index.M, "ef_construction": hn_index.efC, "ef_search": hn_index.efS,
+                    "build_s": build_s, "p50_ms": float(np.median(lat1) * 1e3),
+                    "p95_ms": float(np.percentile(lat1, 95) * 1e3),
+                    "value": float(nqh / lat1.sum()), "unit": UNIT, "cores": 1,
+                    "all_cores": {"value": nqh * 4 / dt_all, "cores": thr},
+                    "recall_at_20_vs_exact": hits / (nqh * K),
+                    "sample": f"graph over the first {hn} rows of the corpus (bounded build time), {nqh} queries, "
+                              "approximate: speed baseline only"}
+                hn_index.close()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

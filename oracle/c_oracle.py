@@ -15,8 +15,8 @@ vp = C.c_void_p
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "cqs_oracle.c")
-    if force or not os.path.exists(_PATH) or os.path.getmtime(_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "cqs_oracle.c"), os.path.join(_HERE, "hnsw_baseline.c")]
+    if force or not os.path.exists(_PATH) or os.path.getmtime(_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _PATH
 
@@ -36,6 +36,11 @@ def _load():
     dll.oracle_sparse_search.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint64, vp, vp, C.c_uint32,
                                          C.c_uint32, vp, vp, vp, vp]
     dll.oracle_sparse_search.restype = C.c_int
+    dll.hnsw_tier.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    dll.hnsw_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64]
+    dll.hnsw_build.restype = vp
+    dll.hnsw_free.argtypes = [vp]
+    dll.hnsw_search_batch.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp, vp, vp, vp]
     return dll
 
 
@@ -123,3 +128,38 @@ def sparse_search(tptr, doc, w, vocab, n_docs, q_tok, q_w, k, bitset=None):
                                     _p(bs), _p(o_r), _p(o_s), C.byref(n))
     assert rc == 0
     return o_r[: n.value].astype(np.int64), o_s[: n.value].copy()
+
+
+class Hnsw:
+    """CPU HNSW restatement with the reference's tier parameters (oracle/hnsw_baseline.c):
+    a TIMING baseline (approximate; never a parity oracle)."""
+
+    def __init__(self, rows: np.ndarray, threads: int = 0, seed: int = 0):
+        self.rows = np.ascontiguousarray(rows, np.float32)   # must outlive the graph
+        n, dim = self.rows.shape
+        M, efC, efS = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        dll().hnsw_tier(n, C.byref(M), C.byref(efC), C.byref(efS))
+        self.M, self.efC, self.efS = M.value, efC.value, efS.value
+        self.threads = threads or num_threads()
+        self._h = dll().hnsw_build(_p(self.rows), n, dim, self.M, self.efC, self.threads, seed)
+
+    def search(self, queries: np.ndarray, k: int, threads: int = 1):
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        ids = np.zeros((nq, k), np.uint32)
+        sc = np.zeros((nq, k), np.float32)
+        n = np.zeros(nq, np.uint32)
+        lat = np.zeros(nq, np.float64)
+        dll().hnsw_search_batch(self._h, _p(q), nq, k, self.efS, threads, _p(ids), _p(sc), _p(n), _p(lat))
+        return ids, sc, n, lat
+
+    def close(self):
+        if self._h:
+            dll().hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -131,3 +131,21 @@ def test_c_port_sparse_agrees_with_numpy_oracle():
         r1, s1 = O.sparse_search_csr(indptr, tok, w, qt, qw, n_docs, 30, mask)
         r2, s2 = CO.sparse_search(tptr, pdoc, pw, vocab, n_docs, qt, qw, 30, bs)
         assert np.array_equal(r1, r2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+
+
+def test_hnsw_baseline_port_reaches_reference_like_recall():
+    """oracle/hnsw_baseline.c is a timing baseline (approximate, never a parity oracle); this
+    only guards that the restated graph works: tier parameters of src/hnsw/mod.rs:104-112,
+    self-match reachable (src/hnsw/mod.rs:962-984), high recall on clustered data."""
+    rows = O.fast_unit_rows(2500, 128, seed=7, clustered=True)
+    h = CO.Hnsw(rows, threads=4)
+    assert (h.M, h.efC, h.efS) == (16, 100, 50)
+    ids, sc, n, lat = h.search(rows[:100], 10, threads=2)
+    assert (ids[:, 0] == np.arange(100)).mean() > 0.97 and np.allclose(sc[ids[:, 0] == np.arange(100), 0], 1.0, atol=1e-4)
+    hits = 0
+    for i in range(100):
+        r, _ = CO.brute_force(rows, rows[i], 10)
+        hits += len(set(r.tolist()) & set(ids[i, :n[i]].tolist()))
+    assert hits / 1000 > 0.9
+    assert np.all(np.diff(sc, axis=1) <= 1e-6)      # sorted descending
+    h.close()
