@@ -422,6 +422,19 @@ int cqs_b200_reopen(cqs_b200_index* ix) {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   ix->finalized = false;
+  // everything that is aligned row-by-row with the dense matrix is now stale: the sparse
+  // postings, the type/language codes and the score signals must be attached again after
+  // the next finalize
+  for (auto& s : ix->shards) {
+    cudaSetDevice(s.device);
+    cudaStreamSynchronize(s.stream);
+    cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+    s.sparse = SparseDev();
+    cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
+    s.d_ctype = s.d_lang = nullptr;
+    s.d_note_boost = s.d_importance = nullptr;
+  }
+  ix->max_note_boost = ix->max_importance = 1.f;
   return CQS_B200_OK;
 }
 

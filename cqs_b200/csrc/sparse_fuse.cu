@@ -50,13 +50,13 @@ struct BoundsParams {
   uint32_t* bounds;  // [q_nnz][n_blocks + 1]
 };
 constexpr uint32_t kBoundsChunk = 8192;  // postings per streaming work unit
-constexpr uint32_t kBoundsShort = 2048;  // lists up to this long are binary-searched per block instead
+constexpr uint32_t kBoundsShort = 256;   // lists up to this long are binary-searched per block instead
 __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p) {
   __shared__ uint64_t s_base[kSpMaxQ];
   __shared__ uint32_t s_len[kSpMaxQ];
   __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // work units before token i
   const uint32_t tid = threadIdx.x;
-  const uint32_t search_units = (p.n_blocks + 1 + 255) / 256;  // 256 block boundaries per unit
+  const uint32_t search_units = (p.n_blocks + 1 + 1023) / 1024;  // 1024 block boundaries per unit
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
     uint64_t b0 = 0, b1 = 0;
@@ -89,15 +89,24 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
     const uint32_t unit = (uint32_t)(c - s_prefix[i]);
     uint32_t* row = p.bounds + (size_t)i * (p.n_blocks + 1);
     if (len <= kBoundsShort) {
-      const uint32_t j = unit * 256 + tid;  // block boundary
-      if (j <= p.n_blocks) {
-        const uint64_t target = (uint64_t)j * kSpBlock;
-        uint32_t a = 0, b = len;  // first posting with doc >= target
-        while (a < b) {
-          const uint32_t m = (a + b) >> 1;
-          if ((uint64_t)__ldg(p.doc + base + m) < target) a = m + 1; else b = m;
+      // four independent binary searches per thread (<= 8 steps each)
+      uint32_t a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = 0; b[u] = len; }
+      for (int step = 0; step < 9; ++step) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint64_t target = (uint64_t)(unit * 1024 + u * 256 + tid) * kSpBlock;
+          if (a[u] < b[u]) {
+            const uint32_t m = (a[u] + b[u]) >> 1;
+            if ((uint64_t)__ldg(p.doc + base + m) < target) a[u] = m + 1; else b[u] = m;
+          }
         }
-        row[j] = a;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = unit * 1024 + u * 256 + tid;  // block boundary
+        if (j <= p.n_blocks) row[j] = a[u];              // first posting with doc >= j*64
       }
       continue;
     }

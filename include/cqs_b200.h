@@ -73,7 +73,9 @@ int cqs_b200_append_rows_f32(cqs_b200_index* ix, const float* rows, uint64_t n_r
 /* Same, but `d_rows` is a device pointer on the index's (single) device. */
 int cqs_b200_append_rows_f32_device(cqs_b200_index* ix, const float* d_rows, uint64_t n_rows);
 /* Seal the index: after this, searches are allowed and appends are rejected
- * until cqs_b200_reopen (the TieredIndex::extend analogue, src/tiered.rs:317-360). */
+ * until cqs_b200_reopen (the TieredIndex::extend analogue, src/tiered.rs:317-360).
+ * cqs_b200_reopen drops everything aligned row-by-row with the matrix (sparse postings,
+ * row meta, row signals): attach them again after the next finalize. */
 int cqs_b200_finalize(cqs_b200_index* ix);
 int cqs_b200_reopen(cqs_b200_index* ix);
 void cqs_b200_destroy(cqs_b200_index* ix); /* syncs all streams first (src/cagra.rs:289-301) */
