@@ -47,7 +47,7 @@ struct Shard {
   uint64_t first_row = 0;  // offset of this shard's row 0 inside the index
   float* d_stage = nullptr;  // staging for row ingest
   uint64_t stage_rows = 0;
-  float* d_query = nullptr;   // [kBatchMax][ld]
+  float* d_query = nullptr;   // [ld], zero padded beyond dim
   float* h_query = nullptr;   // pinned
   uint32_t* d_bitset = nullptr;
   uint64_t bitset_words = 0;
@@ -105,7 +105,6 @@ struct Shard {
   SparseDev sparse;
 };
 
-constexpr uint32_t kQuerySlots = 1;  // single-query path keeps one query resident
 constexpr uint32_t kSpMaxQ = 1024;
 constexpr size_t kHostOutBytes = kMaxK * (8 + 4 + 4 + 4 + 1) + 64;
 
@@ -174,8 +173,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaSetDevice(device));
   CK(ix, cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(ix, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  CK(ix, cudaMalloc((void**)&s.d_query, sizeof(float) * ix->layout.ld * kQuerySlots));
-  CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld * kQuerySlots,
+  CK(ix, cudaMalloc((void**)&s.d_query, sizeof(float) * ix->layout.ld));
+  CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld,
                        cudaHostAllocDefault));
   CK(ix, cudaMalloc((void**)&s.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));

@@ -21,11 +21,20 @@
 //   * per lane 4 independent fp32 accumulators, then a 5-step shuffle
 //     butterfly: the summation tree is fixed (independent of grid size), error
 //     a few ulp, well inside the 1e-5 relative contract.
-//   * a row whose key beats the CTA's current threshold is appended to a
-//     shared-memory candidate buffer; the consumers re-select (bitonic sort)
-//     only when the buffer might overflow.  Each CTA emits <= k sorted keys;
-//     the last CTA to finish (atomic ticket) merges the G lists and writes the
-//     final (score desc, row asc) result.  One launch per query.
+//   * tiles are handed out by a global atomic counter (dynamic scheduling):
+//     SMs that stream faster take more tiles, all CTAs finish within ~1 us.
+//   * top-k, k <= 32: every consumer warp keeps a sorted 32-entry list in
+//     registers (ballot + shuffle insert; no shared memory, no barriers while
+//     streaming).  k > 32: a row whose key beats the CTA's current threshold
+//     is appended to a shared-memory candidate buffer that is re-selected
+//     (histogram select, ~3 us) only when it might overflow.  Each CTA emits
+//     <= k sorted keys; the last CTA to finish (atomic ticket) bounds the
+//     global k-th key from the list heads, pulls the few survivors and writes
+//     the final (score desc, row asc) result — straight into host-mapped
+//     memory on the latency path.  One launch per query.
+//   * optional structured filter (type / language codes) and the string-free
+//     part of the reference's scoring fold run inside the same loop, before
+//     the top-k (Store::search_filtered semantics).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
