@@ -44,7 +44,7 @@ constexpr uint32_t kStages = 4;
 constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kBatchThreads = 256;
+constexpr uint32_t kBatchThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr uint32_t kAccStages = 2;            // 2 x 256 TMEM columns
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kBatchSmem = kStages * kStageBytes + 1024;  // + alignment slack
@@ -150,7 +150,8 @@ constexpr uint32_t kSub = 64;        // slots per (query, CTA) sub-pool and roun
 constexpr uint32_t kMaxGridB = 160;  // sub-pool stride bound (SMs)
 
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle,
-// 4..7 = epilogue (warp % 4 selects the TMEM lane quarter = 32 queries).
+// 4..11 = epilogue: warp % 4 selects the TMEM lane quarter (32 queries), (warp-4)/4 the
+// column half (128 corpus rows): two threads share a query and split its columns.
 // A work item is (row chunk of 256, query tile of 128); items are dealt
 // round-robin so that neighbouring CTAs share the same row chunk through L2.
 __global__ void __launch_bounds__(kBatchThreads, 1)
@@ -161,7 +162,7 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   __shared__ __align__(8) uint64_t s_tfull[kAccStages], s_tempty[kAccStages];
   __shared__ uint32_t s_tmem_base;
-  __shared__ uint8_t s_subcnt[kBatchMaxQ];
+  __shared__ uint32_t s_subcnt[kBatchMaxQ];
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t i = threadIdx.x; i < kBatchMaxQ; i += kBatchThreads) s_subcnt[i] = 0;
@@ -175,7 +176,7 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     for (uint32_t a = 0; a < kAccStages; ++a) {
       mbar_init(&s_tfull[a], 1);
-      mbar_init(&s_tempty[a], 4);
+      mbar_init(&s_tempty[a], 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -246,12 +247,12 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = query, columns = corpus rows =====
-    const uint32_t quarter = warp & 3;
+    const uint32_t quarter = warp & 3, half = (warp - 4) >> 2;
     uint32_t acc = 0, aph = 0;
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint64_t chunk = item / p.n_qt;
       const uint32_t qt = (uint32_t)(item - chunk * p.n_qt);
-      const uint64_t row0 = p.row_begin + chunk * kBN;
+      const uint64_t row0 = p.row_begin + chunk * kBN + half * (kBN / 2);
       const uint32_t q = qt * kBM + quarter * 32 + lane;
       const bool active = q < p.nq;
       ckey_t thr_key = 0;
@@ -262,12 +263,11 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       mbar_wait(&s_tfull[acc], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kBN;
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kBN + half * (kBN / 2);
       ckey_t* my_cand = p.cand + (size_t)q * p.cap;
       ckey_t* my_sub = p.sub + ((size_t)q * gridDim.x + blockIdx.x) * kSub;
-      uint32_t my_cnt = active ? s_subcnt[q] : 0;
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < kBN; c0 += 32) {
+      for (uint32_t c0 = 0; c0 < kBN / 2; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         if (!active) continue;
@@ -297,13 +297,13 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               bool ok = key > thr_key;
               if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
               if (ok) {
-                if (my_cnt < kSub) my_sub[my_cnt++] = key; else p.overflow[q] = 1;
+                const uint32_t slot = atomicAdd(&s_subcnt[q], 1u);  // shared with the other half's thread
+                if (slot < kSub) my_sub[slot] = key; else p.overflow[q] = 1;
               }
             }
           }
         }
       }
-      if (active) s_subcnt[q] = (uint8_t)my_cnt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_tempty[acc]);
@@ -313,15 +313,13 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   }
-  if (warp >= 4 && !p.dense) {
-    // publish this CTA's sub-pool fill levels (each thread owns its queries)
-    for (uint32_t qt = 0; qt < p.n_qt; ++qt) {
-      const uint32_t q = qt * kBM + (warp & 3) * 32 + lane;
-      p.subcnt[(size_t)blockIdx.x * p.nq_pad + q] = s_subcnt[q];
-    }
-  }
   tc_fence_before();
   __syncthreads();
+  if (!p.dense) {
+    // publish this CTA's sub-pool fill levels
+    for (uint32_t q = threadIdx.x; q < p.nq_pad; q += kBatchThreads)
+      p.subcnt[(size_t)blockIdx.x * p.nq_pad + q] = (uint8_t)min(s_subcnt[q], kSub);
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
