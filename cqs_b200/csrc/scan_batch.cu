@@ -44,7 +44,8 @@ constexpr uint32_t kStages = 4;
 constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kBatchThreads = 384;  // 4 control warps + 8 epilogue warps
+constexpr uint32_t kEpiParts = 4;          // column parts per TMEM lane quarter
+constexpr uint32_t kBatchThreads = 128 + 128 * kEpiParts;  // 4 control warps + 4*kEpiParts epilogue warps
 constexpr uint32_t kAccStages = 2;            // 2 x 256 TMEM columns
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kBatchSmem = kStages * kStageBytes + 1024;  // + alignment slack
@@ -176,7 +177,7 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     for (uint32_t a = 0; a < kAccStages; ++a) {
       mbar_init(&s_tfull[a], 1);
-      mbar_init(&s_tempty[a], 8);
+      mbar_init(&s_tempty[a], 4 * kEpiParts);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -247,12 +248,12 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread = query, columns = corpus rows =====
-    const uint32_t quarter = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t quarter = warp & 3, half = (warp - 4) >> 2;  // half = column part
     uint32_t acc = 0, aph = 0;
     for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint64_t chunk = item / p.n_qt;
       const uint32_t qt = (uint32_t)(item - chunk * p.n_qt);
-      const uint64_t row0 = p.row_begin + chunk * kBN + half * (kBN / 2);
+      const uint64_t row0 = p.row_begin + chunk * kBN + half * (kBN / kEpiParts);
       const uint32_t q = qt * kBM + quarter * 32 + lane;
       const bool active = q < p.nq;
       ckey_t thr_key = 0;
@@ -263,11 +264,11 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       mbar_wait(&s_tfull[acc], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kBN + half * (kBN / 2);
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kBN + half * (kBN / kEpiParts);
       ckey_t* my_cand = p.cand + (size_t)q * p.cap;
       ckey_t* my_sub = p.sub + ((size_t)q * gridDim.x + blockIdx.x) * kSub;
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < kBN / 2; c0 += 32) {
+      for (uint32_t c0 = 0; c0 < kBN / kEpiParts; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         if (!active) continue;
