@@ -365,48 +365,47 @@ __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, u
                                                                  const uint8_t* subcnt,
                                                                  uint32_t sub_grid, uint32_t nq_pad) {
   __shared__ ckey_t s_buf[kUpdCap];
+  __shared__ uint32_t s_hist[kSelBuckets + 96];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
-  TopK tk{s_buf, &s_cnt, &s_thr, kUpdCap, Group{tid, kUpdThreads, 0}};
+  TopK tk{s_buf, &s_cnt, &s_thr, kUpdCap, Group{tid, kUpdThreads, 0}, s_hist};
   tk.init();
   __syncthreads();
   ckey_t* pool = cand + (size_t)q * cap;
   const uint32_t n = min(cnt[q], cap);
-  const uint32_t step = kUpdCap / 2 - kprime;  // pushes per compaction (upper half = scratch)
-  for (uint32_t base = 0; base < n; base += step) {
+  // the pool itself (k' keys, or the 18,944 keys of the dense round): chunks of cap/2 pushes,
+  // shrunk by the histogram select in between (a superset of the k' best survives)
+  constexpr uint32_t kStep = kUpdCap / 2;
+  for (uint32_t base = 0; base < n; base += kStep) {
+    if (s_cnt + kStep > kUpdCap) tk.template select<kUpdCap / kUpdThreads>(kprime);
     const ckey_t t = s_thr;
-    const uint32_t end = min(n, base + step);
+    const uint32_t end = min(n, base + kStep);
     for (uint32_t i = base + tid; i < end; i += kUpdThreads) {
       const ckey_t key = pool[i];
       if (key > t) tk.push(key);
     }
-    tk.compact(kprime);
+    __syncthreads();
   }
-  // this round's sub-pools.  Usually everything fits at once (a few hundred keys per query
-  // and round); otherwise `per` sub-pools between compactions (per * kSub <= step).
-  __shared__ uint32_t s_total;
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-  {
-    uint32_t mine = 0;
-    for (uint32_t c = tid; c < sub_grid; c += kUpdThreads) mine += subcnt[(size_t)c * nq_pad + q];
-    if (mine) atomicAdd(&s_total, mine);
-  }
-  __syncthreads();
-  const uint32_t per = (s_cnt + s_total <= kUpdCap / 2) ? sub_grid + 1 : step / kSub;
-  for (uint32_t c0 = 0; c0 < sub_grid; c0 += per) {
+  // this round's sub-pools: one thread per (CTA) sub-pool walks its few keys; at most
+  // kSub * 32 = cap/2 pushes between two selects
+  for (uint32_t c0 = 0; c0 < sub_grid; c0 += 32) {
+    if (s_cnt + 32 * kSub > kUpdCap) tk.template select<kUpdCap / kUpdThreads>(kprime);
     const ckey_t t = s_thr;
-    const uint32_t c1 = min(sub_grid, c0 + per);
-    for (uint32_t i = tid; i < (c1 - c0) * kSub; i += kUpdThreads) {
-      const uint32_t c = c0 + i / kSub, j = i % kSub;
-      if (j < subcnt[(size_t)c * nq_pad + q]) {
-        const ckey_t key = sub[((size_t)q * sub_grid + c) * kSub + j];
+    const uint32_t c1 = min(sub_grid, c0 + 32);
+    // 8 threads per sub-pool
+    for (uint32_t i = tid; i < (c1 - c0) * 8; i += kUpdThreads) {
+      const uint32_t c = c0 + (i >> 3);
+      const uint32_t m = subcnt[(size_t)c * nq_pad + q];
+      const ckey_t* sp = sub + ((size_t)q * sub_grid + c) * kSub;
+      for (uint32_t j = i & 7; j < m; j += 8) {
+        const ckey_t key = sp[j];
         if (key > t) tk.push(key);
       }
     }
-    tk.compact(kprime);
+    __syncthreads();
   }
+  tk.compact(kprime);
   const uint32_t m = s_cnt;
   for (uint32_t i = tid; i < m; i += kUpdThreads) pool[i] = s_buf[i];
   if (tid == 0) {
