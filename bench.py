@@ -161,6 +161,119 @@ def run_reference(args):
     }))
 
 
+def run_batch(args):
+    """--workload batch: BASELINE configs[2] (10M x 768 bf16, 1024-query batches, top-20; N=1) and
+    configs[3]'s batch half (rows row-sharded over N GPUs; per-shard tensor-core scan + exact
+    rescoring, then ONE gather+merge kernel over NVLink peer memory).  A step = one batch through
+    the C ABI with host buffers (cqs_b200_search_batch / _search_batch_sharded)."""
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib
+    from cqs_b200.sharded import PeerGroup, search_batch_sharded, shard_range
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n_total = args.rows
+    row0, n_local = shard_range(n_total, world, rank)
+    nq = args.queries_per_step
+    ix = cqs_b200.B200Index(DIM, storage=args.storage, devices=[local], row_base=row0)
+    ix.reserve(n_local)
+    for blk in gen_rows_torch(torch, dev, row0, n_local):
+        ix.append_device(blk.data_ptr(), blk.shape[0])
+        del blk
+    ix.finalize()
+    ix.set_timing(True)
+    torch.cuda.empty_cache()
+    pg = PeerGroup.from_dist(dist, local, max_elems=nq * K) if world > 1 else None
+    lib.cqs_b200_debug_last_batch_ms.restype = C.c_float      # device ms of the last batch pipeline
+    lib.cqs_b200_debug_last_batch_ms.argtypes = [C.c_void_p]
+    queries = make_queries(nq * (args.steps + args.warmup), 7)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(s):
+        q = queries[s * nq:(s + 1) * nq]
+        if pg is not None:
+            return search_batch_sharded(ix, pg, q, K)
+        return ix.search_batch_rows(q, K)
+
+    for s in range(args.warmup):
+        step(s)
+    barrier()
+    launches0 = lib.cqs_b200_kernel_launches()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    dev_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        last = step(args.warmup + s)
+        dev_ms += lib.cqs_b200_debug_last_batch_ms(ix._h)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clk.__exit__()
+    launches = lib.cqs_b200_kernel_launches() - launches0
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        # sanity: the batch answer equals the single-query path on a few queries (N=1 only: the
+        # sharded single-query call is collective)
+        agree = None
+        if world == 1:
+            q = queries[(args.warmup + args.steps - 1) * nq:]
+            agree = sum(int(np.array_equal(last[0][i, :last[2][i]], ix.search_rows(q[i], K)[0])) for i in (0, 1, nq // 2, nq - 1))
+        peak_tf = 1668.9
+        src = "fallback"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_tf, src = float(mp["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+        flop = 2.0 * nq * n_local * DIM                      # per batch pipeline, per GPU
+        tf = flop / (dev_ms / args.steps / 1e3) / 1e12
+        print(json.dumps({
+            "metric": f"queries_per_s_exact_top20_{n_total}x{DIM}_{args.storage}_batch{nq}",
+            "value": nq * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (tcgen05), candidates re-scored in f32",
+            "data": "synthetic",
+            "config": {"workload": f"exact top-{K}, {nq}-query batches, {n_total}x{DIM} {args.storage} "
+                                   f"(BASELINE configs[2]/[3]), row-sharded over {world} GPU(s)",
+                       "rows_per_gpu": n_local,
+                       "l2": f"per-GPU shard {n_local * DIM * 2 / 1e6:.0f} MB > 126 MB L2: no flush needed",
+                       "collective": "none" if world == 1 else "one gather+merge kernel per batch over NVLink peer memory (csrc/peer.cu)",
+                       "value_is": "device time of the batch pipeline (CUDA events on the library's stream), max over ranks"},
+            "clocks": clk.summary(),
+            "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "ms_per_batch": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 12 + nq * 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "traffic": None, "peak_source": src, "kernel": "scan_batch_kernel (+ threshold updates, rescore)",
+                         "algorithmic_flop_per_launch": flop},
+            "batch_equals_single_query_path": None if agree is None else f"{agree}/4",
+        }))
+    if pg is not None:
+        st = pg.status()
+        dist.barrier()
+        pg.close()
+        if st:
+            raise RuntimeError("peer exchange timed out during the run")
+    if world > 1:
+        dist.destroy_process_group()
+    ix.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -171,12 +284,22 @@ def main():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-shard top-k lists are exchanged — 'peer' = inside the scan kernel "
+                         "over NVLink peer memory (product path), 'nccl' = all_gather_into_tensor + merge kernel")
     ap.add_argument("--hnsw-rows", type=int, default=100_000,
                     help="rows of the corpus the CPU HNSW baseline is built on (0 = skip)")
+    ap.add_argument("--workload", default="single", choices=["single", "batch"],
+                    help="single = BASELINE configs[1] (the headline, default); batch = configs[2]/[3]: "
+                         "1024-query tensor-core batches (use --rows 10000000 --storage bf16 --queries-per-step 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == "batch":
+        if args.storage == "f32":
+            args.storage = "bf16"
+        return run_batch(args)
 
     import torch
     import cqs_b200
@@ -221,6 +344,10 @@ def main():
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
     d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
+    pg = None
+    if world > 1 and args.transport == "peer":
+        from cqs_b200.sharded import PeerGroup
+        pg = PeerGroup.from_dist(dist, local)   # CUDA IPC mailboxes; handles swapped over the process group
     if world > 1:
         g_sc = torch.empty((world, Q, K), dtype=torch.float32, device=dev)
         g_rw = torch.empty((world, Q, K), dtype=torch.int64, device=dev)
@@ -229,8 +356,18 @@ def main():
         m_n = torch.empty((Q,), dtype=torch.int32, device=dev)
 
     def step_device(s: int):
-        """Q single-query scans (one kernel each), then (N>1) one all-gather + merge."""
+        """Q single-query scans, one kernel each.  N>1: the kernel also pushes its top-k to every
+        peer over NVLink, waits for theirs and merges (transport 'peer'); or one all-gather +
+        merge kernel per step (transport 'nccl')."""
         base = s * Q
+        if pg is not None:
+            for i in range(Q):
+                qp = d_queries.data_ptr() + (base + i) * DIM * 4
+                check(lib.cqs_b200_search_sharded_device(ix._h, pg._h, C.c_void_p(qp), K, None,
+                                                         C.c_void_p(m_sc.data_ptr() + i * K * 4),
+                                                         C.c_void_p(m_rw.data_ptr() + i * K * 8),
+                                                         C.c_void_p(m_n.data_ptr() + i * 4), sp))
+            return
         for i in range(Q):
             qp = d_queries.data_ptr() + (base + i) * DIM * 4
             check(lib.cqs_b200_search_device(ix._h, C.c_void_p(qp), K, None,
@@ -285,9 +422,19 @@ def main():
     p_rows, p_sc, p_n = out_rows.ctypes.data_as(C.c_void_p), out_sc.ctypes.data_as(C.c_void_p), C.byref(out_n)
     search = lib.cqs_b200_search
 
+    search_sh = lib.cqs_b200_search_sharded
+
     def step_e2e(s: int):
         base = s * Q
-        if world == 1:
+        if pg is not None:
+            # sharded, product path: host query in, GLOBAL host top-k out, one launch per rank
+            for i in range(Q):
+                t0 = time.perf_counter()
+                rc = search_sh(ix._h, pg._h, C.c_void_p(q_base + (base + i) * DIM * 4), K, None, p_rows, p_sc, p_n)
+                lat.append(time.perf_counter() - t0)
+                if rc:
+                    check(rc)
+        elif world == 1:
             for i in range(Q):
                 t0 = time.perf_counter()
                 rc = search(ix._h, C.c_void_p(q_base + (base + i) * DIM * 4), K, None, p_rows, p_sc, p_n)
@@ -338,10 +485,13 @@ def main():
                                    f"(BASELINE configs[1]), row-sharded over {world} GPU(s)",
                        "queries_per_step": Q, "rows_per_gpu": n_local,
                        "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",
-                       "collective": "none" if world == 1 else "2 x all_gather_into_tensor per step (scores, rows) + merge kernel"},
+                       "collective": "none" if world == 1 else (
+                           "none: every scan kernel stores its top-k into the peers' mailboxes over NVLink, "
+                           "waits for theirs and merges in its own tail (csrc/peer.cuh)" if pg is not None else
+                           "2 x all_gather_into_tensor per step (scores, rows) + merge kernel")},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
-                    "d2h_bytes_per_step": Q * K * 12 + (Q * 4 if world == 1 else 0)},
+                    "d2h_bytes_per_step": Q * K * 12 + (Q * 4 if (world == 1 or pg is not None) else 0)},
             "gpu_launches": int(launches),
             "p50_ms_e2e": float(np.median(lat) * 1e3) if lat else None,
             "p95_ms_e2e": float(np.percentile(lat, 95) * 1e3) if lat else None,
@@ -402,6 +552,11 @@ def main():
                               "approximate: speed baseline only"}
                 hn_index.close()
         print(json.dumps(line))
+    if pg is not None:
+        if pg.status() != 0:
+            raise RuntimeError("peer exchange timed out during the run")
+        dist.barrier()
+        pg.close()
     if world > 1:
         dist.destroy_process_group()
     ix.close()

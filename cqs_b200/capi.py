@@ -51,6 +51,17 @@ SIGNATURES = {
     "cqs_b200_search_device": (C.c_int, [vp, vp, C.c_uint32, vp, vp, vp, vp, vp]),
     "cqs_b200_merge_topk_device": (C.c_int, [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32,
                                              vp, vp, vp, vp]),
+    "cqs_b200_peer_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "cqs_b200_peer_handle": (C.c_int, [vp, vp]),
+    "cqs_b200_peer_connect": (C.c_int, [vp, vp]),
+    "cqs_b200_peer_connect_local": (C.c_int, [C.POINTER(vp), C.c_uint32]),
+    "cqs_b200_peer_set_timeout_ms": (C.c_int, [vp, C.c_uint32]),
+    "cqs_b200_peer_status": (C.c_int, [vp]),
+    "cqs_b200_peer_destroy": (None, [vp]),
+    "cqs_b200_search_sharded": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, vp]),
+    "cqs_b200_search_sharded_device": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]),
+    "cqs_b200_search_batch_sharded": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
+    "cqs_b200_peer_gather_merge": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_len": (C.c_uint64, [vp]),
     "cqs_b200_dim": (C.c_uint32, [vp]),
     "cqs_b200_max_k": (C.c_uint32, [vp]),

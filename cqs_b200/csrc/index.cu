@@ -17,6 +17,7 @@
 
 #include "../../include/cqs_b200.h"
 #include "internal.h"
+#include "peer_host.h"
 
 namespace cqs {
 std::atomic<uint64_t> g_kernel_launches{0};
@@ -33,6 +34,11 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   t_last_error = buf;
   return code;
+}
+
+// used by the other translation units (peer.cu) to report through the same thread-local slot
+__attribute__((visibility("hidden"))) int cqs_b200_internal_fail(int code, const char* msg) {
+  return fail(code, "%s", msg);
 }
 
 namespace {
@@ -95,6 +101,9 @@ struct Shard {
   uint64_t* d_bout_rows = nullptr;
   uint32_t* d_bout_n = nullptr;   // [kBatchMaxQ]
   uint32_t* d_bflags = nullptr;   // [kBatchMaxQ]
+  float* d_bm_scores = nullptr;   // [kBatchMaxQ][kMaxK] cross-shard merged results (sharded batch)
+  uint64_t* d_bm_rows = nullptr;
+  uint32_t* d_bm_n = nullptr;
   float* d_maxnorm = nullptr;     // [1]
   float max_row_norm = 0.f;
   // structured filter / per-row signals (cqs_b200_set_row_meta / _signals)
@@ -157,6 +166,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
   cudaFree(s.d_bout_n); cudaFree(s.d_bflags); cudaFree(s.d_maxnorm);
+  cudaFree(s.d_bm_scores); cudaFree(s.d_bm_rows); cudaFree(s.d_bm_n);
   cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
   cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
   if (s.h_query) cudaFreeHost(s.h_query);
@@ -475,7 +485,7 @@ constexpr size_t kOffScores = 0, kOffRows = sizeof(float) * kMaxK,
 // completion word (the latency path of cqs_b200_search); otherwise into the device pool.
 static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
                         const uint32_t* bitset, const ScanSignals* sig = nullptr,
-                        bool to_host = false) {
+                        bool to_host = false, const PeerCtx* peer = nullptr) {
   CK(ix, cudaSetDevice(s.device));
   if (int rc = order_after_last(ix, s, s.stream)) return rc;
   memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
@@ -504,10 +514,35 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   }
   a.d_trace = s.d_trace;
   a.signals = sig;
+  a.peer = peer;
   if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
   if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
   return mark_last(ix, s, s.stream);
+}
+
+// Poll the completion word the kernel writes into mapped host memory; fall back to the
+// stream status every so often so a faulted kernel cannot hang the caller.
+static int wait_host_flag(cqs_b200_index* ix, Shard& s) {
+  volatile uint32_t* flag = (volatile uint32_t*)(s.h_out + kOffFlag);
+  for (uint64_t spin = 0; *flag != s.seq; ++spin) {
+    if ((spin & 0xFFF) == 0xFFF) {
+      CK(ix, cudaSetDevice(s.device));
+      cudaError_t e = cudaStreamQuery(s.stream);
+      if (e == cudaSuccess) {
+        if (*flag != s.seq) {
+          ix->poisoned.store(1);
+          return fail(CQS_B200_ERR_CUDA, "scan finished without publishing its result");
+        }
+        break;
+      }
+      if (e != cudaErrorNotReady) CK(ix, e);
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  return 0;
 }
 
 static int check_searchable(cqs_b200_index* ix) {
@@ -549,26 +584,7 @@ static int search_impl(cqs_b200_index* ix, const float* query, uint32_t k, const
   }
   float kms = 0.f;
   for (Shard* s : live) {
-    // poll the completion word the kernel writes into mapped host memory; fall back to the
-    // stream status every so often so a faulted kernel cannot hang the caller
-    volatile uint32_t* flag = (volatile uint32_t*)(s->h_out + kOffFlag);
-    for (uint64_t spin = 0; *flag != s->seq; ++spin) {
-      if ((spin & 0xFFF) == 0xFFF) {
-        CK(ix, cudaSetDevice(s->device));
-        cudaError_t e = cudaStreamQuery(s->stream);
-        if (e == cudaSuccess) {
-          if (*flag != s->seq) {
-            ix->poisoned.store(1);
-            return fail(CQS_B200_ERR_CUDA, "scan finished without publishing its result");
-          }
-          break;
-        }
-        if (e != cudaErrorNotReady) CK(ix, e);
-      }
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
+    if (int rcw = wait_host_flag(ix, *s)) return rcw;
     if (ix->timing) {
       CK(ix, cudaSetDevice(s->device));
       CK(ix, cudaEventSynchronize(s->ev1));
@@ -743,6 +759,90 @@ int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t
   return CQS_B200_OK;
 }
 
+// ---- row-sharded corpus over NVLink peer memory (peer.cu / peer.cuh) ----------
+static int check_peer(cqs_b200_index* ix, cqs_b200_peer* peer) {
+  if (!peer) return fail(CQS_B200_ERR_INVALID, "peer is NULL");
+  if (ix->shards.size() != 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "a sharded search needs a single-device index per rank");
+  if (peer->device != ix->shards[0].device)
+    return fail(CQS_B200_ERR_INVALID, "peer group and index live on different devices");
+  if (!peer->connected) return fail(CQS_B200_ERR_INVALID, "peer group is not connected");
+  if (peer->failed.load()) return fail(CQS_B200_ERR_POISONED, "peer group failed earlier; rebuild it");
+  if (ix->shards[0].n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty shard");
+  return 0;
+}
+
+int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_query,
+                                   uint32_t k, const uint32_t* d_bitset, float* d_out_scores,
+                                   uint64_t* d_out_rows, uint32_t* d_out_n, void* stream) {
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!d_query || !d_out_scores || !d_out_rows || !d_out_n)
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u out of range 1..%u", k, kMaxK);
+  std::lock_guard<std::mutex> g(ix->mu);
+  if ((rc = check_peer(ix, peer))) return rc;
+  std::lock_guard<std::mutex> gp(peer->mu);
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+  if (int rc2 = order_after_last(ix, s, st)) return rc2;
+  const float* qp = d_query;
+  if (ix->layout.ld != ix->dim) {
+    CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
+    CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+    qp = s.d_query;
+  }
+  PeerCtx pc;
+  CK(ix, peer_begin(peer, st, &pc));
+  ScanArgs a;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
+  a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
+  a.peer = &pc;
+  CK(ix, launch_scan_single(a, s.num_sms, st));
+  CK(ix, peer_mark(peer, st));
+  return mark_last(ix, s, st);
+}
+
+int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query, uint32_t k,
+                            const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                            uint32_t* out_n) {
+  if (out_n) *out_n = 0;
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (!query || !out_rows || !out_scores || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u out of range 1..%u", k, kMaxK);
+  // a non-finite query gives an empty result on EVERY rank (src/cagra.rs:458-470); the ranks
+  // all see the same query, so skipping the exchange keeps their sequence numbers aligned
+  if (!query_is_finite(query, ix->dim)) return CQS_B200_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  if ((rc = check_peer(ix, peer))) return rc;
+  std::lock_guard<std::mutex> gp(peer->mu);
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  PeerCtx pc;
+  CK(ix, peer_begin(peer, s.stream, &pc));
+  if ((rc = launch_dense(ix, s, query, k, bitset, nullptr, /*to_host=*/true, &pc))) return rc;
+  CK(ix, peer_mark(peer, s.stream));
+  if ((rc = wait_host_flag(ix, s))) return rc;
+  uint32_t n = std::min(*(uint32_t*)(s.h_out + kOffN), k);
+  if (n == 0) {
+    // empty can also mean "a peer never answered": the kernel raised the sticky status word
+    uint32_t st = 0;
+    CK(ix, cudaMemcpy(&st, peer->d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st) {
+      peer->failed.store(1);
+      return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this search)");
+    }
+  }
+  memcpy(out_scores, s.h_out + kOffScores, sizeof(float) * n);
+  memcpy(out_rows, s.h_out + kOffRows, sizeof(uint64_t) * n);
+  *out_n = n;
+  return CQS_B200_OK;
+}
+
 // Tensor-core path for one chunk of <= kBatchMaxQ queries on a single-device bf16 index.
 static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
                            const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
@@ -843,6 +943,90 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
       if (rc) return rc;
     }
     ix->last_batch_reruns += (uint32_t)rerun.size();
+  }
+  return CQS_B200_OK;
+}
+
+int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries,
+                                  uint32_t nq, uint32_t k, const uint32_t* bitset,
+                                  uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (nq && (!queries || !out_rows || !out_scores || !out_n))
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u out of range 1..%u", k, kMaxK);
+  for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
+  if (nq == 0) return CQS_B200_OK;
+  {
+    std::lock_guard<std::mutex> g(ix->mu);
+    if ((rc = check_peer(ix, peer))) return rc;
+  }
+  const bool tensor_path = ix->storage != CQS_B200_STORAGE_F32 && nq >= 8 && ix->n_rows < (1ull << 31);
+  if (!tensor_path) {
+    // every rank takes this branch together (same nq, same storage): one fused
+    // scan + exchange per query
+    for (uint32_t i = 0; i < nq; ++i) {
+      rc = cqs_b200_search_sharded(ix, peer, queries + (size_t)i * ix->dim, k, bitset,
+                                   out_rows + (size_t)i * k, out_scores + (size_t)i * k, out_n + i);
+      if (rc) return rc;
+    }
+    return CQS_B200_OK;
+  }
+  // exchange granularity: as many queries as fit the mailbox (identical on every rank)
+  const uint32_t q_per_x = std::min<uint32_t>(std::min(kBatchMaxQ, kPeerMaxQ), peer->cap / k);
+  for (uint32_t q0 = 0; q0 < nq; q0 += q_per_x) {
+    const uint32_t m = std::min(q_per_x, nq - q0);
+    const float* qs = queries + (size_t)q0 * ix->dim;
+    uint64_t* orow = out_rows + (size_t)q0 * k;
+    float* osc = out_scores + (size_t)q0 * k;
+    std::vector<uint32_t> rerun;
+    // 1. local shard: tensor-core candidate scan + exact rescoring; lists stay in d_bout_*
+    if ((rc = search_batch_tc(ix, qs, m, k, bitset, orow, osc, out_n + q0, &rerun))) return rc;
+    std::vector<uint8_t> bad(m, 0);
+    for (uint32_t i = 0; i < m; ++i) bad[i] = !query_is_finite(qs + (size_t)i * ix->dim, ix->dim);
+    // 2. queries whose candidate pool could not be proven complete: exact scan, patched into the lists
+    for (uint32_t i : rerun) {
+      rc = cqs_b200_search(ix, qs + (size_t)i * ix->dim, k, bitset, orow + (size_t)i * k,
+                           osc + (size_t)i * k, out_n + q0 + i);
+      if (rc) return rc;
+    }
+    ix->last_batch_reruns += (uint32_t)rerun.size();
+    std::lock_guard<std::mutex> g(ix->mu);
+    std::lock_guard<std::mutex> gp(peer->mu);
+    Shard& s = ix->shards[0];
+    CK(ix, cudaSetDevice(s.device));
+    if (!s.d_bm_scores) {
+      CK(ix, cudaMalloc((void**)&s.d_bm_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+      CK(ix, cudaMalloc((void**)&s.d_bm_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+      CK(ix, cudaMalloc((void**)&s.d_bm_n, sizeof(uint32_t) * kBatchMaxQ));
+    }
+    for (uint32_t i : rerun) {
+      CK(ix, cudaMemcpyAsync(s.d_bout_scores + (size_t)i * k, osc + (size_t)i * k, sizeof(float) * out_n[q0 + i],
+                             cudaMemcpyHostToDevice, s.stream));
+      CK(ix, cudaMemcpyAsync(s.d_bout_rows + (size_t)i * k, orow + (size_t)i * k, sizeof(uint64_t) * out_n[q0 + i],
+                             cudaMemcpyHostToDevice, s.stream));
+      CK(ix, cudaMemcpyAsync(s.d_bout_n + i, out_n + q0 + i, sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    }
+    // 3. push the lists to every peer, wait for theirs, merge (one kernel, no collective call)
+    PeerCtx pc;
+    CK(ix, peer_begin(peer, s.stream, &pc));
+    PeerGatherArgs ga{s.d_bout_scores, s.d_bout_rows, s.d_bout_n, m, k,
+                      s.d_bm_scores, s.d_bm_rows, s.d_bm_n, peer->d_ticket};
+    CK(ix, launch_peer_gather_merge(pc, ga, s.num_sms, s.stream));
+    CK(ix, peer_mark(peer, s.stream));
+    std::vector<uint32_t> ns(m);
+    uint32_t status = 0;
+    CK(ix, cudaMemcpyAsync(osc, s.d_bm_scores, sizeof(float) * (size_t)m * k, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaMemcpyAsync(orow, s.d_bm_rows, sizeof(uint64_t) * (size_t)m * k, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaMemcpyAsync(ns.data(), s.d_bm_n, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaMemcpyAsync(&status, peer->d_status, sizeof status, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaStreamSynchronize(s.stream));
+    if (status) {
+      peer->failed.store(1);
+      for (uint32_t i = 0; i < m; ++i) out_n[q0 + i] = 0;
+      return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
+    }
+    for (uint32_t i = 0; i < m; ++i) out_n[q0 + i] = bad[i] ? 0 : std::min(ns[i], k);
   }
   return CQS_B200_OK;
 }

@@ -9,6 +9,7 @@
 namespace cqs {
 
 typedef unsigned long long ckey_t;
+struct PeerCtx;  // peer.cuh
 
 constexpr uint32_t kMaxK = 1024;        // CQS_B200_MAX_K
 constexpr uint32_t kMaxGrid = 1024;     // upper bound on scan CTAs (partial-list slots)
@@ -60,6 +61,7 @@ struct ScanArgs {
   const ScanSignals* signals = nullptr;
   uint32_t* d_host_flag = nullptr;  // device alias of a host-mapped completion word (nullable)
   uint32_t seq = 0;                 // value written to it
+  const PeerCtx* peer = nullptr;    // row-sharded corpus: exchange + merge in the kernel tail; out_* = GLOBAL top-k
 };
 // Kernel 1+3: single-query streaming scan with the top-k select fused in.
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);
@@ -155,5 +157,19 @@ cudaError_t launch_rrf_fuse(const uint64_t* d_ids, const uint32_t* d_list_off, u
 cudaError_t launch_route_centroids(const float* d_centroids, uint32_t n_c, uint32_t dim,
                                    const float* d_queries, uint32_t nq, float threshold,
                                    int32_t* d_out_cat, float* d_out_margin, cudaStream_t stream);
+
+// ---- peer-memory exchange (row-sharded corpora) ----
+struct PeerGatherArgs {
+  const float* d_scores;   // [nq][k] this rank's sorted lists
+  const uint64_t* d_rows;  // [nq][k] GLOBAL rows
+  const uint32_t* d_n;     // [nq]
+  uint32_t nq, k;
+  float* d_out_scores;     // [nq][k] GLOBAL top-k on every rank
+  uint64_t* d_out_rows;
+  uint32_t* d_out_n;
+  uint32_t* d_ticket;      // [2] zero between launches
+};
+cudaError_t launch_peer_gather_merge(const PeerCtx& c, const PeerGatherArgs& a, int num_sms,
+                                     cudaStream_t stream);
 
 }  // namespace cqs

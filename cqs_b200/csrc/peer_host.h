@@ -1,0 +1,40 @@
+// peer_host.h — host-side state of a peer group (cqs_b200_peer, include/cqs_b200.h).
+// Shared by peer.cu (lifecycle, the stand-alone gather+merge) and index.cu (the
+// scan kernels that carry the exchange in their tail).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "peer.cuh"
+
+struct cqs_b200_peer {
+  std::mutex mu;
+  int device = 0;
+  int num_sms = 148;
+  uint32_t world = 0, rank = 0, cap = 0;
+  uint64_t block_bytes = 0;
+  size_t bytes = 0;                 // size of one mailbox
+  uint8_t* d_mbox = nullptr;        // this rank's mailbox (cudaMalloc: exportable over CUDA IPC)
+  uint8_t* mbox[cqs::kPeerMaxWorld] = {};
+  bool ipc_opened[cqs::kPeerMaxWorld] = {};
+  bool connected = false;
+  uint32_t* d_status = nullptr;     // sticky: 1 = an exchange timed out
+  uint32_t* d_ticket = nullptr;     // [2] CTA tickets of the stand-alone kernel
+  uint32_t seq = 0;                 // exchanges issued so far (identical on every rank)
+  uint64_t timeout_ns = 5ull * 1000 * 1000 * 1000;
+  // exchanges must execute on the device in issue order (the mailbox slots are reused):
+  // a launch on a different stream waits for the previous one
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
+  std::atomic<int> failed{0};
+};
+
+namespace cqs {
+// Next exchange of the group: fills `c` and orders stream `st` after the previous exchange.
+// Call with p->mu held; follow the launch with peer_mark(p, st).
+cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c);
+cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st);
+}  // namespace cqs

@@ -39,6 +39,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "peer.cuh"
 
 namespace cqs {
 
@@ -99,6 +100,7 @@ struct ScanParams {
   ScanSignals sig;            // structured filter + per-row signals (sig.pipeline / sig.d_ctype gate them)
   uint32_t* host_flag;        // optional: host-mapped word that receives `seq` once the result is written
   uint32_t seq;
+  PeerCtx peer;               // peer.world != 0: exchange the local list with the other shards and emit the GLOBAL top-k
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -394,9 +396,33 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   TRACE(3);
   if (!s_last) return;
   __threadfence();
-  merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                             p.row_base, p.out_scores, p.out_rows, p.out_n,
-                                             p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+  if (p.peer.world == 0) {
+    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
+                                               p.row_base, p.out_scores, p.out_rows, p.out_n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+  } else {
+    // Row-sharded corpus: the shard's list goes into this rank's own mailbox
+    // block and, by plain stores over NVLink, into every peer's; one release flag per peer
+    // publishes it; then wait for the peers' lists and merge — the all-gather and the merge
+    // ride in the tail of the scan, no collective call and no extra launch.
+    const PeerBlock own = peer_block(p.peer, p.peer.rank, p.peer.rank);
+    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
+                                               p.row_base, own.scores, own.rows, own.n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+    const uint32_t n = *tk.cnt;  // sorted keys are still in tk.buf[0..n)
+    for (uint32_t e = ctid; e < p.peer.world * k; e += kConsumers) {
+      const uint32_t g = e / k, i = e - g * k;
+      if (g == p.peer.rank || i >= n) continue;
+      const PeerBlock pb = peer_block(p.peer, g, p.peer.rank);
+      const ckey_t key = s_buf[i];
+      pb.scores[i] = key_score(key);
+      pb.rows[i] = p.row_base + key_row(key);
+    }
+    if (ctid < p.peer.world && ctid != p.peer.rank) peer_block(p.peer, ctid, p.peer.rank).n[0] = n;
+    peer_signal(p.peer, tk.g);
+    if (peer_wait(p.peer, tk.g)) peer_merge_query(p.peer, tk.g, 0, k, p.out_scores, p.out_rows, p.out_n);
+    else peer_emit_empty(tk.g, k, p.out_scores, p.out_rows, p.out_n);
+  }
   TRACE(4);
   if (p.host_flag) {
     // the result went straight into host-mapped memory: make it visible system-wide, then
@@ -489,6 +515,7 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   if (a.signals) p.sig = *a.signals;
   p.host_flag = a.d_host_flag;
   p.seq = a.seq;
+  if (a.peer) p.peer = *a.peer;
   switch (a.layout.mode) {
     case 0: return launch_mode<0>(p, a.layout.nv, num_sms, st);
     case 1: return launch_mode<1>(p, a.layout.nv, num_sms, st);

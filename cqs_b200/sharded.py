@@ -1,9 +1,16 @@
 """Row-sharded corpora across processes: one process per GPU,
-contiguous row blocks in ascending-chunk-id order, per-shard top-k left on the
-device, ONE small all-gather, deterministic merge with the reference's ordering
-rule (score desc by f32 total order, row asc — candidate.rs:321-329).  The
-reference has no multi-GPU path; this is the B200-side extension of
-VectorIndex::search for corpora that do not fit (or should not sit on) one GPU.
+contiguous row blocks in ascending-chunk-id order, per-shard top-k, then the
+lists are exchanged and merged with the reference's ordering rule (score desc
+by f32 total order, row asc — candidate.rs:321-329).  The reference has no
+multi-GPU path; this is the B200-side extension of VectorIndex::search for
+corpora that do not fit (or should not sit on) one GPU.
+
+Two transports for the exchange:
+  * ``PeerGroup`` (the product path): mailboxes in peer HBM over NVLink; the scan
+    kernel itself pushes its list to every peer, waits for theirs and merges —
+    no collective call, no extra launch (csrc/peer.cuh).
+  * ``torch.distributed`` all-gather + merge kernel (works on any backend; what the
+    gloo CPU tests of the host logic use).
 
 torch is used for the plumbing only (device buffers, torch.distributed)."""
 from __future__ import annotations
@@ -36,15 +43,93 @@ def merge_topk_host(scores: np.ndarray, rows: np.ndarray, k: int):
     return s[order], r[order]
 
 
+class PeerGroup:
+    """cqs_b200_peer: this rank's mailbox + the mappings of every peer's (include/cqs_b200.h)."""
+
+    def __init__(self, device: int, world: int, rank: int, max_elems: int = 0):
+        self._h = C.c_void_p()
+        self.device, self.world, self.rank = int(device), int(world), int(rank)
+        check(lib.cqs_b200_peer_create(self.device, self.world, self.rank, int(max_elems), C.byref(self._h)))
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(lib.cqs_b200_peer_handle(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles) -> None:
+        """handles: the 64-byte handle of every rank, in rank order (other PROCESSES)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        check(lib.cqs_b200_peer_connect(self._h, (C.c_uint8 * len(blob)).from_buffer_copy(blob)))
+
+    @staticmethod
+    def connect_local(groups) -> None:
+        """All ranks live in THIS process (one group per device or per emulated shard)."""
+        arr = (C.c_void_p * len(groups))(*[g._h for g in groups])
+        check(lib.cqs_b200_peer_connect_local(arr, len(groups)))
+
+    @classmethod
+    def from_dist(cls, dist, device: int, max_elems: int = 0) -> "PeerGroup":
+        """One process per GPU under torch.distributed: create, swap handles, connect."""
+        g = cls(device, dist.get_world_size(), dist.get_rank(), max_elems)
+        if g.world > 1:
+            handles = [None] * g.world
+            dist.all_gather_object(handles, g.handle())
+            g.connect(handles)
+        return g
+
+    def set_timeout_ms(self, ms: int) -> None:
+        check(lib.cqs_b200_peer_set_timeout_ms(self._h, int(ms)))
+
+    def status(self) -> int:
+        rc = lib.cqs_b200_peer_status(self._h)
+        if rc < 0:
+            check(rc)
+        return rc
+
+    def close(self) -> None:
+        if self._h:
+            lib.cqs_b200_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def search_sharded(index, peer: PeerGroup, query: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
+    """VectorIndex::search over the whole sharded corpus (host in, GLOBAL host top-k out)."""
+    q = np.ascontiguousarray(query, np.float32)
+    rows = np.empty(k, np.uint64)
+    sc = np.empty(k, np.float32)
+    n = C.c_uint32(0)
+    check(lib.cqs_b200_search_sharded(index._h, peer._h, q.ctypes.data_as(C.c_void_p), k,
+                                      None if bitset is None else bitset.ctypes.data_as(C.c_void_p),
+                                      rows.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return rows[:n.value], sc[:n.value]
+
+
+def search_batch_sharded(index, peer: PeerGroup, queries: np.ndarray, k: int, bitset: Optional[np.ndarray] = None):
+    """cqs_b200_search_batch over the sharded corpus: (rows [nq][k], scores [nq][k], n [nq])."""
+    q = np.ascontiguousarray(queries, np.float32)
+    nq = q.shape[0]
+    rows = np.full((nq, k), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    sc = np.full((nq, k), -np.inf, np.float32)
+    n = np.zeros(nq, np.uint32)
+    check(lib.cqs_b200_search_batch_sharded(index._h, peer._h, q.ctypes.data_as(C.c_void_p), nq, k,
+                                            None if bitset is None else bitset.ctypes.data_as(C.c_void_p),
+                                            rows.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                            n.ctypes.data_as(C.c_void_p)))
+    return rows, sc, n
+
+
 class ShardedSearcher:
     """search_batch over a row-sharded corpus: local fused scan+top-k per query, then
     all_gather_into_tensor(scores) + all_gather_into_tensor(rows) and one merge kernel."""
 
-    def __init__(self, index, dist=None, device=None, max_queries: int = 64, k: int = 20):
+    def __init__(self, index, dist=None, device=None, max_queries: int = 64, k: int = 20,
+                 peer: Optional[PeerGroup] = None):
         import torch
         self.torch = torch
         self.index = index
         self.dist = dist
+        self.peer = peer
         self.world = dist.get_world_size() if dist is not None else 1
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.k = k
@@ -68,6 +153,15 @@ class ShardedSearcher:
         assert nq <= self.Q
         stream = C.c_void_p(t.cuda.current_stream().cuda_stream)
         dim = self.index.dim()
+        if self.peer is not None and self.world > 1:
+            # product path: every launch scans, exchanges over NVLink and merges
+            for i in range(nq):
+                check(lib.cqs_b200_search_sharded_device(
+                    self.index._h, self.peer._h, C.c_void_p(d_queries.data_ptr() + i * dim * 4), self.k, None,
+                    C.c_void_p(self.m_sc.data_ptr() + i * self.k * 4),
+                    C.c_void_p(self.m_rw.data_ptr() + i * self.k * 8),
+                    C.c_void_p(self.m_n.data_ptr() + i * 4), stream))
+            return self.m_sc[:nq], self.m_rw[:nq], self.m_n[:nq]
         for i in range(nq):
             check(lib.cqs_b200_search_device(
                 self.index._h, C.c_void_p(d_queries.data_ptr() + i * dim * 4), self.k, None,

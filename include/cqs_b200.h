@@ -207,6 +207,58 @@ int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t
                                float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
                                void* stream);
 
+/* ---- row-sharded corpora WITHOUT a collective call: NVLink peer memory --------
+ * (the reference has no multi-GPU path — src/index.rs:139-239 is one
+ * index per process.)  A peer group is one mailbox per rank in that rank's HBM,
+ * mapped into every other rank.  The scan kernel's last CTA stores the shard's
+ * sorted top-k straight into every peer's mailbox over NVLink, raises one
+ * release flag per peer, waits for the peers' lists and merges — all-gather and
+ * merge ride in the tail of the kernel that produced the list.  Every rank gets the
+ * GLOBAL top-k, identical to the unsharded result.
+ *
+ * Rules: every rank issues the same sequence of sharded searches on its group (the
+ * exchanges are numbered); a rank that does not show up within the timeout (default
+ * 5 s) makes the others return an error and marks the group failed (rebuild it).
+ *
+ * One process per GPU:   peer_create -> peer_handle -> exchange the 64-byte handles
+ *                        through any side channel (the tests use torch.distributed
+ *                        all_gather_object) -> peer_connect(all handles, rank order).
+ * One process, n GPUs:   peer_create x n -> peer_connect_local(array, n). */
+typedef struct cqs_b200_peer cqs_b200_peer; /* opaque */
+#define CQS_B200_PEER_HANDLE_BYTES 64u
+#define CQS_B200_PEER_MAX_WORLD 8u
+/* max_elems: capacity of one exchange in (query, slot) pairs, nq*k <= max_elems
+ * (0 = 65536: 1024 queries x top-64). */
+int cqs_b200_peer_create(int device, uint32_t world, uint32_t rank, uint32_t max_elems,
+                         cqs_b200_peer** out);
+int cqs_b200_peer_handle(cqs_b200_peer* p, uint8_t* out_handle /* [64] */);
+int cqs_b200_peer_connect(cqs_b200_peer* p, const uint8_t* handles /* [world][64], rank order */);
+int cqs_b200_peer_connect_local(cqs_b200_peer** peers, uint32_t world);
+int cqs_b200_peer_set_timeout_ms(cqs_b200_peer* p, uint32_t ms);
+/* 0 = healthy, 1 = an exchange timed out (sticky), < 0 = error.  Synchronises the device. */
+int cqs_b200_peer_status(cqs_b200_peer* p);
+void cqs_b200_peer_destroy(cqs_b200_peer* p);
+/* VectorIndex::search over the whole row-sharded corpus, host query in, GLOBAL host
+ * top-k out on every rank (ONE kernel launch per rank: scan + exchange + merge; the
+ * result lands in host-mapped memory).  `bitset` covers this rank's rows. */
+int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query, uint32_t k,
+                            const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                            uint32_t* out_n);
+/* Same with device buffers, asynchronous on `stream` (0 = the index's own stream). */
+int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_query,
+                                   uint32_t k, const uint32_t* d_bitset, float* d_out_scores,
+                                   uint64_t* d_out_rows, uint32_t* d_out_n, void* stream);
+/* cqs_b200_search_batch over the row-sharded corpus: per-shard tensor-core scan +
+ * exact rescoring, then ONE gather+merge kernel over peer memory per <= 1024 queries. */
+int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries,
+                                  uint32_t nq, uint32_t k, const uint32_t* bitset,
+                                  uint64_t* out_rows, float* out_scores, uint32_t* out_n);
+/* The exchange alone: this rank's nq sorted lists (device, [nq][k], GLOBAL rows) ->
+ * GLOBAL top-k of every query on every rank.  nq <= 1024, nq*k <= max_elems. */
+int cqs_b200_peer_gather_merge(cqs_b200_peer* p, const float* d_scores, const uint64_t* d_rows,
+                               const uint32_t* d_n, uint32_t nq, uint32_t k, float* d_out_scores,
+                               uint64_t* d_out_rows, uint32_t* d_out_n, void* stream);
+
 /* ---- introspection: VectorIndex::{len,dim,max_k,is_poisoned,name} ----------
  * (src/index.rs:149-217) */
 uint64_t cqs_b200_len(const cqs_b200_index* ix);

@@ -1,0 +1,280 @@
+"""Row-sharded search over NVLink peer memory (csrc/peer.cuh): the
+exchange + merge that rides in the kernels must give, on EVERY rank, exactly the
+unsharded answer (same rows, bit-identical scores, reference order
+(score desc, id asc) — candidate.rs:321-329).
+
+One GPU is enough for: the fused tail with world = 1, and the stand-alone
+gather+merge kernel with the ranks emulated on one device (separate streams).
+The fused scan with world > 1 needs the ranks on different GPUs (a scan CTA
+that waits for a peer holds its SM): those tests skip below 2 GPUs."""
+import ctypes as C
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import cqs_oracle as O
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_world1_fused_tail_equals_plain_search(storage):
+    import cqs_b200
+    from cqs_b200.sharded import PeerGroup, search_sharded
+    n, dim = 40_007, 768
+    rows = O.fast_unit_rows(n, dim, seed=11)
+    rows[3] = rows[n - 9]
+    ix = cqs_b200.B200Index(dim, storage=storage, row_base=1000)
+    ix.append(None, rows); ix.finalize()
+    pg = PeerGroup(0, 1, 0)
+    mask = np.random.default_rng(1).random(n) < 0.3
+    for qi in (3, 77, n - 1):
+        for k in (1, 20, 33, 500, 1024):
+            a, b = ix.search_rows(rows[qi], k)
+            c, d = search_sharded(ix, pg, rows[qi], k)
+            assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32))
+        a, b = ix.search_rows(rows[qi], 20, O.mask_to_bitset(mask))
+        c, d = search_sharded(ix, pg, rows[qi], 20, O.mask_to_bitset(mask))
+        assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32))
+    bad = rows[0].copy(); bad[5] = np.nan
+    c, d = search_sharded(ix, pg, bad, 20)
+    assert c.shape[0] == 0                                  # non-finite query -> empty (src/cagra.rs:458-470)
+    assert pg.status() == 0
+    pg.close(); ix.close()
+
+
+def _random_sorted_lists(rng, G, Q, k, tie_every=7):
+    """Per emulated rank: Q sorted lists of <= k (score, global row) pairs with cross-list score ties."""
+    sc = np.full((G, Q, k), -np.inf, f32)
+    rw = np.full((G, Q, k), EMPTY, np.uint64)
+    nn = np.zeros((G, Q), np.uint32)
+    pool = (rng.standard_normal(64) * 0.3).astype(f32)     # few distinct scores -> many exact ties
+    for g in range(G):
+        for q in range(Q):
+            n = int(rng.integers(0, k + 1)) if q % 5 else k
+            s = np.where(rng.random(n) < 1.0 / tie_every, rng.choice(pool, n), rng.standard_normal(n).astype(f32) * 0.3)
+            r = rng.choice(1_000_000, n, replace=False).astype(np.uint64) * np.uint64(G) + np.uint64(g)  # disjoint across ranks
+            order = np.lexsort((r, -s.astype(np.float64)))
+            sc[g, q, :n] = s[order].astype(f32)
+            rw[g, q, :n] = r[order]
+            nn[g, q] = n
+    return sc, rw, nn
+
+
+@pytest.mark.parametrize("G,Q,k", [(2, 8, 20), (4, 140, 20), (8, 64, 64), (3, 5, 1024), (2, 1024, 20)])
+def test_gather_merge_emulated_ranks_on_one_device(G, Q, k):
+    import torch
+    from cqs_b200.capi import lib, check
+    from cqs_b200.sharded import PeerGroup, merge_topk_host
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(G * 1000 + Q + k)
+    sc, rw, nn = _random_sorted_lists(rng, G, Q, k)
+    groups = [PeerGroup(0, G, g, max_elems=max(Q * k, 1024)) for g in range(G)]
+    PeerGroup.connect_local(groups)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(G)]
+    d_in = [(torch.from_numpy(sc[g]).to(dev), torch.from_numpy(rw[g].view(np.int64)).to(dev),
+             torch.from_numpy(nn[g].view(np.int32)).to(dev)) for g in range(G)]
+    d_out = [(torch.empty((Q, k), dtype=torch.float32, device=dev), torch.empty((Q, k), dtype=torch.int64, device=dev),
+              torch.empty((Q,), dtype=torch.int32, device=dev)) for g in range(G)]
+    torch.cuda.synchronize()
+    for rep in range(3):                                    # three exchanges: both mailbox slots get reused
+        for g in range(G):
+            check(lib.cqs_b200_peer_gather_merge(groups[g]._h, _vp(d_in[g][0]), _vp(d_in[g][1]), _vp(d_in[g][2]), Q, k,
+                                                 _vp(d_out[g][0]), _vp(d_out[g][1]), _vp(d_out[g][2]),
+                                                 C.c_void_p(streams[g].cuda_stream)))
+    torch.cuda.synchronize()
+    for g in range(G):
+        assert groups[g].status() == 0
+        o_s = d_out[g][0].cpu().numpy(); o_r = d_out[g][1].cpu().numpy().view(np.uint64); o_n = d_out[g][2].cpu().numpy()
+        for q in range(Q):
+            es, er = merge_topk_host(sc[:, q], rw[:, q], k)
+            assert int(o_n[q]) == er.shape[0]
+            assert o_r[q, :er.shape[0]].tolist() == er.tolist()
+            assert np.array_equal(o_s[q, :er.shape[0]].view(np.uint32), es.view(np.uint32))
+            assert (o_r[q, er.shape[0]:] == EMPTY).all()
+    for g in groups:
+        g.close()
+
+
+def test_missing_rank_times_out_instead_of_hanging():
+    import torch
+    from cqs_b200.capi import lib, check, B200Error
+    from cqs_b200.sharded import PeerGroup
+    dev = torch.device("cuda", 0)
+    groups = [PeerGroup(0, 2, g) for g in range(2)]
+    PeerGroup.connect_local(groups)
+    groups[0].set_timeout_ms(200)
+    Q, k = 4, 20
+    d_s = torch.zeros((Q, k), dtype=torch.float32, device=dev)
+    d_r = torch.arange(Q * k, dtype=torch.int64, device=dev).reshape(Q, k)
+    d_n = torch.full((Q,), k, dtype=torch.int32, device=dev)
+    o_s = torch.empty_like(d_s); o_r = torch.empty_like(d_r); o_n = torch.empty_like(d_n)
+    st = torch.cuda.Stream(device=dev)
+    check(lib.cqs_b200_peer_gather_merge(groups[0]._h, _vp(d_s), _vp(d_r), _vp(d_n), Q, k, _vp(o_s), _vp(o_r), _vp(o_n),
+                                         C.c_void_p(st.cuda_stream)))           # rank 1 never shows up
+    st.synchronize()
+    assert groups[0].status() == 1
+    assert o_n.cpu().tolist() == [0] * Q
+    with pytest.raises(B200Error):                           # the group is failed from now on
+        check(lib.cqs_b200_peer_gather_merge(groups[0]._h, _vp(d_s), _vp(d_r), _vp(d_n), Q, k, _vp(o_s), _vp(o_r),
+                                             _vp(o_n), C.c_void_p(st.cuda_stream)))
+    for g in groups:
+        g.close()
+
+
+def _need_gpus(n):
+    import torch
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
+    _need_gpus(2)
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    from cqs_b200.sharded import PeerGroup, shard_range, search_sharded, search_batch_sharded
+    G = min(torch.cuda.device_count(), 4)
+    n, dim, k, Q = 120_011, 768, 20, 12
+    rows = O.fast_unit_rows(n, dim, seed=31)
+    rows[17] = rows[n - 3]                                   # cross-shard exact tie
+    queries = O.fast_unit_rows(Q, dim, seed=32)
+    queries[0] = rows[17]
+    whole = cqs_b200.B200Index(dim, storage=storage, devices=[0])
+    whole.append(None, rows); whole.finalize()
+    shards, groups = [], []
+    for g in range(G):
+        row0, nl = shard_range(n, G, g)
+        ix = cqs_b200.B200Index(dim, storage=storage, devices=[g], row_base=row0)
+        ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        shards.append(ix)
+        groups.append(PeerGroup(g, G, g))
+    PeerGroup.connect_local(groups)
+    # (a) asynchronous device entry: one launch per (rank, query), nothing else
+    outs = []
+    for g in range(G):
+        dev = torch.device("cuda", g)
+        outs.append((torch.from_numpy(queries).to(dev), torch.empty((Q, k), dtype=torch.float32, device=dev),
+                     torch.empty((Q, k), dtype=torch.int64, device=dev), torch.empty((Q,), dtype=torch.int32, device=dev)))
+    for g in range(G):
+        torch.cuda.synchronize(g)
+    for qi in range(Q):
+        for g in range(G):
+            d_q, d_s, d_r, d_n = outs[g]
+            check(lib.cqs_b200_search_sharded_device(shards[g]._h, groups[g]._h, C.c_void_p(d_q.data_ptr() + qi * dim * 4), k, None,
+                                                     C.c_void_p(d_s[qi].data_ptr()), C.c_void_p(d_r[qi].data_ptr()),
+                                                     C.c_void_p(d_n[qi].data_ptr()), None))
+    for g in range(G):
+        torch.cuda.synchronize(g)
+    for qi in range(Q):
+        a, b = whole.search_rows(queries[qi], k)
+        for g in range(G):
+            _, d_s, d_r, d_n = outs[g]
+            assert int(d_n[qi]) == k
+            assert d_r[qi].cpu().numpy().view(np.uint64).tolist() == a.tolist()
+            assert np.array_equal(d_s[qi].cpu().numpy().view(np.uint32), b.view(np.uint32))
+    assert outs[0][2][0, :2].cpu().tolist() == [17, n - 3]
+    # (b) blocking host entry from one thread per rank (the daemon's client threads), k up to max_k
+    res = [None] * G
+
+    def run(g):
+        out = []
+        for qi in range(Q):
+            for kk in (1, 20, 500):
+                out.append(search_sharded(shards[g], groups[g], queries[qi], kk))
+        if storage == "bf16":
+            out.append(search_batch_sharded(shards[g], groups[g], queries, k))
+        res[g] = out
+
+    th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    i = 0
+    for qi in range(Q):
+        for kk in (1, 20, 500):
+            a, b = whole.search_rows(queries[qi], kk)
+            for g in range(G):
+                c, d = res[g][i]
+                assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32))
+            i += 1
+    if storage == "bf16":
+        for g in range(G):
+            r, s, nn = res[g][i]
+            for qi in range(Q):
+                a, b = whole.search_rows(queries[qi], k)
+                assert int(nn[qi]) == k and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32))
+    for g in range(G):
+        assert groups[g].status() == 0
+        groups[g].close(); shards[g].close()
+    whole.close()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _ipc_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    import cqs_b200
+    from cqs_b200.sharded import PeerGroup, shard_range, search_sharded, search_batch_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    n, dim, k, Q = 90_001, 768, 20, 40
+    rows = O.fast_unit_rows(n, dim, seed=51)
+    rows[5] = rows[n - 2]
+    queries = O.fast_unit_rows(Q, dim, seed=52)
+    queries[0] = rows[5]
+    ok = True
+    for storage in ("f32", "bf16"):
+        row0, nl = shard_range(n, world, rank)
+        ix = cqs_b200.B200Index(dim, storage=storage, devices=[rank], row_base=row0)
+        ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        whole = cqs_b200.B200Index(dim, storage=storage, devices=[rank])
+        whole.append(None, rows); whole.finalize()
+        pg = PeerGroup.from_dist(dist, rank)                 # CUDA IPC handles over all_gather_object
+        for qi in range(Q):
+            a, b = whole.search_rows(queries[qi], k)
+            c, d = search_sharded(ix, pg, queries[qi], k)
+            ok &= bool(np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32)))
+        r, s, nn = search_batch_sharded(ix, pg, queries, k)
+        for qi in range(Q):
+            a, b = whole.search_rows(queries[qi], k)
+            ok &= bool(int(nn[qi]) == k and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32)))
+        ok &= pg.status() == 0
+        dist.barrier()
+        pg.close(); ix.close(); whole.close()
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_two_processes_cuda_ipc_mailboxes():
+    _need_gpus(2)
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
