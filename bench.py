@@ -289,6 +289,10 @@ def main():
                          "over NVLink peer memory (product path), 'nccl' = all_gather_into_tensor + merge kernel")
     ap.add_argument("--hnsw-rows", type=int, default=100_000,
                     help="rows of the corpus the CPU HNSW baseline is built on (0 = skip)")
+    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
+                    help="device-resident timing: launches are issued alternately on this many streams, so the "
+                         "tail of one query's kernel (list merge, cross-shard exchange) overlaps the streaming "
+                         "phase of the next query's kernel; every query is still its own launch")
     ap.add_argument("--workload", default="single", choices=["single", "batch"],
                     help="single = BASELINE configs[1] (the headline, default); batch = configs[2]/[3]: "
                          "1024-query tensor-core batches (use --rows 10000000 --storage bf16 --queries-per-step 1024)")
@@ -341,6 +345,9 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
+    lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(P - 1)]
+    lane_ptr = [C.c_void_p(st.cuda_stream) for st in lanes]
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
     d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
@@ -366,14 +373,14 @@ def main():
                 check(lib.cqs_b200_search_sharded_device(ix._h, pg._h, C.c_void_p(qp), K, None,
                                                          C.c_void_p(m_sc.data_ptr() + i * K * 4),
                                                          C.c_void_p(m_rw.data_ptr() + i * K * 8),
-                                                         C.c_void_p(m_n.data_ptr() + i * 4), sp))
+                                                         C.c_void_p(m_n.data_ptr() + i * 4), lane_ptr[i % P]))
             return
         for i in range(Q):
             qp = d_queries.data_ptr() + (base + i) * DIM * 4
             check(lib.cqs_b200_search_device(ix._h, C.c_void_p(qp), K, None,
                                              C.c_void_p(d_sc.data_ptr() + i * K * 4),
                                              C.c_void_p(d_rw.data_ptr() + i * K * 8),
-                                             C.c_void_p(d_n.data_ptr() + i * 4), sp))
+                                             C.c_void_p(d_n.data_ptr() + i * 4), lane_ptr[i % P]))
         if world > 1:
             dist.all_gather_into_tensor(g_sc, d_sc)
             dist.all_gather_into_tensor(g_rw, d_rw)
@@ -396,8 +403,14 @@ def main():
     clk.__enter__()
     barrier()
     e0.record(stream)
+    for st in lanes[1:]:
+        st.wait_event(e0)                      # fork: the other lanes start after e0
     for s in range(args.steps):
         step_device(args.warmup + s)
+    for st in lanes[1:]:
+        ej = torch.cuda.Event()
+        ej.record(st)
+        stream.wait_event(ej)                  # join: e1 comes after the last launch of every lane
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -484,6 +497,7 @@ def main():
             "config": {"workload": f"exact top-{K}, single query at a time, {n_total}x{DIM} {args.storage} "
                                    f"(BASELINE configs[1]), row-sharded over {world} GPU(s)",
                        "queries_per_step": Q, "rows_per_gpu": n_local,
+                       "launch_lanes": P,
                        "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",
                        "collective": "none" if world == 1 else (
                            "none: every scan kernel stores its top-k into the peers' mailboxes over NVLink, "

@@ -53,13 +53,23 @@ struct Shard {
   uint64_t first_row = 0;  // offset of this shard's row 0 inside the index
   float* d_stage = nullptr;  // staging for row ingest
   uint64_t stage_rows = 0;
-  float* d_query = nullptr;   // [ld], zero padded beyond dim
   float* h_query = nullptr;   // pinned
   uint32_t* d_bitset = nullptr;
   uint64_t bitset_words = 0;
-  ckey_t* d_partial = nullptr;
-  uint32_t* d_partial_cnt = nullptr;
-  uint32_t* d_done = nullptr;
+  // Scratch of one dense scan launch: per-CTA partial lists, CTA ticket + tile counter, the
+  // zero-padded query.  TWO sets, used alternately, so that a caller that alternates between
+  // two streams gets the tail of launch i (list merge, cross-shard exchange) overlapped with
+  // the streaming phase of launch i+1; a launch only waits for the launch two back.
+  struct ScanScratch {
+    ckey_t* d_partial = nullptr;
+    uint32_t* d_partial_cnt = nullptr;
+    uint32_t* d_done = nullptr;
+    float* d_query = nullptr;      // [ld], zero padded beyond dim
+    cudaEvent_t ev = nullptr;      // recorded after the last launch that used this set
+    cudaStream_t stream = nullptr;
+    bool used = false;
+  } scr[2];
+  uint32_t next_scr = 0;
   // dense result / pool
   float* d_out_scores = nullptr;
   uint64_t* d_out_rows = nullptr;
@@ -87,12 +97,6 @@ struct Shard {
   uint8_t* d_hout = nullptr;    // device alias of h_out
   uint32_t seq = 0;             // completion sequence number of the latency path
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // The partial-list scratch, the tile counter and d_query are shared by every launch of this
-  // shard; launches may come on the shard's own stream or on a caller's stream
-  // (cqs_b200_search_device).  ev_last orders a launch after the previous one when the
-  // stream changes.
-  cudaEvent_t ev_last = nullptr;
-  cudaStream_t last_stream = nullptr;
   unsigned long long* d_trace = nullptr;  // development aid (CQS_B200_TRACE=1)
   // batched tensor-core path (bf16 storage), allocated on first use
   float* d_bq = nullptr;          // [kBatchMaxQ][ld] padded f32 queries
@@ -156,8 +160,11 @@ static size_t row_bytes(const cqs_b200_index* ix) {
 static void free_shard(Shard& s) {
   cudaSetDevice(s.device);
   if (s.stream) cudaStreamSynchronize(s.stream);
-  cudaFree(s.d_rows); cudaFree(s.d_rows16); cudaFree(s.d_stage); cudaFree(s.d_query); cudaFree(s.d_bitset);
-  cudaFree(s.d_partial); cudaFree(s.d_partial_cnt); cudaFree(s.d_done);
+  cudaFree(s.d_rows); cudaFree(s.d_rows16); cudaFree(s.d_stage); cudaFree(s.d_bitset);
+  for (auto& c : s.scr) {
+    cudaFree(c.d_partial); cudaFree(c.d_partial_cnt); cudaFree(c.d_done); cudaFree(c.d_query);
+    if (c.ev) cudaEventDestroy(c.ev);
+  }
   cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
   cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
   cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
@@ -173,7 +180,6 @@ static void free_shard(Shard& s) {
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
-  if (s.ev_last) cudaEventDestroy(s.ev_last);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Shard();
 }
@@ -183,13 +189,16 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaSetDevice(device));
   CK(ix, cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(ix, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  CK(ix, cudaMalloc((void**)&s.d_query, sizeof(float) * ix->layout.ld));
   CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld,
                        cudaHostAllocDefault));
-  CK(ix, cudaMalloc((void**)&s.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
-  CK(ix, cudaMalloc((void**)&s.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
-  CK(ix, cudaMalloc((void**)&s.d_done, 4 * sizeof(uint32_t)));
-  CK(ix, cudaMemset(s.d_done, 0, 4 * sizeof(uint32_t)));
+  for (auto& c : s.scr) {
+    CK(ix, cudaMalloc((void**)&c.d_query, sizeof(float) * ix->layout.ld));
+    CK(ix, cudaMalloc((void**)&c.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
+    CK(ix, cudaMalloc((void**)&c.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
+    CK(ix, cudaMalloc((void**)&c.d_done, 4 * sizeof(uint32_t)));
+    CK(ix, cudaMemset(c.d_done, 0, 4 * sizeof(uint32_t)));
+    CK(ix, cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+  }
   CK(ix, cudaMalloc((void**)&s.d_out_scores, sizeof(float) * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_out_rows, sizeof(uint64_t) * kMaxK));
   CK(ix, cudaMalloc((void**)&s.d_out_n, sizeof(uint32_t)));
@@ -213,8 +222,6 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaHostGetDevicePointer((void**)&s.d_hout, s.h_out, 0));
   CK(ix, cudaEventCreate(&s.ev0));
   CK(ix, cudaEventCreate(&s.ev1));
-  CK(ix, cudaEventCreateWithFlags(&s.ev_last, cudaEventDisableTiming));
-  s.last_stream = s.stream;
   if (getenv("CQS_B200_TRACE")) {
     CK(ix, cudaMalloc((void**)&s.d_trace, sizeof(unsigned long long) * kMaxGrid * 8));
     CK(ix, cudaMemset(s.d_trace, 0, sizeof(unsigned long long) * kMaxGrid * 8));
@@ -469,12 +476,31 @@ static uint32_t host_ordered(float f) {
 // shard's dense pool buffers.  Asynchronous on s.stream.
 // Make `st` wait for the last launch that used this shard's scratch on another stream.
 static int order_after_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
-  if (s.last_stream != st) CK(ix, cudaStreamWaitEvent(st, s.ev_last, 0));
+  for (auto& c : s.scr)
+    if (c.used && c.stream != st) CK(ix, cudaStreamWaitEvent(st, c.ev, 0));
   return 0;
 }
 static int mark_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
-  CK(ix, cudaEventRecord(s.ev_last, st));
-  s.last_stream = st;
+  for (auto& c : s.scr) {
+    CK(ix, cudaEventRecord(c.ev, st));
+    c.stream = st;
+    c.used = true;
+  }
+  return 0;
+}
+// Dense scans: take the next scratch set; `st` only has to wait for the launch that used
+// that set last (two launches back), so launches issued alternately on two streams overlap.
+static int acquire_scratch(cqs_b200_index* ix, Shard& s, cudaStream_t st, Shard::ScanScratch** out) {
+  Shard::ScanScratch& c = s.scr[s.next_scr];
+  s.next_scr ^= 1u;
+  if (c.used && c.stream != st) CK(ix, cudaStreamWaitEvent(st, c.ev, 0));
+  *out = &c;
+  return 0;
+}
+static int release_scratch(cqs_b200_index* ix, Shard::ScanScratch* c, cudaStream_t st) {
+  CK(ix, cudaEventRecord(c->ev, st));
+  c->stream = st;
+  c->used = true;
   return 0;
 }
 
@@ -487,10 +513,11 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
                         const uint32_t* bitset, const ScanSignals* sig = nullptr,
                         bool to_host = false, const PeerCtx* peer = nullptr) {
   CK(ix, cudaSetDevice(s.device));
-  if (int rc = order_after_last(ix, s, s.stream)) return rc;
+  Shard::ScanScratch* scr = nullptr;
+  if (int rc = acquire_scratch(ix, s, s.stream, &scr)) return rc;
   memset(s.h_query, 0, sizeof(float) * ix->layout.ld);
   memcpy(s.h_query, query, sizeof(float) * ix->dim);
-  CK(ix, cudaMemcpyAsync(s.d_query, s.h_query, sizeof(float) * ix->layout.ld,
+  CK(ix, cudaMemcpyAsync(scr->d_query, s.h_query, sizeof(float) * ix->layout.ld,
                          cudaMemcpyHostToDevice, s.stream));
   const uint32_t* d_bits = nullptr;
   if (bitset) {
@@ -500,9 +527,9 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
     d_bits = s.d_bitset;
   }
   ScanArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = s.d_query;
+  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = scr->d_query;
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
   a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
   if (to_host) {
     a.d_out_scores = (float*)(s.d_hout + kOffScores);
@@ -518,7 +545,7 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
   if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
   CK(ix, launch_scan_single(a, s.num_sms, s.stream));
   if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
-  return mark_last(ix, s, s.stream);
+  return release_scratch(ix, scr, s.stream);
 }
 
 // Poll the completion word the kernel writes into mapped host memory; fall back to the
@@ -727,21 +754,22 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   if (s.n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty index");
   CK(ix, cudaSetDevice(s.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-  if (int rc2 = order_after_last(ix, s, st)) return rc2;
+  Shard::ScanScratch* scr = nullptr;
+  if (int rc2 = acquire_scratch(ix, s, st, &scr)) return rc2;
   const float* qp = d_query;
   if (ix->layout.ld != ix->dim) {
     // the query must be zero padded to the row stride: stage it through d_query
-    CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
-    CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
-    qp = s.d_query;
+    CK(ix, cudaMemsetAsync(scr->d_query, 0, sizeof(float) * ix->layout.ld, st));
+    CK(ix, cudaMemcpyAsync(scr->d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+    qp = scr->d_query;
   }
   ScanArgs a;
   a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
   a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   CK(ix, launch_scan_single(a, s.num_sms, st));
-  return mark_last(ix, s, st);
+  return release_scratch(ix, scr, st);
 }
 
 int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t* d_rows,
@@ -786,24 +814,25 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   Shard& s = ix->shards[0];
   CK(ix, cudaSetDevice(s.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-  if (int rc2 = order_after_last(ix, s, st)) return rc2;
+  Shard::ScanScratch* scr = nullptr;
+  if (int rc2 = acquire_scratch(ix, s, st, &scr)) return rc2;
   const float* qp = d_query;
   if (ix->layout.ld != ix->dim) {
-    CK(ix, cudaMemsetAsync(s.d_query, 0, sizeof(float) * ix->layout.ld, st));
-    CK(ix, cudaMemcpyAsync(s.d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
-    qp = s.d_query;
+    CK(ix, cudaMemsetAsync(scr->d_query, 0, sizeof(float) * ix->layout.ld, st));
+    CK(ix, cudaMemcpyAsync(scr->d_query, d_query, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, st));
+    qp = scr->d_query;
   }
   PeerCtx pc;
-  CK(ix, peer_begin(peer, st, &pc));
+  CK(ix, peer_begin(peer, st, &pc, /*exclusive=*/false));
   ScanArgs a;
   a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
   a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = s.d_partial; a.d_partial_cnt = s.d_partial_cnt; a.d_done = s.d_done;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   a.peer = &pc;
   CK(ix, launch_scan_single(a, s.num_sms, st));
-  CK(ix, peer_mark(peer, st));
-  return mark_last(ix, s, st);
+  CK(ix, peer_mark(peer, st, /*exclusive=*/false));
+  return release_scratch(ix, scr, st);
 }
 
 int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query, uint32_t k,
@@ -823,9 +852,9 @@ int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float
   Shard& s = ix->shards[0];
   CK(ix, cudaSetDevice(s.device));
   PeerCtx pc;
-  CK(ix, peer_begin(peer, s.stream, &pc));
+  CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/false));
   if ((rc = launch_dense(ix, s, query, k, bitset, nullptr, /*to_host=*/true, &pc))) return rc;
-  CK(ix, peer_mark(peer, s.stream));
+  CK(ix, peer_mark(peer, s.stream, /*exclusive=*/false));
   if ((rc = wait_host_flag(ix, s))) return rc;
   uint32_t n = std::min(*(uint32_t*)(s.h_out + kOffN), k);
   if (n == 0) {
@@ -1009,11 +1038,11 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
     }
     // 3. push the lists to every peer, wait for theirs, merge (one kernel, no collective call)
     PeerCtx pc;
-    CK(ix, peer_begin(peer, s.stream, &pc));
+    CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/true));
     PeerGatherArgs ga{s.d_bout_scores, s.d_bout_rows, s.d_bout_n, m, k,
                       s.d_bm_scores, s.d_bm_rows, s.d_bm_n, peer->d_ticket};
     CK(ix, launch_peer_gather_merge(pc, ga, s.num_sms, s.stream));
-    CK(ix, peer_mark(peer, s.stream));
+    CK(ix, peer_mark(peer, s.stream, /*exclusive=*/true));
     std::vector<uint32_t> ns(m);
     uint32_t status = 0;
     CK(ix, cudaMemcpyAsync(osc, s.d_bm_scores, sizeof(float) * (size_t)m * k, cudaMemcpyDeviceToHost, s.stream));

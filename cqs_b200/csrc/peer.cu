@@ -69,12 +69,15 @@ cudaError_t launch_peer_gather_merge(const PeerCtx& c, const PeerGatherArgs& a, 
   return cudaGetLastError();
 }
 
-cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c) {
-  if (p->have_last && p->last_stream != st) {
-    cudaError_t e = cudaStreamWaitEvent(st, p->ev_last, 0);
-    if (e != cudaSuccess) return e;
+cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c, bool exclusive) {
+  if (++p->seq == 0) p->seq = 2;  // keep the parity sequence after a wrap
+  for (uint32_t i = 0; i < 2; ++i) {
+    if (!exclusive && i != (p->seq & 1u)) continue;
+    if (p->ev_used[i] && p->ev_stream[i] != st) {
+      cudaError_t e = cudaStreamWaitEvent(st, p->ev[i], 0);
+      if (e != cudaSuccess) return e;
+    }
   }
-  if (++p->seq == 0) p->seq = 1;
   c->world = p->world;
   c->rank = p->rank;
   c->seq = p->seq;
@@ -85,10 +88,15 @@ cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c) {
   for (uint32_t r = 0; r < kPeerMaxWorld; ++r) c->mbox[r] = p->mbox[r];
   return cudaSuccess;
 }
-cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st) {
-  p->last_stream = st;
-  p->have_last = true;
-  return cudaEventRecord(p->ev_last, st);
+cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st, bool exclusive) {
+  for (uint32_t i = 0; i < 2; ++i) {
+    if (!exclusive && i != (p->seq & 1u)) continue;
+    cudaError_t e = cudaEventRecord(p->ev[i], st);
+    if (e != cudaSuccess) return e;
+    p->ev_stream[i] = st;
+    p->ev_used[i] = true;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace cqs
@@ -144,7 +152,8 @@ int cqs_b200_peer_create(int device, uint32_t world, uint32_t rank, uint32_t max
   if (e == cudaSuccess) e = cudaMemset(p->d_status, 0, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_ticket, 2 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(p->d_ticket, 0, 2 * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -227,10 +236,10 @@ int cqs_b200_peer_gather_merge(cqs_b200_peer* p, const float* d_scores, const ui
   PCK(p, cudaSetDevice(p->device));
   cudaStream_t st = (cudaStream_t)stream;
   PeerCtx c;
-  PCK(p, peer_begin(p, st, &c));
+  PCK(p, peer_begin(p, st, &c, /*exclusive=*/true));
   PeerGatherArgs a{d_scores, d_rows, d_n, nq, k, d_out_scores, d_out_rows, d_out_n, p->d_ticket};
   PCK(p, launch_peer_gather_merge(c, a, p->num_sms, st));
-  PCK(p, peer_mark(p, st));
+  PCK(p, peer_mark(p, st, /*exclusive=*/true));
   return CQS_B200_OK;
 }
 
@@ -261,7 +270,8 @@ void cqs_b200_peer_destroy(cqs_b200_peer* p) {
   cudaFree(p->d_mbox);
   cudaFree(p->d_status);
   cudaFree(p->d_ticket);
-  if (p->ev_last) cudaEventDestroy(p->ev_last);
+  for (int i = 0; i < 2; ++i)
+    if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   cudaGetLastError();
   delete p;
 }

@@ -13,9 +13,11 @@
 //   [slot 0..kPeerSlots)[source rank 0..world)  block
 //   block = | flag u32, pad to 128 B | n[maxq] u32 | rows[cap] u64 | scores[cap] f32 |
 // Exchange number `seq` (same on every rank, 1, 2, 3, ...) uses slot seq % kPeerSlots
-// and writes `seq` into the flag.  Two slots suffice: a rank can start exchange
-// seq+1 only after it has RECEIVED every peer's lists of exchange seq, and a
-// peer sends those only after it finished reading its own slot of seq-1.
+// and writes `seq` into the flag.  A rank orders exchange seq after its own exchange
+// seq-2 (two may be in flight: the tail of one scan overlaps the next scan), and it
+// can only FINISH exchange seq-2 after every peer has pushed seq-2, which a peer does
+// after finishing (reading) its seq-4.  So when a push of `seq` lands in a peer's slot,
+// that peer is done with seq-4, the previous user of the slot: four slots suffice.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,7 +27,7 @@
 namespace cqs {
 
 constexpr uint32_t kPeerMaxWorld = 8;
-constexpr uint32_t kPeerSlots = 2;
+constexpr uint32_t kPeerSlots = 4;
 constexpr uint32_t kPeerMaxQ = 1024;   // queries per exchange
 constexpr uint32_t kPeerFlagBytes = 128;
 
@@ -102,11 +104,6 @@ __device__ __forceinline__ bool peer_wait(const PeerCtx& c, const Group& g) {
     if (late) atomicExch(c.status, 1u);
   }
   return !g.any(late);
-}
-
-// (s2, r2) ranks ahead of (s, r) in the result order
-__device__ __forceinline__ bool peer_before(uint32_t s2, uint64_t r2, uint32_t s, uint64_t r) {
-  return s2 > s || (s2 == s && r2 < r);
 }
 
 // Collective over g.  Merge the `world` sorted lists of query qi (k slots each, n valid)

@@ -24,17 +24,19 @@ struct cqs_b200_peer {
   uint32_t* d_ticket = nullptr;     // [2] CTA tickets of the stand-alone kernel
   uint32_t seq = 0;                 // exchanges issued so far (identical on every rank)
   uint64_t timeout_ns = 5ull * 1000 * 1000 * 1000;
-  // exchanges must execute on the device in issue order (the mailbox slots are reused):
-  // a launch on a different stream waits for the previous one
-  cudaEvent_t ev_last = nullptr;
-  cudaStream_t last_stream = nullptr;
-  bool have_last = false;
+  // Mailbox slots are reused every kPeerSlots exchanges and a fused scan may overlap the one
+  // before it (the caller alternates two streams): exchange seq waits for exchange seq-2
+  // (events by parity).  The stand-alone kernel shares d_ticket, so it is `exclusive`:
+  // ordered after every earlier exchange, and every later one after it.
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t ev_stream[2] = {nullptr, nullptr};
+  bool ev_used[2] = {false, false};
   std::atomic<int> failed{0};
 };
 
 namespace cqs {
 // Next exchange of the group: fills `c` and orders stream `st` after the previous exchange.
 // Call with p->mu held; follow the launch with peer_mark(p, st).
-cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c);
-cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st);
+cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c, bool exclusive);
+cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st, bool exclusive);
 }  // namespace cqs

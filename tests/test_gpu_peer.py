@@ -168,12 +168,14 @@ def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
                      torch.empty((Q, k), dtype=torch.int64, device=dev), torch.empty((Q,), dtype=torch.int32, device=dev)))
     for g in range(G):
         torch.cuda.synchronize(g)
+    # two launch lanes per rank: the exchange of query i overlaps the scan of query i+1
+    lanes = [[torch.cuda.Stream(device=torch.device("cuda", g)) for _ in range(2)] for g in range(G)]
     for qi in range(Q):
         for g in range(G):
             d_q, d_s, d_r, d_n = outs[g]
             check(lib.cqs_b200_search_sharded_device(shards[g]._h, groups[g]._h, C.c_void_p(d_q.data_ptr() + qi * dim * 4), k, None,
                                                      C.c_void_p(d_s[qi].data_ptr()), C.c_void_p(d_r[qi].data_ptr()),
-                                                     C.c_void_p(d_n[qi].data_ptr()), None))
+                                                     C.c_void_p(d_n[qi].data_ptr()), C.c_void_p(lanes[g][qi % 2].cuda_stream)))
     for g in range(G):
         torch.cuda.synchronize(g)
     for qi in range(Q):

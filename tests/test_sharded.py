@@ -191,3 +191,38 @@ def test_search_device_and_host_search_interleave_safely():
         assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
         assert np.array_equal(host[15 - i][0], a)
     ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [20, 500])
+def test_search_device_on_two_alternating_streams(k):
+    """Launches issued alternately on two streams use the two scratch sets of the index: the tail
+    of one launch may overlap the next launch's streaming phase, results must not change."""
+    import ctypes as C
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    n, dim, Q = 300_000, 768, 48
+    rows = O.fast_unit_rows(n, dim, seed=95)
+    ix = cqs_b200.B200Index(dim)
+    ix.append(None, rows); ix.finalize()
+    dev = torch.device("cuda", 0)
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    qs = O.fast_unit_rows(Q, dim, seed=96)
+    d_q = torch.from_numpy(qs).to(dev)
+    d_sc = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    d_rw = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for i in range(Q):
+            lane = lanes[i % 2] if rep == 0 else lanes[(i // 3) % 2]      # in and out of phase with the scratch sets
+            check(lib.cqs_b200_search_device(ix._h, C.c_void_p(d_q.data_ptr() + i * dim * 4), k, None,
+                                             C.c_void_p(d_sc[i].data_ptr()), C.c_void_p(d_rw[i].data_ptr()),
+                                             C.c_void_p(d_n[i].data_ptr()), C.c_void_p(lane.cuda_stream)))
+        torch.cuda.synchronize()
+        for i in range(Q):
+            a, b = ix.search_rows(qs[i], k)
+            assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
+            assert np.array_equal(d_sc[i].cpu().numpy().view(np.uint32), b.view(np.uint32))
+    ix.close()
