@@ -101,6 +101,17 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# stdout carries exactly ONE line, the JSON result: file descriptor 1 is pointed at stderr for
+# the whole run (NCCL prints its version banner on stdout, torchrun its OMP notice), and the
+# result is written to the saved descriptor at the end.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
+
 def make_queries(nq: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     q = rng.uniform(-1, 1, size=(nq, DIM)).astype(np.float32)
@@ -149,7 +160,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = qper * args.steps / dt
     sample = f"{qper} queries/step x {args.steps} steps over the full {N_ROWS}x{DIM} f32 corpus in RAM (no SQLite)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -158,7 +169,7 @@ def run_reference(args):
                    "queries_per_step": qper},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def run_batch(args):
@@ -242,7 +253,7 @@ def run_batch(args):
             pass
         flop = 2.0 * nq * n_local * DIM                      # per batch pipeline, per GPU
         tf = flop / (dev_ms / args.steps / 1e3) / 1e12
-        print(json.dumps({
+        emit({
             "metric": f"queries_per_s_exact_top20_{n_total}x{DIM}_{args.storage}_batch{nq}",
             "value": nq * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -262,7 +273,7 @@ def run_batch(args):
                          "traffic": None, "peak_source": src, "kernel": "scan_batch_kernel (+ threshold updates, rescore)",
                          "algorithmic_flop_per_launch": flop},
             "batch_equals_single_query_path": None if agree is None else f"{agree}/4",
-        }))
+        })
     if pg is not None:
         st = pg.status()
         dist.barrier()
@@ -565,7 +576,7 @@ def main():
                     "sample": f"graph over the first {hn} rows of the corpus (bounded build time), {nqh} queries, "
                               "approximate: speed baseline only"}
                 hn_index.close()
-        print(json.dumps(line))
+        emit(line)
     if pg is not None:
         if pg.status() != 0:
             raise RuntimeError("peer exchange timed out during the run")
