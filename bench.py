@@ -112,6 +112,14 @@ def emit(line: dict) -> None:
     os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
+def ncu_traffic(key: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def make_queries(nq: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     q = rng.uniform(-1, 1, size=(nq, DIM)).astype(np.float32)
@@ -270,7 +278,9 @@ def run_batch(args):
                     "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 12 + nq * 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": None, "peak_source": src, "kernel": "scan_batch_kernel (+ threshold updates, rescore)",
+                         "traffic": ncu_traffic(f"scan_batch_kernel:{n_local}x{DIM}:{args.storage}:{nq}q"),
+                         "peak_source": src, "kernel": "scan_batch_kernel (+ threshold updates, rescore)",
+                         "frac_of_burst_peak": tf / 1668.9,
                          "algorithmic_flop_per_launch": flop},
             "batch_equals_single_query_path": None if agree is None else f"{agree}/4",
         })
@@ -521,9 +531,14 @@ def main():
             "p50_ms_e2e": float(np.median(lat) * 1e3) if lat else None,
             "p95_ms_e2e": float(np.percentile(lat, 95) * 1e3) if lat else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic(f"scan_topk_kernel:{n_local}x{DIM}:{args.storage}"),
+                         "peak_source": peak_src,
                          "kernel": "scan_topk_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "avg_launch_us": avg_launch_s * 1e6},
+                         "avg_launch_us": avg_launch_s * 1e6,
+                         "avg_launch_is": "timed region / launches = launch interval (CUDA events on the launching "
+                                          "stream); with 2 launch lanes the tail of a launch overlaps the next one",
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
         }
         if world == 1 and not args.no_cpu_baseline and keep_host:
             from oracle import c_oracle as CO
