@@ -367,8 +367,6 @@ def main():
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
-    lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(P - 1)]
-    lane_ptr = [C.c_void_p(st.cuda_stream) for st in lanes]
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
     d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
@@ -384,24 +382,31 @@ def main():
         m_n = torch.empty((Q,), dtype=torch.int32, device=dev)
 
     def step_device(s: int):
-        """Q single-query scans, one kernel each.  N>1: the kernel also pushes its top-k to every
-        peer over NVLink, waits for theirs and merges (transport 'peer'); or one all-gather +
-        merge kernel per step (transport 'nccl')."""
+        """Q single-query scans, one kernel launch each, everything resident on the device.
+        P == 2: ONE library call per step (cqs_b200_search_many_device) issues the Q launches
+        alternately on two lanes; N>1: every launch also pushes its top-k to the peers over
+        NVLink, waits for theirs and merges in its tail (transport 'peer').  P == 1: a call per
+        query on one stream; transport 'nccl': + one all-gather + merge kernel per step."""
         base = s * Q
+        q0 = d_queries.data_ptr() + base * DIM * 4
+        if P == 2:
+            o_sc, o_rw, o_n = (m_sc, m_rw, m_n) if world > 1 else (d_sc, d_rw, d_n)
+            check(lib.cqs_b200_search_many_device(ix._h, pg._h if pg is not None else None, C.c_void_p(q0), Q, K, None,
+                                                  C.c_void_p(o_sc.data_ptr()), C.c_void_p(o_rw.data_ptr()),
+                                                  C.c_void_p(o_n.data_ptr()), sp))
+            return
         if pg is not None:
             for i in range(Q):
-                qp = d_queries.data_ptr() + (base + i) * DIM * 4
-                check(lib.cqs_b200_search_sharded_device(ix._h, pg._h, C.c_void_p(qp), K, None,
+                check(lib.cqs_b200_search_sharded_device(ix._h, pg._h, C.c_void_p(q0 + i * DIM * 4), K, None,
                                                          C.c_void_p(m_sc.data_ptr() + i * K * 4),
                                                          C.c_void_p(m_rw.data_ptr() + i * K * 8),
-                                                         C.c_void_p(m_n.data_ptr() + i * 4), lane_ptr[i % P]))
+                                                         C.c_void_p(m_n.data_ptr() + i * 4), sp))
             return
         for i in range(Q):
-            qp = d_queries.data_ptr() + (base + i) * DIM * 4
-            check(lib.cqs_b200_search_device(ix._h, C.c_void_p(qp), K, None,
+            check(lib.cqs_b200_search_device(ix._h, C.c_void_p(q0 + i * DIM * 4), K, None,
                                              C.c_void_p(d_sc.data_ptr() + i * K * 4),
                                              C.c_void_p(d_rw.data_ptr() + i * K * 8),
-                                             C.c_void_p(d_n.data_ptr() + i * 4), lane_ptr[i % P]))
+                                             C.c_void_p(d_n.data_ptr() + i * 4), sp))
         if world > 1:
             dist.all_gather_into_tensor(g_sc, d_sc)
             dist.all_gather_into_tensor(g_rw, d_rw)
@@ -424,14 +429,8 @@ def main():
     clk.__enter__()
     barrier()
     e0.record(stream)
-    for st in lanes[1:]:
-        st.wait_event(e0)                      # fork: the other lanes start after e0
     for s in range(args.steps):
-        step_device(args.warmup + s)
-    for st in lanes[1:]:
-        ej = torch.cuda.Event()
-        ej.record(st)
-        stream.wait_event(ej)                  # join: e1 comes after the last launch of every lane
+        step_device(args.warmup + s)           # the library joins its second lane back into `stream`
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -457,31 +456,42 @@ def main():
     search = lib.cqs_b200_search
 
     search_sh = lib.cqs_b200_search_sharded
+    b_rows = np.empty((Q, K), np.uint64)
+    b_sc = np.empty((Q, K), np.float32)
+    b_n = np.zeros(Q, np.uint32)
+    pb_rows, pb_sc, pb_n = (b_rows.ctypes.data_as(C.c_void_p), b_sc.ctypes.data_as(C.c_void_p),
+                            b_n.ctypes.data_as(C.c_void_p))
 
     def step_e2e(s: int):
+        """One public batch call per step: Q host queries in, Q host top-k lists out (H2D of the
+        queries, Q scan launches, D2H of the results, all inside the call)."""
         base = s * Q
-        if pg is not None:
-            # sharded, product path: host query in, GLOBAL host top-k out, one launch per rank
-            for i in range(Q):
-                t0 = time.perf_counter()
-                rc = search_sh(ix._h, pg._h, C.c_void_p(q_base + (base + i) * DIM * 4), K, None, p_rows, p_sc, p_n)
-                lat.append(time.perf_counter() - t0)
-                if rc:
-                    check(rc)
-        elif world == 1:
-            for i in range(Q):
-                t0 = time.perf_counter()
-                rc = search(ix._h, C.c_void_p(q_base + (base + i) * DIM * 4), K, None, p_rows, p_sc, p_n)
-                lat.append(time.perf_counter() - t0)
-                if rc:
-                    check(rc)
-        else:
-            # sharded: host queries -> H2D (pinned) -> scans -> all-gather -> merge -> D2H
+        qp = C.c_void_p(q_base + base * DIM * 4)
+        if world > 1 and pg is None:
+            # transport 'nccl': host queries -> H2D (pinned) -> scans -> all-gather -> merge -> D2H
             d_queries[base:base + Q].copy_(h_q[base:base + Q], non_blocking=True)
             step_device(s)
             h_pin.copy_(m_sc, non_blocking=True)
             h_pin_r.copy_(m_rw, non_blocking=True)
             torch.cuda.synchronize()
+        elif pg is not None:
+            check(lib.cqs_b200_search_batch_sharded(ix._h, pg._h, qp, Q, K, None, pb_rows, pb_sc, pb_n))
+        else:
+            check(lib.cqs_b200_search_batch(ix._h, qp, Q, K, None, pb_rows, pb_sc, pb_n))
+
+    def latency_pass(nq: int):
+        """Per-query latency of the blocking single-query call (VectorIndex::search shape):
+        host query in, host top-k out, one launch, result polled from host-mapped memory."""
+        for i in range(nq):
+            qp = C.c_void_p(q_base + i * DIM * 4)
+            t0 = time.perf_counter()
+            if pg is not None:
+                rc = search_sh(ix._h, pg._h, qp, K, None, p_rows, p_sc, p_n)
+            else:
+                rc = search(ix._h, qp, K, None, p_rows, p_sc, p_n)
+            lat.append(time.perf_counter() - t0)
+            if rc:
+                check(rc)
 
     for s in range(args.warmup):
         step_e2e(s)
@@ -493,6 +503,10 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clk.__exit__()
+    if world == 1 or pg is not None:
+        latency_pass(16)
+        lat.clear()
+        latency_pass(min(nq_total, 128))
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -528,8 +542,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
                     "d2h_bytes_per_step": Q * K * 12 + (Q * 4 if (world == 1 or pg is not None) else 0)},
             "gpu_launches": int(launches),
-            "p50_ms_e2e": float(np.median(lat) * 1e3) if lat else None,
-            "p95_ms_e2e": float(np.percentile(lat, 95) * 1e3) if lat else None,
+            "e2e_call": ("cqs_b200_search_batch" if world == 1 else "cqs_b200_search_batch_sharded" if pg is not None
+                         else "search_device + all_gather + merge") + f", one call per step of {Q} queries",
+            "p50_ms_single_query_call": float(np.median(lat) * 1e3) if lat else None,
+            "p95_ms_single_query_call": float(np.percentile(lat, 95) * 1e3) if lat else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": ncu_traffic(f"scan_topk_kernel:{n_local}x{DIM}:{args.storage}"),

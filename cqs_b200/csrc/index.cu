@@ -70,6 +70,9 @@ struct Shard {
     bool used = false;
   } scr[2];
   uint32_t next_scr = 0;
+  // second launch lane of the many-query entry points (lane 0 is the caller's stream)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // dense result / pool
   float* d_out_scores = nullptr;
   uint64_t* d_out_rows = nullptr;
@@ -180,6 +183,9 @@ static void free_shard(Shard& s) {
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+  if (s.ev_join) cudaEventDestroy(s.ev_join);
+  if (s.stream2) cudaStreamDestroy(s.stream2);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Shard();
 }
@@ -189,6 +195,9 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaSetDevice(device));
   CK(ix, cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(ix, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  CK(ix, cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+  CK(ix, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+  CK(ix, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
   CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld,
                        cudaHostAllocDefault));
   for (auto& c : s.scr) {
@@ -835,6 +844,133 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   return release_scratch(ix, scr, st);
 }
 
+// nq single-query scans, one launch each, issued alternately on two lanes (`st` and the
+// shard's second stream) so the tail of launch i — list merge and, with `peer`, the
+// cross-shard exchange — overlaps the streaming phase of launch i+1.  Everything stays on
+// the device; `st` is joined with the second lane before returning.  d_queries: f32
+// [nq][q_stride]; `skip` (nullable): queries that are not launched (non-finite).  Caller
+// holds ix->mu (and peer->mu).
+static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, const float* d_queries,
+                             uint32_t q_stride, uint32_t nq, uint32_t k, const uint32_t* d_bitset,
+                             float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
+                             const uint8_t* skip, cudaStream_t st) {
+  const bool staged = q_stride < ix->layout.ld;  // query must be zero padded to the row stride
+  cudaStream_t lanes[2] = {st, s.stream2};
+  bool forked = false;
+  uint32_t li = 0;
+  for (uint32_t i = 0; i < nq; ++i) {
+    if (skip && skip[i]) continue;
+    cudaStream_t ln = lanes[li & 1u];
+    if ((li & 1u) && !forked) {
+      CK(ix, cudaEventRecord(s.ev_fork, st));
+      CK(ix, cudaStreamWaitEvent(s.stream2, s.ev_fork, 0));
+      forked = true;
+    }
+    ++li;
+    Shard::ScanScratch* scr = nullptr;
+    if (int rc = acquire_scratch(ix, s, ln, &scr)) return rc;
+    const float* qp = d_queries + (size_t)i * q_stride;
+    if (staged) {
+      CK(ix, cudaMemsetAsync(scr->d_query, 0, sizeof(float) * ix->layout.ld, ln));
+      CK(ix, cudaMemcpyAsync(scr->d_query, qp, sizeof(float) * ix->dim, cudaMemcpyDeviceToDevice, ln));
+      qp = scr->d_query;
+    }
+    PeerCtx pc;
+    if (peer) CK(ix, peer_begin(peer, ln, &pc, /*exclusive=*/false));
+    ScanArgs a;
+    a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
+    a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
+    a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
+    a.d_out_scores = d_out_scores + (size_t)i * k;
+    a.d_out_rows = d_out_rows + (size_t)i * k;
+    a.d_out_n = d_out_n + i;
+    a.peer = peer ? &pc : nullptr;
+    CK(ix, launch_scan_single(a, s.num_sms, ln));
+    if (peer) CK(ix, peer_mark(peer, ln, /*exclusive=*/false));
+    if (int rc = release_scratch(ix, scr, ln)) return rc;
+  }
+  if (forked) {
+    CK(ix, cudaEventRecord(s.ev_join, s.stream2));
+    CK(ix, cudaStreamWaitEvent(st, s.ev_join, 0));
+  }
+  return 0;
+}
+
+int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_queries,
+                                uint32_t nq, uint32_t k, const uint32_t* d_bitset,
+                                float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
+                                void* stream) {
+  int rc = check_searchable(ix);
+  if (rc) return rc;
+  if (nq == 0) return CQS_B200_OK;
+  if (!d_queries || !d_out_scores || !d_out_rows || !d_out_n)
+    return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  if (k == 0 || k > kMaxK) return fail(CQS_B200_ERR_INVALID, "k=%u out of range 1..%u", k, kMaxK);
+  if (ix->shards.size() != 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "search_many_device needs a single-device index");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (peer && (rc = check_peer(ix, peer))) return rc;
+  std::unique_lock<std::mutex> gp;
+  if (peer) gp = std::unique_lock<std::mutex>(peer->mu);
+  Shard& s = ix->shards[0];
+  if (s.n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty index");
+  CK(ix, cudaSetDevice(s.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+  return launch_scan_lanes(ix, s, peer, d_queries, ix->dim, nq, k, d_bitset, d_out_scores, d_out_rows,
+                           d_out_n, nullptr, st);
+}
+
+// Exact (CUDA-core) batch: host queries in, host results out, one H2D, nq pipelined launches,
+// one D2H.  Used by cqs_b200_search_batch on f32 storage / small batches and by its sharded
+// twin; results are those of nq cqs_b200_search calls.  <= kBatchMaxQ queries per call.
+static int search_batch_exact(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries, uint32_t nq,
+                              uint32_t k, const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
+                              uint32_t* out_n) {
+  std::lock_guard<std::mutex> g(ix->mu);
+  std::unique_lock<std::mutex> gp;
+  if (peer) gp = std::unique_lock<std::mutex>(peer->mu);
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  const uint32_t ld = ix->layout.ld;
+  if (!s.d_bq) CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
+  if (!s.d_bout_scores) {
+    CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
+  }
+  std::vector<float> padded((size_t)nq * ld, 0.f);
+  std::vector<uint8_t> bad(nq, 0);
+  for (uint32_t i = 0; i < nq; ++i) {
+    const float* q = queries + (size_t)i * ix->dim;
+    if (query_is_finite(q, ix->dim)) memcpy(&padded[(size_t)i * ld], q, sizeof(float) * ix->dim);
+    else bad[i] = 1;  // empty result (src/cagra.rs:458-470); not launched — on every rank alike
+  }
+  if (int rc = order_after_last(ix, s, s.stream)) return rc;
+  CK(ix, cudaMemcpyAsync(s.d_bq, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, s.stream));
+  const uint32_t* d_bits = nullptr;
+  if (bitset) {
+    CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
+    d_bits = s.d_bitset;
+  }
+  CK(ix, cudaMemsetAsync(s.d_bout_n, 0, sizeof(uint32_t) * nq, s.stream));
+  if (int rc = launch_scan_lanes(ix, s, peer, s.d_bq, ld, nq, k, d_bits, s.d_bout_scores, s.d_bout_rows,
+                                 s.d_bout_n, bad.data(), s.stream))
+    return rc;
+  std::vector<uint32_t> ns(nq);
+  uint32_t status = 0;
+  CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(out_rows, s.d_bout_rows, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaMemcpyAsync(ns.data(), s.d_bout_n, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
+  if (peer) CK(ix, cudaMemcpyAsync(&status, peer->d_status, sizeof status, cudaMemcpyDeviceToHost, s.stream));
+  CK(ix, cudaStreamSynchronize(s.stream));
+  if (status) {
+    peer->failed.store(1);
+    return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
+  }
+  for (uint32_t i = 0; i < nq; ++i) out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
+  return CQS_B200_OK;
+}
+
 int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query, uint32_t k,
                             const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
                             uint32_t* out_n) {
@@ -951,6 +1087,16 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
   const bool tensor_path = ix->storage != CQS_B200_STORAGE_F32 && ix->shards.size() == 1 &&
                            nq >= 8 && ix->n_rows < (1ull << 31);
   if (!tensor_path) {
+    if (ix->shards.size() == 1 && nq > 1) {
+      // exact scans, pipelined: one H2D, nq launches on two lanes, one D2H
+      for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
+        const uint32_t m = std::min(kBatchMaxQ, nq - q0);
+        rc = search_batch_exact(ix, nullptr, queries + (size_t)q0 * ix->dim, m, k, bitset,
+                                out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_n + q0);
+        if (rc) return rc;
+      }
+      return CQS_B200_OK;
+    }
     for (uint32_t i = 0; i < nq; ++i) {
       rc = cqs_b200_search(ix, queries + (size_t)i * ix->dim, k, bitset, out_rows + (size_t)i * k,
                            out_scores + (size_t)i * k, out_n + i);
@@ -993,10 +1139,11 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
   const bool tensor_path = ix->storage != CQS_B200_STORAGE_F32 && nq >= 8 && ix->n_rows < (1ull << 31);
   if (!tensor_path) {
     // every rank takes this branch together (same nq, same storage): one fused
-    // scan + exchange per query
-    for (uint32_t i = 0; i < nq; ++i) {
-      rc = cqs_b200_search_sharded(ix, peer, queries + (size_t)i * ix->dim, k, bitset,
-                                   out_rows + (size_t)i * k, out_scores + (size_t)i * k, out_n + i);
+    // scan + exchange per query, pipelined on two lanes
+    for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
+      const uint32_t m = std::min(kBatchMaxQ, nq - q0);
+      rc = search_batch_exact(ix, peer, queries + (size_t)q0 * ix->dim, m, k, bitset,
+                              out_rows + (size_t)q0 * k, out_scores + (size_t)q0 * k, out_n + q0);
       if (rc) return rc;
     }
     return CQS_B200_OK;

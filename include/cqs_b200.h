@@ -248,6 +248,16 @@ int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float
 int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_query,
                                    uint32_t k, const uint32_t* d_bitset, float* d_out_scores,
                                    uint64_t* d_out_rows, uint32_t* d_out_n, void* stream);
+/* nq exact single-query scans with everything on the device: one launch per query,
+ * issued alternately on two launch lanes (`stream` and an internal one) so the tail of
+ * one launch (list merge, cross-shard exchange) overlaps the streaming phase of the
+ * next; `stream` is joined with the internal lane before the call returns
+ * (asynchronous).  d_queries f32 [nq][dim]; outputs [nq][k] / [nq].  peer == NULL: this
+ * index alone; otherwise the GLOBAL top-k over the sharded corpus on every rank. */
+int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_queries,
+                                uint32_t nq, uint32_t k, const uint32_t* d_bitset,
+                                float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
+                                void* stream);
 /* cqs_b200_search_batch over the row-sharded corpus: per-shard tensor-core scan +
  * exact rescoring, then ONE gather+merge kernel over peer memory per <= 1024 queries. */
 int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries,

@@ -194,8 +194,7 @@ def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
         for qi in range(Q):
             for kk in (1, 20, 500):
                 out.append(search_sharded(shards[g], groups[g], queries[qi], kk))
-        if storage == "bf16":
-            out.append(search_batch_sharded(shards[g], groups[g], queries, k))
+        out.append(search_batch_sharded(shards[g], groups[g], queries, k))   # bf16: tensor cores; f32: pipelined exact scans
         res[g] = out
 
     th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
@@ -212,12 +211,11 @@ def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
                 c, d = res[g][i]
                 assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32))
             i += 1
-    if storage == "bf16":
-        for g in range(G):
-            r, s, nn = res[g][i]
-            for qi in range(Q):
-                a, b = whole.search_rows(queries[qi], k)
-                assert int(nn[qi]) == k and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32))
+    for g in range(G):
+        r, s, nn = res[g][i]
+        for qi in range(Q):
+            a, b = whole.search_rows(queries[qi], k)
+            assert int(nn[qi]) == k and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32))
     for g in range(G):
         assert groups[g].status() == 0
         groups[g].close(); shards[g].close()

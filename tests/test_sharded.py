@@ -226,3 +226,51 @@ def test_search_device_on_two_alternating_streams(k):
             assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
             assert np.array_equal(d_sc[i].cpu().numpy().view(np.uint32), b.view(np.uint32))
     ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,storage", [(768, "f32"), (100, "f32"), (768, "bf16")])
+def test_exact_batch_is_pipelined_single_queries(dim, storage):
+    """cqs_b200_search_batch on f32 storage (and small bf16 batches) = nq exact scans issued on two
+    launch lanes with one H2D / one D2H; cqs_b200_search_many_device is the device-resident form.
+    Both must equal nq cqs_b200_search calls, including bitset, padded dims and non-finite queries."""
+    import ctypes as C
+    import torch
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    n, k = 60_001, 20
+    nq = 37 if storage == "f32" else 7                       # bf16 with nq < 8 stays on the exact path
+    rows = O.fast_unit_rows(n, dim, seed=97)
+    rows[4] = rows[n - 1]
+    ix = cqs_b200.B200Index(dim, storage=storage)
+    ix.append(None, rows); ix.finalize()
+    qs = O.fast_unit_rows(nq, dim, seed=98)
+    qs[0] = rows[4]
+    qs[3, 1] = np.inf                                        # -> empty result, the others unaffected
+    mask = np.random.default_rng(5).random(n) < 0.4
+    for bits in (None, O.mask_to_bitset(mask)):
+        r, s, nn = ix.search_batch_rows(qs, k, bits)
+        for i in range(nq):
+            a, b = ix.search_rows(qs[i], k, bits)
+            assert int(nn[i]) == a.shape[0]
+            assert np.array_equal(r[i, :nn[i]], a) and np.array_equal(s[i, :nn[i]].view(np.uint32), b.view(np.uint32))
+        assert int(nn[3]) == 0
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    good = np.delete(qs, 3, axis=0)
+    d_q = torch.from_numpy(good).to(dev)
+    m = good.shape[0]
+    d_sc = torch.empty((m, k), dtype=torch.float32, device=dev)
+    d_rw = torch.empty((m, k), dtype=torch.int64, device=dev)
+    d_n = torch.empty((m,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        check(lib.cqs_b200_search_many_device(ix._h, None, C.c_void_p(d_q.data_ptr()), m, k, None,
+                                              C.c_void_p(d_sc.data_ptr()), C.c_void_p(d_rw.data_ptr()),
+                                              C.c_void_p(d_n.data_ptr()), C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    for i in range(m):
+        a, b = ix.search_rows(good[i], k)
+        assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
+        assert np.array_equal(d_sc[i].cpu().numpy().view(np.uint32), b.view(np.uint32))
+    ix.close()
