@@ -305,15 +305,16 @@ def main():
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl", "none"],
                     help="N > 1: how the per-shard top-k lists are exchanged — 'peer' = inside the scan kernel "
                          "over NVLink peer memory (product path), 'nccl' = all_gather_into_tensor + merge kernel")
     ap.add_argument("--hnsw-rows", type=int, default=100_000,
                     help="rows of the corpus the CPU HNSW baseline is built on (0 = skip)")
-    ap.add_argument("--pipeline", type=int, default=2, choices=[1, 2],
-                    help="device-resident timing: launches are issued alternately on this many streams, so the "
-                         "tail of one query's kernel (list merge, cross-shard exchange) overlaps the streaming "
-                         "phase of the next query's kernel; every query is still its own launch")
+    ap.add_argument("--pipeline", type=int, default=4, choices=[1, 4],
+                    help="device-resident timing: 4 = one cqs_b200_search_many_device call per step, which issues "
+                         "the launches round-robin on the library's 4 launch lanes so the tail of one query's kernel "
+                         "(list merge, cross-shard exchange) overlaps the streaming phase of the next queries' kernels; "
+                         "1 = one call per query on one stream.  Every query is its own launch either way")
     ap.add_argument("--workload", default="single", choices=["single", "batch"],
                     help="single = BASELINE configs[1] (the headline, default); batch = configs[2]/[3]: "
                          "1024-query tensor-core batches (use --rows 10000000 --storage bf16 --queries-per-step 1024)")
@@ -367,6 +368,7 @@ def main():
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
     P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
+    diag_no_exchange = world > 1 and args.transport == "none"   # diagnostic only: shards scanned, lists never merged
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
     d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
@@ -383,13 +385,13 @@ def main():
 
     def step_device(s: int):
         """Q single-query scans, one kernel launch each, everything resident on the device.
-        P == 2: ONE library call per step (cqs_b200_search_many_device) issues the Q launches
-        alternately on two lanes; N>1: every launch also pushes its top-k to the peers over
+        P > 1: ONE library call per step (cqs_b200_search_many_device) issues the Q launches
+        round-robin on the library's launch lanes; N>1: every launch also pushes its top-k to the peers over
         NVLink, waits for theirs and merges in its tail (transport 'peer').  P == 1: a call per
         query on one stream; transport 'nccl': + one all-gather + merge kernel per step."""
         base = s * Q
         q0 = d_queries.data_ptr() + base * DIM * 4
-        if P == 2:
+        if P > 1:
             o_sc, o_rw, o_n = (m_sc, m_rw, m_n) if world > 1 else (d_sc, d_rw, d_n)
             check(lib.cqs_b200_search_many_device(ix._h, pg._h if pg is not None else None, C.c_void_p(q0), Q, K, None,
                                                   C.c_void_p(o_sc.data_ptr()), C.c_void_p(o_rw.data_ptr()),
@@ -407,7 +409,7 @@ def main():
                                              C.c_void_p(d_sc.data_ptr() + i * K * 4),
                                              C.c_void_p(d_rw.data_ptr() + i * K * 8),
                                              C.c_void_p(d_n.data_ptr() + i * 4), sp))
-        if world > 1:
+        if world > 1 and not diag_no_exchange:
             dist.all_gather_into_tensor(g_sc, d_sc)
             dist.all_gather_into_tensor(g_rw, d_rw)
             check(lib.cqs_b200_merge_topk_device(local, C.c_void_p(g_sc.data_ptr()), C.c_void_p(g_rw.data_ptr()),
@@ -435,10 +437,13 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.cqs_b200_kernel_launches() - launches0
+    per_rank_ms = [ms]
     if world > 1:
         t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        allms = torch.empty((world,), device=dev)
+        dist.all_gather_into_tensor(allms, t)
+        per_rank_ms = [float(x) for x in allms.cpu().tolist()]
+        ms = max(per_rank_ms)
     nq_timed = Q * args.steps
     value = nq_timed / (ms / 1e3)
 
@@ -532,7 +537,9 @@ def main():
             "config": {"workload": f"exact top-{K}, single query at a time, {n_total}x{DIM} {args.storage} "
                                    f"(BASELINE configs[1]), row-sharded over {world} GPU(s)",
                        "queries_per_step": Q, "rows_per_gpu": n_local,
-                       "launch_lanes": P,
+                       "launch_lanes": P, "per_rank_ms_timed_region": per_rank_ms,
+                       **({"DIAGNOSTIC": "transport none: per-shard lists are never merged; not a search result"}
+                          if diag_no_exchange else {}),
                        "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",
                        "collective": "none" if world == 1 else (
                            "none: every scan kernel stores its top-k into the peers' mailboxes over NVLink, "
@@ -553,7 +560,7 @@ def main():
                          "kernel": "scan_topk_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "avg_launch_us": avg_launch_s * 1e6,
                          "avg_launch_is": "timed region / launches = launch interval (CUDA events on the launching "
-                                          "stream); with 2 launch lanes the tail of a launch overlaps the next one",
+                                          "stream); with 4 launch lanes the tail of a launch overlaps the next ones",
                          "frac_of_nominal_8TBs": achieved / 8000.0},
         }
         if world == 1 and not args.no_cpu_baseline and keep_host:

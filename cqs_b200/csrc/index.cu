@@ -57,9 +57,9 @@ struct Shard {
   uint32_t* d_bitset = nullptr;
   uint64_t bitset_words = 0;
   // Scratch of one dense scan launch: per-CTA partial lists, CTA ticket + tile counter, the
-  // zero-padded query.  TWO sets, used alternately, so that a caller that alternates between
-  // two streams gets the tail of launch i (list merge, cross-shard exchange) overlapped with
-  // the streaming phase of launch i+1; a launch only waits for the launch two back.
+  // zero-padded query.  kLanes sets, used round-robin, so that a caller that rotates over
+  // kLanes streams gets the tail of launch i (list merge, cross-shard exchange) overlapped with
+  // the streaming phase of the next launches; a launch only waits for the launch kLanes back.
   struct ScanScratch {
     ckey_t* d_partial = nullptr;
     uint32_t* d_partial_cnt = nullptr;
@@ -68,11 +68,12 @@ struct Shard {
     cudaEvent_t ev = nullptr;      // recorded after the last launch that used this set
     cudaStream_t stream = nullptr;
     bool used = false;
-  } scr[2];
+  } scr[kLanes];
   uint32_t next_scr = 0;
-  // second launch lane of the many-query entry points (lane 0 is the caller's stream)
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // extra launch lanes of the many-query entry points (lane 0 is the caller's stream)
+  cudaStream_t lane_stream[kLanes - 1] = {};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[kLanes - 1] = {};
   // dense result / pool
   float* d_out_scores = nullptr;
   uint64_t* d_out_rows = nullptr;
@@ -184,8 +185,8 @@ static void free_shard(Shard& s) {
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   if (s.ev_fork) cudaEventDestroy(s.ev_fork);
-  if (s.ev_join) cudaEventDestroy(s.ev_join);
-  if (s.stream2) cudaStreamDestroy(s.stream2);
+  for (auto& e : s.ev_join) if (e) cudaEventDestroy(e);
+  for (auto& st : s.lane_stream) if (st) cudaStreamDestroy(st);
   if (s.stream) cudaStreamDestroy(s.stream);
   s = Shard();
 }
@@ -195,9 +196,9 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaSetDevice(device));
   CK(ix, cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, device));
   CK(ix, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  CK(ix, cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+  for (auto& st : s.lane_stream) CK(ix, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(ix, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
-  CK(ix, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+  for (auto& e : s.ev_join) CK(ix, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld,
                        cudaHostAllocDefault));
   for (auto& c : s.scr) {
@@ -498,10 +499,10 @@ static int mark_last(cqs_b200_index* ix, Shard& s, cudaStream_t st) {
   return 0;
 }
 // Dense scans: take the next scratch set; `st` only has to wait for the launch that used
-// that set last (two launches back), so launches issued alternately on two streams overlap.
+// that set last (kLanes launches back), so launches issued round-robin on kLanes streams overlap.
 static int acquire_scratch(cqs_b200_index* ix, Shard& s, cudaStream_t st, Shard::ScanScratch** out) {
   Shard::ScanScratch& c = s.scr[s.next_scr];
-  s.next_scr ^= 1u;
+  s.next_scr = (s.next_scr + 1) % kLanes;
   if (c.used && c.stream != st) CK(ix, cudaStreamWaitEvent(st, c.ev, 0));
   *out = &c;
   return 0;
@@ -844,9 +845,9 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   return release_scratch(ix, scr, st);
 }
 
-// nq single-query scans, one launch each, issued alternately on two lanes (`st` and the
-// shard's second stream) so the tail of launch i — list merge and, with `peer`, the
-// cross-shard exchange — overlaps the streaming phase of launch i+1.  Everything stays on
+// nq single-query scans, one launch each, issued round-robin on kLanes lanes (`st` and the
+// shard's own lane streams) so the tail of launch i — list merge and, with `peer`, the
+// cross-shard exchange — overlaps the streaming phase of the following launches.  Everything stays on
 // the device; `st` is joined with the second lane before returning.  d_queries: f32
 // [nq][q_stride]; `skip` (nullable): queries that are not launched (non-finite).  Caller
 // holds ix->mu (and peer->mu).
@@ -855,16 +856,21 @@ static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, 
                              float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
                              const uint8_t* skip, cudaStream_t st) {
   const bool staged = q_stride < ix->layout.ld;  // query must be zero padded to the row stride
-  cudaStream_t lanes[2] = {st, s.stream2};
-  bool forked = false;
+  cudaStream_t lanes[kLanes];
+  lanes[0] = st;
+  for (uint32_t l = 1; l < kLanes; ++l) lanes[l] = s.lane_stream[l - 1];
+  bool forked[kLanes] = {};
+  bool fork_recorded = false;
   uint32_t li = 0;
   for (uint32_t i = 0; i < nq; ++i) {
     if (skip && skip[i]) continue;
-    cudaStream_t ln = lanes[li & 1u];
-    if ((li & 1u) && !forked) {
-      CK(ix, cudaEventRecord(s.ev_fork, st));
-      CK(ix, cudaStreamWaitEvent(s.stream2, s.ev_fork, 0));
-      forked = true;
+    const uint32_t l = li % kLanes;
+    cudaStream_t ln = lanes[l];
+    if (l && !forked[l]) {
+      if (!fork_recorded) CK(ix, cudaEventRecord(s.ev_fork, st));
+      fork_recorded = true;
+      CK(ix, cudaStreamWaitEvent(ln, s.ev_fork, 0));
+      forked[l] = true;
     }
     ++li;
     Shard::ScanScratch* scr = nullptr;
@@ -889,10 +895,11 @@ static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, 
     if (peer) CK(ix, peer_mark(peer, ln, /*exclusive=*/false));
     if (int rc = release_scratch(ix, scr, ln)) return rc;
   }
-  if (forked) {
-    CK(ix, cudaEventRecord(s.ev_join, s.stream2));
-    CK(ix, cudaStreamWaitEvent(st, s.ev_join, 0));
-  }
+  for (uint32_t l = 1; l < kLanes; ++l)
+    if (forked[l]) {
+      CK(ix, cudaEventRecord(s.ev_join[l - 1], lanes[l]));
+      CK(ix, cudaStreamWaitEvent(st, s.ev_join[l - 1], 0));
+    }
   return 0;
 }
 

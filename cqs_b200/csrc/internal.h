@@ -13,6 +13,10 @@ struct PeerCtx;  // peer.cuh
 
 constexpr uint32_t kMaxK = 1024;        // CQS_B200_MAX_K
 constexpr uint32_t kMaxGrid = 1024;     // upper bound on scan CTAs (partial-list slots)
+// Launch lanes: single-query scans issued round-robin over this many streams / scratch sets,
+// so the tail of launch i (list merge, cross-shard exchange — slow while the next scans keep
+// HBM saturated) is hidden behind launches i+1 .. i+kLanes-1.  Launch i only waits for i-kLanes.
+constexpr uint32_t kLanes = 4;
 
 extern std::atomic<uint64_t> g_kernel_launches;
 

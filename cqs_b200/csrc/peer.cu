@@ -20,6 +20,8 @@
 
 namespace cqs {
 
+static_assert(kPeerLanes == kLanes, "peer lanes must match the scan launch lanes");
+
 // One launch = one exchange of nq lists per rank.  Grid <= number of SMs so every CTA is
 // resident (phase 2 spins on flags that the PEERS' phase 1 raises; nothing in phase 1 waits).
 //   phase 1: copy this rank's lists into every rank's mailbox (own HBM + NVLink stores);
@@ -70,9 +72,9 @@ cudaError_t launch_peer_gather_merge(const PeerCtx& c, const PeerGatherArgs& a, 
 }
 
 cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c, bool exclusive) {
-  if (++p->seq == 0) p->seq = 2;  // keep the parity sequence after a wrap
-  for (uint32_t i = 0; i < 2; ++i) {
-    if (!exclusive && i != (p->seq & 1u)) continue;
+  if (++p->seq == 0) p->seq = kPeerSlots;  // 0 is the mailbox's initial flag value
+  for (uint32_t i = 0; i < kPeerLanes; ++i) {
+    if (!exclusive && i != p->seq % kPeerLanes) continue;
     if (p->ev_used[i] && p->ev_stream[i] != st) {
       cudaError_t e = cudaStreamWaitEvent(st, p->ev[i], 0);
       if (e != cudaSuccess) return e;
@@ -89,8 +91,8 @@ cudaError_t peer_begin(cqs_b200_peer* p, cudaStream_t st, PeerCtx* c, bool exclu
   return cudaSuccess;
 }
 cudaError_t peer_mark(cqs_b200_peer* p, cudaStream_t st, bool exclusive) {
-  for (uint32_t i = 0; i < 2; ++i) {
-    if (!exclusive && i != (p->seq & 1u)) continue;
+  for (uint32_t i = 0; i < kPeerLanes; ++i) {
+    if (!exclusive && i != p->seq % kPeerLanes) continue;
     cudaError_t e = cudaEventRecord(p->ev[i], st);
     if (e != cudaSuccess) return e;
     p->ev_stream[i] = st;
@@ -152,7 +154,7 @@ int cqs_b200_peer_create(int device, uint32_t world, uint32_t rank, uint32_t max
   if (e == cudaSuccess) e = cudaMemset(p->d_status, 0, sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_ticket, 2 * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMemset(p->d_ticket, 0, 2 * sizeof(uint32_t));
-  for (int i = 0; i < 2; ++i)
+  for (uint32_t i = 0; i < kPeerLanes; ++i)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -270,7 +272,7 @@ void cqs_b200_peer_destroy(cqs_b200_peer* p) {
   cudaFree(p->d_mbox);
   cudaFree(p->d_status);
   cudaFree(p->d_ticket);
-  for (int i = 0; i < 2; ++i)
+  for (uint32_t i = 0; i < kPeerLanes; ++i)
     if (p->ev[i]) cudaEventDestroy(p->ev[i]);
   cudaGetLastError();
   delete p;

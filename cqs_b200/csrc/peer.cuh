@@ -14,10 +14,10 @@
 //   block = | flag u32, pad to 128 B | n[maxq] u32 | rows[cap] u64 | scores[cap] f32 |
 // Exchange number `seq` (same on every rank, 1, 2, 3, ...) uses slot seq % kPeerSlots
 // and writes `seq` into the flag.  A rank orders exchange seq after its own exchange
-// seq-2 (two may be in flight: the tail of one scan overlaps the next scan), and it
-// can only FINISH exchange seq-2 after every peer has pushed seq-2, which a peer does
-// after finishing (reading) its seq-4.  So when a push of `seq` lands in a peer's slot,
-// that peer is done with seq-4, the previous user of the slot: four slots suffice.
+// seq-L (L = kPeerLanes may be in flight: the tail of one scan overlaps the next scans),
+// and it can only FINISH exchange seq-L after every peer has pushed seq-L, which a peer
+// does after finishing (reading) its seq-2L.  So when a push of `seq` lands in a peer's
+// slot, that peer is done with seq-2L, the previous user of the slot: 2L slots suffice.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +27,8 @@
 namespace cqs {
 
 constexpr uint32_t kPeerMaxWorld = 8;
-constexpr uint32_t kPeerSlots = 4;
+constexpr uint32_t kPeerLanes = 4;   // == kLanes (internal.h)
+constexpr uint32_t kPeerSlots = 2 * kPeerLanes;
 constexpr uint32_t kPeerMaxQ = 1024;   // queries per exchange
 constexpr uint32_t kPeerFlagBytes = 128;
 

@@ -24,13 +24,13 @@ struct cqs_b200_peer {
   uint32_t* d_ticket = nullptr;     // [2] CTA tickets of the stand-alone kernel
   uint32_t seq = 0;                 // exchanges issued so far (identical on every rank)
   uint64_t timeout_ns = 5ull * 1000 * 1000 * 1000;
-  // Mailbox slots are reused every kPeerSlots exchanges and a fused scan may overlap the one
-  // before it (the caller alternates two streams): exchange seq waits for exchange seq-2
-  // (events by parity).  The stand-alone kernel shares d_ticket, so it is `exclusive`:
-  // ordered after every earlier exchange, and every later one after it.
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  cudaStream_t ev_stream[2] = {nullptr, nullptr};
-  bool ev_used[2] = {false, false};
+  // Mailbox slots are reused every kPeerSlots exchanges and a fused scan may overlap the
+  // kPeerLanes-1 before it (the caller rotates over that many streams): exchange seq waits for
+  // exchange seq-kPeerLanes (events by seq % kPeerLanes).  The stand-alone kernel shares
+  // d_ticket, so it is `exclusive`: ordered after every earlier exchange, and every later one after it.
+  cudaEvent_t ev[cqs::kPeerLanes] = {};
+  cudaStream_t ev_stream[cqs::kPeerLanes] = {};
+  bool ev_used[cqs::kPeerLanes] = {};
   std::atomic<int> failed{0};
 };
 
