@@ -41,6 +41,9 @@ SIGNATURES = {
     "cqs_b200_rrf_fuse": (C.c_int, [C.c_int, vp, vp, C.c_uint32, C.c_float, C.c_uint32, vp, vp, vp]),
     "cqs_b200_search_batch": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_sparse_attach": (C.c_int, [vp, vp, vp, vp, C.c_uint32]),
+    "cqs_b200_sparse_attach_device": (C.c_int, [vp, vp, vp, vp, C.c_uint64, C.c_uint32]),
+    "cqs_b200_sparse_save": (C.c_int, [vp, C.c_char_p, C.c_uint64]),
+    "cqs_b200_sparse_load": (C.c_int, [vp, C.c_char_p, C.c_uint64]),
     "cqs_b200_search_sparse": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_search_hybrid": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_float, C.c_uint32, vp,
                                          vp, vp, vp, vp, vp, vp]),

@@ -1216,6 +1216,54 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
 
 // ---- sparse ------------------------------------------------------------------
 
+// Build the token-major postings from a doc-major CSR that already sits on the device
+// (SpladeIndex::build, src/splade/index.rs:177-221, as a stable counting sort — sparse_build.cu).
+static int sparse_build_on_device(cqs_b200_index* ix, Shard& s, const uint64_t* d_indptr, const uint32_t* d_tok,
+                                  const float* d_w, uint64_t nnz, uint32_t vocab) {
+  if ((size_t)vocab * sizeof(uint32_t) > 220 * 1024)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "vocab %u too large for the on-device build (max 56320)", vocab);
+  SparseDev sp;
+  void* d_scratch = nullptr;
+  uint32_t* d_err = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_scratch); cudaFree(d_err);
+  };
+  auto drop = [&]() {
+    cudaFree(sp.d_tptr); cudaFree(sp.d_doc); cudaFree(sp.d_post);
+    cleanup();
+  };
+#define CKB(expr)                                                                      \
+  do {                                                                                 \
+    cudaError_t _eb = (expr);                                                          \
+    if (_eb != cudaSuccess) {                                                          \
+      drop();                                                                          \
+      CK(ix, _eb);                                                                     \
+    }                                                                                  \
+  } while (0)
+  CKB(cudaMalloc((void**)&sp.d_tptr, sizeof(uint64_t) * ((size_t)vocab + 1)));
+  CKB(cudaMalloc((void**)&sp.d_doc, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1)));
+  CKB(cudaMalloc((void**)&sp.d_post, sizeof(uint2) * std::max<uint64_t>(nnz, 1)));
+  CKB(cudaMalloc(&d_scratch, sparse_build_scratch_bytes(vocab, s.num_sms)));
+  CKB(cudaMalloc((void**)&d_err, sizeof(uint32_t)));
+  CKB(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), s.stream));
+  SparseBuildArgs a{d_indptr, d_tok, d_w, s.n_rows, nnz, vocab, sp.d_tptr, sp.d_doc, sp.d_post, d_scratch, d_err};
+  CKB(launch_sparse_build(a, s.num_sms, s.stream));
+  uint32_t err = 0;
+  CKB(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, s.stream));
+  CKB(cudaStreamSynchronize(s.stream));
+#undef CKB
+  if (err) {
+    drop();
+    return fail(CQS_B200_ERR_INVALID, err == 1 ? "a token id is >= vocab %u" : "a doc lists a token twice (vocab %u)", vocab);
+  }
+  cleanup();
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+  sp.vocab = vocab;
+  sp.nnz = nnz;
+  s.sparse = sp;
+  return CQS_B200_OK;
+}
+
 int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
                            const float* w, uint32_t vocab) {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
@@ -1226,51 +1274,180 @@ int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uin
     return fail(CQS_B200_ERR_UNSUPPORTED, "sparse leg needs a single-device index per process");
   Shard& s = ix->shards[0];
   const uint64_t n = s.n_rows;
+  if (indptr[0] != 0) return fail(CQS_B200_ERR_INVALID, "indptr[0] must be 0");
+  for (uint64_t d = 0; d < n; ++d)
+    if (indptr[d + 1] < indptr[d]) return fail(CQS_B200_ERR_INVALID, "indptr not monotone at %llu", (unsigned long long)d);
   const uint64_t nnz = indptr[n];
   if (nnz && (!tok || !w)) return fail(CQS_B200_ERR_INVALID, "NULL tok / w");
-  // doc-major CSR -> token-major postings, stable in doc order (what
-  // SpladeIndex::build produces, src/splade/index.rs:197-203).
-  std::vector<uint64_t> tptr((size_t)vocab + 1, 0);
-  for (uint64_t d = 0; d < n; ++d) {
-    if (indptr[d + 1] < indptr[d]) return fail(CQS_B200_ERR_INVALID, "indptr not monotone at %llu", (unsigned long long)d);
-    for (uint64_t e = indptr[d]; e < indptr[d + 1]; ++e) {
-      if (tok[e] >= vocab) return fail(CQS_B200_ERR_INVALID, "token id %u >= vocab %u", tok[e], vocab);
-      tptr[tok[e] + 1]++;
-    }
+  // upload the doc-major rows as they come out of `sparse_vectors` (src/store/sparse.rs:342);
+  // the transposition into posting lists happens on the device
+  CK(ix, cudaSetDevice(s.device));
+  uint64_t* d_indptr = nullptr;
+  uint32_t* d_tok = nullptr;
+  float* d_w = nullptr;
+  auto free_in = [&]() { cudaFree(d_indptr); cudaFree(d_tok); cudaFree(d_w); };
+  cudaError_t e = cudaMalloc((void**)&d_indptr, sizeof(uint64_t) * (n + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_tok, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_w, sizeof(float) * std::max<uint64_t>(nnz, 1));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_indptr, indptr, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(d_tok, tok, sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(d_w, w, sizeof(float) * nnz, cudaMemcpyHostToDevice, s.stream);
+  if (e != cudaSuccess) {
+    free_in();
+    CK(ix, e);
   }
-  for (uint32_t t = 0; t < vocab; ++t) tptr[t + 1] += tptr[t];
-  std::vector<uint32_t> pdoc(nnz);
-  std::vector<uint2> ppost(nnz);
-  {
-    std::vector<uint64_t> cur(tptr.begin(), tptr.end() - 1);
-    for (uint64_t d = 0; d < n; ++d)
-      for (uint64_t e = indptr[d]; e < indptr[d + 1]; ++e) {
-        uint64_t pos = cur[tok[e]]++;
-        // a doc listing the same token twice would make two lanes update one
-        // accumulator in the same step; the SPLADE encoder never emits that
-        // (src/splade/mod.rs:685-729, one weight per vocabulary slot).
-        if (pos > tptr[tok[e]] && pdoc[pos - 1] == (uint32_t)d)
-          return fail(CQS_B200_ERR_INVALID, "doc %llu lists token %u twice", (unsigned long long)d, tok[e]);
-        pdoc[pos] = (uint32_t)d;
-        uint32_t wbits;
-        memcpy(&wbits, &w[e], 4);
-        ppost[pos] = make_uint2((uint32_t)d, wbits);
-      }
+  int rc = sparse_build_on_device(ix, s, d_indptr, d_tok, d_w, nnz, vocab);
+  free_in();
+  return rc;
+}
+
+int cqs_b200_sparse_attach_device(cqs_b200_index* ix, const uint64_t* d_indptr, const uint32_t* d_tok,
+                                  const float* d_w, uint64_t nnz, uint32_t vocab) {
+  if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
+  if (!d_indptr || vocab == 0 || (nnz && (!d_tok || !d_w))) return fail(CQS_B200_ERR_INVALID, "NULL argument / zero vocab");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  if (ix->shards.size() != 1)
+    return fail(CQS_B200_ERR_UNSUPPORTED, "sparse leg needs a single-device index per process");
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  // the caller vouches for a monotone indptr with indptr[n_rows] == nnz; the two ends are checked
+  uint64_t ends[2] = {1, 0};
+  CK(ix, cudaMemcpy(&ends[0], d_indptr, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CK(ix, cudaMemcpy(&ends[1], d_indptr + s.n_rows, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (ends[0] != 0 || ends[1] != nnz) return fail(CQS_B200_ERR_INVALID, "indptr[0] != 0 or indptr[n_rows] != nnz");
+  return sparse_build_on_device(ix, s, d_indptr, d_tok, d_w, nnz, vocab);
+}
+
+// ---- SPLADE persistence (SpladeIndex::save / ::load, src/splade/index.rs:308-560) ----
+// Same contract as the reference's "SPDX" file: a 64-byte header carrying a format version, the
+// store's `splade_generation` counter, the chunk count and a body checksum; a load with a stale
+// generation, a different chunk count or a damaged body fails and the caller rebuilds from
+// `sparse_vectors`.  The body is this library's token-major layout (tptr, then (doc, weight)
+// pairs); chunk ids stay in the flat-matrix sidecar.  Written to a temp file and renamed.
+namespace {
+struct SparseFileHeader {
+  char magic[8];         // "CQSB2SPX"
+  uint32_t version;      // 1
+  uint32_t vocab;
+  uint64_t generation;
+  uint64_t n_docs;
+  uint64_t nnz;
+  uint64_t checksum;     // of header[0..40) + body
+  uint8_t pad[16];
+};
+static_assert(sizeof(SparseFileHeader) == 64, "header must be 64 bytes");
+uint64_t checksum_update(uint64_t h, const uint8_t* p, size_t n);
+}  // namespace
+
+int cqs_b200_sparse_save(cqs_b200_index* ix, const char* path, uint64_t generation) {
+  if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index only");
+  Shard& s = ix->shards[0];
+  if (!s.sparse.d_tptr) return fail(CQS_B200_ERR_INVALID, "no sparse index attached");
+  CK(ix, cudaSetDevice(s.device));
+  const uint32_t vocab = s.sparse.vocab;
+  const uint64_t nnz = s.sparse.nnz;
+  std::vector<uint64_t> tptr((size_t)vocab + 1);
+  std::vector<uint2> post(std::max<uint64_t>(nnz, 1));
+  CK(ix, cudaMemcpy(tptr.data(), s.sparse.d_tptr, sizeof(uint64_t) * tptr.size(), cudaMemcpyDeviceToHost));
+  if (nnz) CK(ix, cudaMemcpy(post.data(), s.sparse.d_post, sizeof(uint2) * nnz, cudaMemcpyDeviceToHost));
+  SparseFileHeader h{};
+  memcpy(h.magic, "CQSB2SPX", 8);
+  h.version = 1; h.vocab = vocab; h.generation = generation; h.n_docs = s.n_rows; h.nnz = nnz;
+  uint64_t ck = checksum_update(0xcbf29ce484222325ull, (const uint8_t*)&h, 40);
+  ck = checksum_update(ck, (const uint8_t*)tptr.data(), sizeof(uint64_t) * tptr.size());
+  ck = checksum_update(ck, (const uint8_t*)post.data(), sizeof(uint2) * nnz);
+  h.checksum = ck;
+  std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return fail(CQS_B200_ERR_INVALID, "cannot open %s for writing", tmp.c_str());
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(tptr.data(), sizeof(uint64_t), tptr.size(), f) == tptr.size() &&
+            (nnz == 0 || fwrite(post.data(), sizeof(uint2), nnz, f) == nnz);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {
+    remove(tmp.c_str());
+    return fail(CQS_B200_ERR_INVALID, "writing %s failed", path);
+  }
+  return CQS_B200_OK;
+}
+
+int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected_generation) {
+  if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
+  if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index only");
+  Shard& s = ix->shards[0];
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(CQS_B200_ERR_INVALID, "cannot open %s", path);
+  SparseFileHeader h{};
+  auto bad = [&](const char* why) {
+    fclose(f);
+    return fail(CQS_B200_ERR_INVALID, "%s: %s (rebuild from sparse_vectors)", path, why);
+  };
+  if (fread(&h, sizeof h, 1, f) != 1) return bad("short header");
+  if (memcmp(h.magic, "CQSB2SPX", 8) != 0 || h.version != 1) return bad("bad magic / version");
+  if (h.generation != expected_generation) return bad("stale generation");
+  if (h.n_docs != s.n_rows) return bad("chunk count differs from the index");
+  if (h.vocab == 0 || h.nnz > (1ull << 36)) return bad("implausible header");
+  std::vector<uint64_t> tptr((size_t)h.vocab + 1);
+  std::vector<uint2> post(std::max<uint64_t>(h.nnz, 1));
+  if (fread(tptr.data(), sizeof(uint64_t), tptr.size(), f) != tptr.size()) return bad("truncated");
+  if (h.nnz && fread(post.data(), sizeof(uint2), h.nnz, f) != h.nnz) return bad("truncated");
+  uint8_t extra;
+  if (fread(&extra, 1, 1, f) == 1) return bad("trailing bytes");
+  uint64_t ck = checksum_update(0xcbf29ce484222325ull, (const uint8_t*)&h, 40);
+  ck = checksum_update(ck, (const uint8_t*)tptr.data(), sizeof(uint64_t) * tptr.size());
+  ck = checksum_update(ck, (const uint8_t*)post.data(), sizeof(uint2) * h.nnz);
+  if (ck != h.checksum) return bad("checksum mismatch");
+  if (tptr[0] != 0 || tptr[h.vocab] != h.nnz) return bad("inconsistent offsets");
+  for (uint32_t t = 0; t < h.vocab; ++t)
+    if (tptr[t + 1] < tptr[t]) return bad("inconsistent offsets");
+  fclose(f);
+  std::vector<uint32_t> doc(std::max<uint64_t>(h.nnz, 1));
+  for (uint64_t i = 0; i < h.nnz; ++i) {
+    if (post[i].x >= s.n_rows) return fail(CQS_B200_ERR_INVALID, "%s: posting refers to chunk %u >= %llu", path, post[i].x, (unsigned long long)s.n_rows);
+    doc[i] = post[i].x;
   }
   CK(ix, cudaSetDevice(s.device));
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
-  s.sparse = SparseDev();
-  CK(ix, cudaMalloc((void**)&s.sparse.d_tptr, sizeof(uint64_t) * ((size_t)vocab + 1)));
-  CK(ix, cudaMalloc((void**)&s.sparse.d_doc, sizeof(uint32_t) * std::max<uint64_t>(nnz, 1)));
-  CK(ix, cudaMalloc((void**)&s.sparse.d_post, sizeof(uint2) * std::max<uint64_t>(nnz, 1)));
-  CK(ix, cudaMemcpy(s.sparse.d_tptr, tptr.data(), sizeof(uint64_t) * ((size_t)vocab + 1), cudaMemcpyHostToDevice));
-  if (nnz) {
-    CK(ix, cudaMemcpy(s.sparse.d_doc, pdoc.data(), sizeof(uint32_t) * nnz, cudaMemcpyHostToDevice));
-    CK(ix, cudaMemcpy(s.sparse.d_post, ppost.data(), sizeof(uint2) * nnz, cudaMemcpyHostToDevice));
+  SparseDev sp;
+  cudaError_t e = cudaMalloc((void**)&sp.d_tptr, sizeof(uint64_t) * tptr.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&sp.d_doc, sizeof(uint32_t) * doc.size());
+  if (e == cudaSuccess) e = cudaMalloc((void**)&sp.d_post, sizeof(uint2) * post.size());
+  if (e == cudaSuccess) e = cudaMemcpy(sp.d_tptr, tptr.data(), sizeof(uint64_t) * tptr.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sp.d_doc, doc.data(), sizeof(uint32_t) * doc.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(sp.d_post, post.data(), sizeof(uint2) * post.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(sp.d_tptr); cudaFree(sp.d_doc); cudaFree(sp.d_post);
+    CK(ix, e);
   }
-  s.sparse.vocab = vocab;
-  s.sparse.nnz = nnz;
+  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+  sp.vocab = h.vocab;
+  sp.nnz = h.nnz;
+  s.sparse = sp;
   return CQS_B200_OK;
+}
+
+// test hook: download the built postings (tptr [vocab+1], doc [nnz], weight [nnz])
+int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t* doc, float* w) {
+  if (!ix || ix->shards.size() != 1 || !ix->shards[0].sparse.d_tptr) return CQS_B200_ERR_INVALID;
+  Shard& s = ix->shards[0];
+  cudaSetDevice(s.device);
+  const uint64_t nnz = s.sparse.nnz;
+  if (tptr) cudaMemcpy(tptr, s.sparse.d_tptr, sizeof(uint64_t) * ((size_t)s.sparse.vocab + 1), cudaMemcpyDeviceToHost);
+  if (nnz && doc && w) {
+    std::vector<uint2> post(nnz);
+    cudaMemcpy(post.data(), s.sparse.d_post, sizeof(uint2) * nnz, cudaMemcpyDeviceToHost);
+    std::vector<uint32_t> d2(nnz);
+    cudaMemcpy(d2.data(), s.sparse.d_doc, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToHost);
+    for (uint64_t i = 0; i < nnz; ++i) {
+      if (d2[i] != post[i].x) return CQS_B200_ERR_INVALID;   // the two arrays must agree
+      doc[i] = post[i].x;
+      memcpy(&w[i], &post[i].y, 4);
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? CQS_B200_OK : CQS_B200_ERR_CUDA;
 }
 
 static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,

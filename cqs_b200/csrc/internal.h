@@ -144,6 +144,22 @@ constexpr uint32_t kSparseDocsPerBlock = 64;    // docs owned by one warp at a t
 size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz);
 cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
 
+// Inverted-index build on the device (sparse_build.cu): doc-major CSR -> token-major postings.
+struct SparseBuildArgs {
+  const uint64_t* d_indptr;  // [n_docs+1]
+  const uint32_t* d_tok;     // [nnz]
+  const float* d_w;          // [nnz]
+  uint64_t n_docs, nnz;
+  uint32_t vocab;            // <= 56,320 (the histogram lives in shared memory)
+  uint64_t* d_tptr;          // out [vocab+1]
+  uint32_t* d_doc;           // out [nnz]
+  void* d_post;              // out [nnz] (doc, weight bits)
+  void* d_scratch;           // sparse_build_scratch_bytes(vocab, num_sms)
+  uint32_t* d_err;           // out: 0 ok, 1 token id >= vocab, 2 a doc lists a token twice
+};
+size_t sparse_build_scratch_bytes(uint32_t vocab, int num_sms);
+cudaError_t launch_sparse_build(const SparseBuildArgs& a, int num_sms, cudaStream_t stream);
+
 struct FuseArgs {
   const uint64_t* d_dense_rows; const float* d_dense_scores; const uint32_t* d_n_dense;
   const uint64_t* d_sparse_rows; const float* d_sparse_scores; const uint32_t* d_n_sparse;

@@ -275,6 +275,19 @@ class B200Index:
         ww = np.ascontiguousarray(w, dtype=np.float32)
         check(lib.cqs_b200_sparse_attach(self._h, ptr(ip), ptr(t), ptr(ww), int(vocab)))
 
+    def sparse_attach_device(self, d_indptr: int, d_tok: int, d_w: int, nnz: int, vocab: int) -> None:
+        """Doc-major CSR already on the device (raw pointers); the inverted index is built there."""
+        check(lib.cqs_b200_sparse_attach_device(self._h, C.c_void_p(d_indptr), C.c_void_p(d_tok), C.c_void_p(d_w),
+                                                int(nnz), int(vocab)))
+
+    def sparse_save(self, path: str, generation: int) -> None:
+        """SpladeIndex::save (src/splade/index.rs:308): posting lists + the store's splade_generation."""
+        check(lib.cqs_b200_sparse_save(self._h, path.encode(), int(generation)))
+
+    def sparse_load(self, path: str, expected_generation: int) -> bool:
+        """SpladeIndex::load: False when the file is missing, damaged or stale (caller rebuilds)."""
+        return lib.cqs_b200_sparse_load(self._h, path.encode(), int(expected_generation)) == 0
+
     def search_sparse_rows(self, q_tok, q_w, k: int, bitset=None):
         t = np.ascontiguousarray(q_tok, dtype=np.uint32)
         w = np.ascontiguousarray(q_w, dtype=np.float32)

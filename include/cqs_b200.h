@@ -154,6 +154,16 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
  * (row i of the CSR is chunk i): indptr[len+1], tok/w[indptr[len]]. Copied. */
 int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
                            const float* w, uint32_t vocab);
+/* Same with the doc-major CSR already on the device (indptr[n_rows] must equal nnz). */
+int cqs_b200_sparse_attach_device(cqs_b200_index* ix, const uint64_t* d_indptr, const uint32_t* d_tok,
+                                  const float* d_w, uint64_t nnz, uint32_t vocab);
+/* SpladeIndex::save / ::load (src/splade/index.rs:308-560): persist the built posting lists
+ * with the store's `splade_generation` counter (src/splade/index.rs:13-16) in the header.
+ * load fails (-> caller rebuilds from `sparse_vectors`, src/store/sparse.rs:342) when the file
+ * is missing or damaged, its generation differs from `expected_generation`, or its chunk
+ * count differs from cqs_b200_len(ix).  Atomic write (temp file + rename). */
+int cqs_b200_sparse_save(cqs_b200_index* ix, const char* path, uint64_t generation);
+int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected_generation);
 /* Sparse-only search: score[c] = sum over query tokens IN QUERY ORDER of
  * qw*dw (separate f32 mul and add), only chunks touched by >= 1 posting. */
 int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const float* q_w,

@@ -242,3 +242,108 @@ def test_rrf_fuse_reference_vectors_and_random(cqs):
         ids, sc = rrf_fuse_n(lists, limit)
         assert ids.tolist() == [i for i, _ in want]
         assert np.array_equal(bits(sc), bits([s for _, s in want]))
+
+
+# ---- inverted-index build on the device (sparse_build.cu) and its persistence ----------------
+
+def _postings(ix, vocab, nnz):
+    import ctypes as C
+    from cqs_b200.capi import lib
+    lib.cqs_b200_debug_sparse_postings.restype = C.c_int
+    lib.cqs_b200_debug_sparse_postings.argtypes = [C.c_void_p] * 4
+    tptr = np.zeros(vocab + 1, np.uint64); doc = np.zeros(max(nnz, 1), np.uint32); w = np.zeros(max(nnz, 1), f32)
+    assert lib.cqs_b200_debug_sparse_postings(ix._h, tptr.ctypes.data_as(C.c_void_p), doc.ctypes.data_as(C.c_void_p),
+                                              w.ctypes.data_as(C.c_void_p)) == 0
+    return tptr, doc[:nnz], w[:nnz]
+
+
+def _zipf_csr(rng, n_docs, vocab, mean_nnz):
+    """Zipf-distributed tokens (a few very long posting lists, many same-token neighbours), some empty docs."""
+    p = 1.0 / np.arange(1, vocab + 1) ** 1.1
+    p /= p.sum()
+    nnz_d = np.clip(rng.poisson(mean_nnz, n_docs), 0, min(vocab, 4 * mean_nnz))
+    nnz_d[rng.random(n_docs) < 0.02] = 0
+    indptr = np.zeros(n_docs + 1, np.uint64); indptr[1:] = np.cumsum(nnz_d)
+    tok = np.empty(int(indptr[-1]), np.uint32)
+    for d in range(n_docs):
+        if nnz_d[d]:
+            tok[int(indptr[d]):int(indptr[d + 1])] = np.sort(rng.choice(vocab, size=int(nnz_d[d]), replace=False, p=p))
+    w = rng.random(tok.shape[0]).astype(f32) + f32(0.01)
+    return indptr, tok, w
+
+
+@pytest.mark.parametrize("n_docs,vocab,mean_nnz", [(1, 7, 3), (700, 97, 20), (40_000, 30522, 60), (3000, 56000, 40)])
+def test_device_build_equals_stable_transposition(cqs, n_docs, vocab, mean_nnz):
+    """SpladeIndex::build (src/splade/index.rs:177-221): token-major lists in ascending chunk order ==
+    a stable sort of the doc-major entries by token id."""
+    rng = np.random.default_rng(n_docs + vocab)
+    indptr, tok, w = _zipf_csr(rng, n_docs, vocab, mean_nnz)
+    ix = cqs.B200Index(8)
+    ix.append(None, O.fast_unit_rows(n_docs, 8, seed=1)); ix.finalize()
+    ix.sparse_attach(indptr, tok, w, vocab)
+    nnz = tok.shape[0]
+    tptr, pdoc, pw = _postings(ix, vocab, nnz)
+    order = np.argsort(tok, kind="stable")
+    doc_of = np.repeat(np.arange(n_docs, dtype=np.uint32), np.diff(indptr.astype(np.int64)))
+    exp_tptr = np.zeros(vocab + 1, np.uint64); exp_tptr[1:] = np.cumsum(np.bincount(tok, minlength=vocab))
+    assert np.array_equal(tptr, exp_tptr)
+    assert np.array_equal(pdoc, doc_of[order])
+    assert np.array_equal(bits(pw), bits(w[order]))
+    ix.close()
+
+
+def test_device_build_rejects_bad_tokens_and_accepts_device_input(cqs):
+    import torch
+    rng = np.random.default_rng(3)
+    n_docs, vocab = 2000, 500
+    indptr, tok, w = _zipf_csr(rng, n_docs, vocab, 25)
+    ix = cqs.B200Index(8)
+    ix.append(None, O.fast_unit_rows(n_docs, 8, seed=1)); ix.finalize()
+    bad = tok.copy(); bad[len(bad) // 2] = vocab
+    with pytest.raises(cqs.B200Error):
+        ix.sparse_attach(indptr, bad, w, vocab)
+    dev = torch.device("cuda", 0)
+    d_ip = torch.from_numpy(indptr.view(np.int64)).to(dev)
+    d_tok = torch.from_numpy(tok.view(np.int32)).to(dev)
+    d_w = torch.from_numpy(w).to(dev)
+    ix.sparse_attach_device(d_ip.data_ptr(), d_tok.data_ptr(), d_w.data_ptr(), tok.shape[0], vocab)
+    a = _postings(ix, vocab, tok.shape[0])
+    ix.sparse_attach(indptr, tok, w, vocab)
+    b = _postings(ix, vocab, tok.shape[0])
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ix.close()
+
+
+def test_sparse_persistence_generation_and_checksum(cqs, tmp_path):
+    """SpladeIndex::save/load contract (src/splade/index.rs:13-16, :308-560): stale generation,
+    damaged body or a different chunk count -> load refuses and the caller rebuilds."""
+    rng = np.random.default_rng(5)
+    n_docs, vocab = 3000, 800
+    indptr, tok, w = _zipf_csr(rng, n_docs, vocab, 30)
+    rows = O.fast_unit_rows(n_docs, 8, seed=1)
+    ix = cqs.B200Index(8)
+    ix.append(None, rows); ix.finalize()
+    ix.sparse_attach(indptr, tok, w, vocab)
+    path = str(tmp_path / "splade.b200.bin")
+    ix.sparse_save(path, generation=41)
+    qt = np.asarray([0, 1, 5, 17, 300], np.uint32); qw = np.asarray([1.0, .5, .25, 2.0, .7], f32)
+    want = ix.search_sparse_rows(qt, qw, 50)
+    ix.close()
+    ix2 = cqs.B200Index(8)
+    ix2.append(None, rows); ix2.finalize()
+    assert not ix2.sparse_load(path, expected_generation=42)            # sparse_vectors changed since the save
+    assert not ix2.sparse_load(str(tmp_path / "missing.bin"), 41)
+    assert ix2.sparse_load(path, expected_generation=41)
+    got = ix2.search_sparse_rows(qt, qw, 50)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(bits(got[1]), bits(want[1]))
+    ix3 = cqs.B200Index(8)
+    ix3.append(None, rows[:-1]); ix3.finalize()
+    assert not ix3.sparse_load(path, expected_generation=41)            # chunk count differs
+    ix3.close()
+    raw = bytearray(open(path, "rb").read())
+    raw[len(raw) // 2] ^= 0x40
+    open(path, "wb").write(bytes(raw))
+    assert not ix2.sparse_load(path, expected_generation=41)            # checksum
+    got = ix2.search_sparse_rows(qt, qw, 50)                            # a refused load leaves the old index in place
+    assert np.array_equal(got[0], want[0])
+    ix2.close()
