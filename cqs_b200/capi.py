@@ -65,6 +65,8 @@ SIGNATURES = {
     "cqs_b200_search_sharded_device": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]),
     "cqs_b200_search_many_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]),
     "cqs_b200_search_batch_sharded": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
+    "cqs_b200_search_hybrid_sharded": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32, C.c_float, C.c_uint32, vp,
+                                                 vp, vp, vp, vp, vp, vp]),
     "cqs_b200_peer_gather_merge": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]),
     "cqs_b200_len": (C.c_uint64, [vp]),
     "cqs_b200_dim": (C.c_uint32, [vp]),

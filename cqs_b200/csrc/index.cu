@@ -82,6 +82,9 @@ struct Shard {
   float* d_sp_scores = nullptr;
   uint64_t* d_sp_rows = nullptr;
   uint32_t* d_sp_n = nullptr;
+  float* d_spm_scores = nullptr;   // cross-shard merged sparse pool (sharded hybrid)
+  uint64_t* d_spm_rows = nullptr;
+  uint32_t* d_spm_n = nullptr;
   ckey_t* d_sp_partial = nullptr;
   uint32_t* d_sp_partial_cnt = nullptr;
   uint32_t* d_sp_done = nullptr;
@@ -171,6 +174,7 @@ static void free_shard(Shard& s) {
   }
   cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
   cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
+  cudaFree(s.d_spm_scores); cudaFree(s.d_spm_rows); cudaFree(s.d_spm_n);
   cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
   cudaFree(s.d_q_tok); cudaFree(s.d_q_w); cudaFree(s.d_bounds);
   cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
@@ -1541,11 +1545,16 @@ static int copy_fused_out(cqs_b200_index* ix, Shard& s, uint32_t cap, uint64_t* 
   return 0;
 }
 
-int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_t* q_tok,
-                           const float* q_w, uint32_t q_nnz, float alpha, uint32_t pool_k,
-                           const uint32_t* bitset, uint64_t* out_rows, float* out_fused,
-                           float* out_dense, float* out_sparse_raw, uint8_t* out_present,
-                           uint32_t* out_n) {
+// peer == nullptr: this index alone.  Otherwise the corpus is row-sharded: the dense leg's scan
+// exchanges + merges in its tail (GLOBAL dense pool on every rank), the sparse leg's per-shard pool
+// goes through one gather+merge kernel (GLOBAL sparse pool), and every rank fuses the same two
+// pools — max_sparse is the merged pool's top-1 — so all ranks return the unsharded answer
+// (SURVEY.md §8e).
+static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query,
+                              const uint32_t* q_tok, const float* q_w, uint32_t q_nnz, float alpha,
+                              uint32_t pool_k, const uint32_t* bitset, uint64_t* out_rows,
+                              float* out_fused, float* out_dense, float* out_sparse_raw,
+                              uint8_t* out_present, uint32_t* out_n) {
   if (out_n) *out_n = 0;
   int rc = check_searchable(ix);
   if (rc) return rc;
@@ -1555,18 +1564,30 @@ int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_
   if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index required");
   if (pool_k == 0 || ix->n_rows == 0) return CQS_B200_OK;
   std::lock_guard<std::mutex> g(ix->mu);
+  if (peer && (rc = check_peer(ix, peer))) return rc;
+  std::unique_lock<std::mutex> gp;
+  if (peer) gp = std::unique_lock<std::mutex>(peer->mu);
   Shard& s = ix->shards[0];
   if (!s.sparse.d_tptr) return fail(CQS_B200_ERR_INVALID, "no sparse index attached");
   CK(ix, cudaSetDevice(s.device));
+  if (peer && !s.d_spm_scores) {
+    CK(ix, cudaMalloc((void**)&s.d_spm_scores, sizeof(float) * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_spm_rows, sizeof(uint64_t) * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_spm_n, sizeof(uint32_t)));
+  }
   // dense leg: a malformed query yields an EMPTY dense pool (src/cagra.rs:458-470);
   // the sparse leg still runs (search_hybrid_inner calls both unconditionally).
   const bool dense_ok = query_is_finite(query, ix->dim);
   CK(ix, cudaMemsetAsync(s.d_out_n, 0, 4, s.stream));
   CK(ix, cudaMemsetAsync(s.d_sp_n, 0, 4, s.stream));
+  if (peer) CK(ix, cudaMemsetAsync(s.d_spm_n, 0, 4, s.stream));
   const uint32_t* d_bits = nullptr;
   if (dense_ok) {
-    rc = launch_dense(ix, s, query, pool_k, bitset);
+    PeerCtx pc;
+    if (peer) CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/false));
+    rc = launch_dense(ix, s, query, pool_k, bitset, nullptr, false, peer ? &pc : nullptr);
     if (rc) return rc;
+    if (peer) CK(ix, peer_mark(peer, s.stream, /*exclusive=*/false));
     if (bitset) d_bits = s.d_bitset;
   } else if (bitset) {
     CK(ix, cudaMemcpyAsync(s.d_bitset, bitset, ((s.n_rows + 31) / 32) * 4, cudaMemcpyHostToDevice, s.stream));
@@ -1576,10 +1597,20 @@ int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_
     if (!q_tok || !q_w) return fail(CQS_B200_ERR_INVALID, "NULL sparse query");
     rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits);
     if (rc) return rc;
+    if (peer) {
+      PeerCtx pc;
+      CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/true));
+      PeerGatherArgs ga{s.d_sp_scores, s.d_sp_rows, s.d_sp_n, 1, pool_k,
+                        s.d_spm_scores, s.d_spm_rows, s.d_spm_n, peer->d_ticket};
+      CK(ix, launch_peer_gather_merge(pc, ga, s.num_sms, s.stream));
+      CK(ix, peer_mark(peer, s.stream, /*exclusive=*/true));
+    }
   }
   FuseArgs f;
   f.d_dense_rows = s.d_out_rows; f.d_dense_scores = s.d_out_scores; f.d_n_dense = s.d_out_n;
-  f.d_sparse_rows = s.d_sp_rows; f.d_sparse_scores = s.d_sp_scores; f.d_n_sparse = s.d_sp_n;
+  f.d_sparse_rows = peer ? s.d_spm_rows : s.d_sp_rows;
+  f.d_sparse_scores = peer ? s.d_spm_scores : s.d_sp_scores;
+  f.d_n_sparse = peer ? s.d_spm_n : s.d_sp_n;
   f.alpha = alpha; f.pool_k = pool_k;
   f.d_out_rows = s.d_f_rows; f.d_out_fused = s.d_f_fused; f.d_out_dense = s.d_f_dense;
   f.d_out_sparse_raw = s.d_f_sraw; f.d_out_present = s.d_f_present; f.d_out_n = s.d_f_n;
@@ -1587,8 +1618,36 @@ int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_
   rc = copy_fused_out(ix, s, pool_k, out_rows, out_fused, out_dense, out_sparse_raw, out_present,
                       out_n, s.stream);
   if (rc) return rc;
+  if (peer) {
+    uint32_t st = 0;
+    CK(ix, cudaMemcpy(&st, peer->d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st) {
+      peer->failed.store(1);
+      *out_n = 0;
+      return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this search)");
+    }
+  }
   if (dense_ok && ix->timing) CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
   return CQS_B200_OK;
+}
+
+int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_t* q_tok,
+                           const float* q_w, uint32_t q_nnz, float alpha, uint32_t pool_k,
+                           const uint32_t* bitset, uint64_t* out_rows, float* out_fused,
+                           float* out_dense, float* out_sparse_raw, uint8_t* out_present,
+                           uint32_t* out_n) {
+  return search_hybrid_impl(ix, nullptr, query, q_tok, q_w, q_nnz, alpha, pool_k, bitset, out_rows,
+                            out_fused, out_dense, out_sparse_raw, out_present, out_n);
+}
+
+int cqs_b200_search_hybrid_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query,
+                                   const uint32_t* q_tok, const float* q_w, uint32_t q_nnz,
+                                   float alpha, uint32_t pool_k, const uint32_t* bitset,
+                                   uint64_t* out_rows, float* out_fused, float* out_dense,
+                                   float* out_sparse_raw, uint8_t* out_present, uint32_t* out_n) {
+  if (!peer) return fail(CQS_B200_ERR_INVALID, "peer is NULL");
+  return search_hybrid_impl(ix, peer, query, q_tok, q_w, q_nnz, alpha, pool_k, bitset, out_rows,
+                            out_fused, out_dense, out_sparse_raw, out_present, out_n);
 }
 
 int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* dense_scores,

@@ -299,7 +299,7 @@ class B200Index:
                                          ptr(rows), ptr(scores), C.byref(n)))
         return rows[: n.value].copy(), scores[: n.value].copy()
 
-    def search_hybrid_rows(self, query, q_tok, q_w, alpha: float, pool_k: int, bitset=None):
+    def search_hybrid_rows(self, query, q_tok, q_w, alpha: float, pool_k: int, bitset=None, peer=None):
         q = np.ascontiguousarray(query, dtype=np.float32)
         t = np.ascontiguousarray(q_tok, dtype=np.uint32)
         w = np.ascontiguousarray(q_w, dtype=np.float32)
@@ -311,9 +311,14 @@ class B200Index:
         present = np.empty(kk, np.uint8)
         n = C.c_uint32(0)
         bs = None if bitset is None else np.ascontiguousarray(bitset, dtype=np.uint32)
-        check(lib.cqs_b200_search_hybrid(self._h, ptr(q), ptr(t), ptr(w), t.shape[0], float(alpha),
-                                         int(pool_k), ptr(bs), ptr(rows), ptr(fused), ptr(dense),
-                                         ptr(sraw), ptr(present), C.byref(n)))
+        if peer is not None:   # row-sharded corpus: every rank gets the global fused list
+            check(lib.cqs_b200_search_hybrid_sharded(self._h, peer._h, ptr(q), ptr(t), ptr(w), t.shape[0],
+                                                     float(alpha), int(pool_k), ptr(bs), ptr(rows), ptr(fused),
+                                                     ptr(dense), ptr(sraw), ptr(present), C.byref(n)))
+        else:
+            check(lib.cqs_b200_search_hybrid(self._h, ptr(q), ptr(t), ptr(w), t.shape[0], float(alpha),
+                                             int(pool_k), ptr(bs), ptr(rows), ptr(fused), ptr(dense),
+                                             ptr(sraw), ptr(present), C.byref(n)))
         m = n.value
         return dict(rows=rows[:m].copy(), fused=fused[:m].copy(), dense=dense[:m].copy(),
                     sparse_raw=sraw[:m].copy(), present=present[:m].copy())

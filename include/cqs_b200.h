@@ -273,6 +273,15 @@ int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const f
 int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries,
                                   uint32_t nq, uint32_t k, const uint32_t* bitset,
                                   uint64_t* out_rows, float* out_scores, uint32_t* out_n);
+/* cqs_b200_search_hybrid over the row-sharded corpus (each rank attached the SPLADE rows of
+ * ITS chunks): GLOBAL dense pool from the scan's own exchange, GLOBAL sparse pool from one
+ * gather+merge kernel, the same fusion on every rank (max_sparse = the merged pool's top-1).
+ * Identical to the unsharded cqs_b200_search_hybrid. */
+int cqs_b200_search_hybrid_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query,
+                                   const uint32_t* q_tok, const float* q_w, uint32_t q_nnz,
+                                   float alpha, uint32_t pool_k, const uint32_t* bitset,
+                                   uint64_t* out_rows, float* out_fused, float* out_dense,
+                                   float* out_sparse_raw, uint8_t* out_present, uint32_t* out_n);
 /* The exchange alone: this rank's nq sorted lists (device, [nq][k], GLOBAL rows) ->
  * GLOBAL top-k of every query on every rank.  nq <= 1024, nq*k <= max_elems. */
 int cqs_b200_peer_gather_merge(cqs_b200_peer* p, const float* d_scores, const uint64_t* d_rows,

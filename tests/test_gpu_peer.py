@@ -278,3 +278,65 @@ def test_two_processes_cuda_ipc_mailboxes():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert out[0] and out[1]
+
+
+def test_two_gpus_sharded_hybrid_equals_unsharded():
+    """Dense pool from the scan's own exchange + sparse pool through the gather+merge kernel + the same
+    fusion on every rank == cqs_b200_search_hybrid on the whole corpus (src/search/query.rs:914-1005)."""
+    _need_gpus(2)
+    import torch
+    import cqs_b200
+    from cqs_b200.sharded import PeerGroup, shard_range
+    G = min(torch.cuda.device_count(), 4)
+    rng = np.random.default_rng(77)
+    n, dim, vocab, pool = 24_000, 768, 3000, 500
+    rows = O.fast_unit_rows(n, dim, seed=77, clustered=True)
+    nnz_d = rng.integers(0, 40, n)
+    indptr = np.zeros(n + 1, np.uint64); indptr[1:] = np.cumsum(nnz_d)
+    tok = np.concatenate([np.sort(rng.choice(vocab, size=int(c), replace=False)) for c in nnz_d]).astype(np.uint32)
+    w = (rng.random(tok.shape[0]) + 0.01).astype(f32)
+    whole = cqs_b200.B200Index(dim, devices=[0])
+    whole.append(None, rows); whole.finalize()
+    whole.sparse_attach(indptr, tok, w, vocab)
+    shards, groups = [], []
+    for g in range(G):
+        row0, nl = shard_range(n, G, g)
+        ix = cqs_b200.B200Index(dim, devices=[g], row_base=row0)
+        ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        lo, hi = int(indptr[row0]), int(indptr[row0 + nl])
+        ix.sparse_attach(indptr[row0:row0 + nl + 1] - indptr[row0], tok[lo:hi], w[lo:hi], vocab)
+        shards.append(ix); groups.append(PeerGroup(g, G, g))
+    PeerGroup.connect_local(groups)
+    cases = []
+    for trial in range(6):
+        q = rows[int(rng.integers(0, n))] + rng.standard_normal(dim).astype(f32) * f32(0.02)
+        q = (q / np.linalg.norm(q)).astype(f32)
+        qn = int(rng.integers(1, 48))
+        qt = np.sort(rng.choice(vocab, size=qn, replace=False)).astype(np.uint32)
+        cases.append((q, qt, rng.random(qn).astype(f32), [0.85, 0.0, 1.0, 0.6, 0.1, 0.8][trial]))
+    bad = cases[0][0].copy(); bad[0] = np.nan
+    cases.append((bad, cases[0][1], cases[0][2], 0.8))        # empty dense pool, sparse leg still runs
+    cases.append((cases[1][0], np.zeros(0, np.uint32), np.zeros(0, f32), 0.8))   # no sparse query
+    res = [None] * G
+
+    def run(g):
+        res[g] = [shards[g].search_hybrid_rows(q, qt, qw, a, pool, peer=groups[g]) for q, qt, qw, a in cases]
+
+    th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    for i, (q, qt, qw, a) in enumerate(cases):
+        want = whole.search_hybrid_rows(q, qt, qw, a, pool)
+        for g in range(G):
+            got = res[g][i]
+            assert np.array_equal(got["rows"], want["rows"]), (i, g)
+            for key in ("fused", "dense", "sparse_raw"):
+                assert np.array_equal(got[key].view(np.uint32), want[key].view(np.uint32)), (i, g, key)
+            assert np.array_equal(got["present"], want["present"])
+    for g in range(G):
+        assert groups[g].status() == 0
+        groups[g].close(); shards[g].close()
+    whole.close()
