@@ -310,6 +310,26 @@ struct TopK {
   }
 };
 
+// Collective: exact top-k of whatever the accumulator holds, descending in buf[0..min(n,k)).
+// Two histogram selections (3 us each) first cut the buffer down to the k best plus the few
+// keys sharing the k-th key's bucket, so the exact sort runs on ~k keys (rank sort when
+// k <= 512) instead of on the whole buffer (a 2048-4096 key bitonic sort costs 20-40 us,
+// paid by every CTA at the end of its scan and again by the last CTA's merge).
+// Not inlined (TopK by value: a handful of shared-memory pointers): the scan file instantiates
+// 48 kernels and this tail code would otherwise be compiled into each of them.
+template <int ITEMS>
+__device__ __noinline__ void topk_finish(TopK tk, uint32_t k) {
+  tk.g.sync();
+  if (min(*tk.cnt, tk.cap) > kRankSortMax) {
+    const ckey_t before = *tk.thr;
+    tk.template select<ITEMS>(k);
+    if (tk.g.tid == 0 && before > *tk.thr) *tk.thr = before;
+    tk.g.sync();
+    if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k) tk.template select<ITEMS>(k);
+  }
+  tk.compact(k);
+}
+
 constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the partial-list scratch
 
 // Last-CTA merge of the per-CTA sorted candidate lists (shared by the dense and
@@ -330,7 +350,7 @@ constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the par
 //     still offers.
 //  3. final exact sort, emit (score desc, row asc); unused slots = (-inf, UINT64_MAX).
 template <int ITEMS>
-__device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_pos, uint32_t k,
+__device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, uint32_t k,
                                                         const ckey_t* partial,
                                                         const uint32_t* partial_cnt, uint32_t G,
                                                         uint64_t row_base, float* out_scores,
@@ -421,7 +441,7 @@ __device__ __forceinline__ void merge_partials_and_emit(TopK& tk, uint32_t* s_po
     }
     tk.g.sync();
   }
-  tk.compact(k);
+  topk_finish<ITEMS>(tk, k);
   if (trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
   uint32_t n = *tk.cnt;
   for (uint32_t i = tid; i < k; i += T) {

@@ -39,404 +39,9 @@
 
 #include "common.cuh"
 #include "internal.h"
-#include "peer.cuh"
+#include "scan_params.cuh"
 
 namespace cqs {
-
-constexpr int kWarps = 8;                       // consumer warps
-constexpr int kConsumers = kWarps * 32;
-constexpr int kThreads = kConsumers + 32;       // + producer warp
-constexpr uint32_t kCap = 4096;                 // candidate slots per CTA (32 KB)
-constexpr uint32_t kStageTarget = 24576;        // bytes per pipeline stage (target)
-constexpr uint32_t kInFlight = 131072;          // bytes in flight per SM (target)
-
-// ---- mbarrier / TMA bulk-copy primitives ---------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t cnt) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(cnt));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)),
-      "r"(phase)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes,
-                                         uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(smem)),
-      "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-struct ScanParams {
-  const uint8_t* rows;
-  uint64_t n_rows;
-  uint64_t row_bytes;
-  const float* query;
-  const uint32_t* bitset;
-  uint32_t k;
-  uint64_t row_base;
-  ckey_t* partial;
-  uint32_t* partial_cnt;
-  uint32_t* done;        // [0] finished-CTA ticket, [1] dynamic tile counter; zero between launches
-  float* out_scores;
-  uint64_t* out_rows;
-  uint32_t* out_n;
-  unsigned long long* trace;  // optional [grid][8] globaltimer stamps (development aid)
-  ScanSignals sig;            // structured filter + per-row signals (sig.pipeline / sig.d_ctype gate them)
-  uint32_t* host_flag;        // optional: host-mapped word that receives `seq` once the result is written
-  uint32_t seq;
-  PeerCtx peer;               // peer.world != 0: exchange the local list with the other shards and emit the GLOBAL top-k
-};
-
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#define TRACE(slot) do { if (p.trace && ctid == 0) p.trace[blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
-
-template <int MODE>
-struct LaneVec;
-template <>
-struct LaneVec<0> {  // f32, 4 elems / 16 B
-  static constexpr int E = 4;
-  static constexpr int BYTES = 16;
-  uint32_t r[4];
-  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
-    uint4 v = *reinterpret_cast<const uint4*>(p);
-    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-  }
-  __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
-  __device__ __forceinline__ void fma(const float* q, float* acc) const {
-    acc[0] = fmaf(__uint_as_float(r[0]), q[0], acc[0]);
-    acc[1] = fmaf(__uint_as_float(r[1]), q[1], acc[1]);
-    acc[2] = fmaf(__uint_as_float(r[2]), q[2], acc[2]);
-    acc[3] = fmaf(__uint_as_float(r[3]), q[3], acc[3]);
-  }
-};
-template <>
-struct LaneVec<1> {  // bf16, 8 elems / 16 B
-  static constexpr int E = 8;
-  static constexpr int BYTES = 16;
-  uint32_t r[4];
-  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
-    uint4 v = *reinterpret_cast<const uint4*>(p);
-    r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-  }
-  __device__ __forceinline__ void zero() { r[0] = r[1] = r[2] = r[3] = 0; }
-  __device__ __forceinline__ void fma(const float* q, float* acc) const {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      // bf16 -> f32 is a 16-bit shift (exact)
-      acc[(2 * i) & 3] = fmaf(__uint_as_float(r[i] << 16), q[2 * i], acc[(2 * i) & 3]);
-      acc[(2 * i + 1) & 3] =
-          fmaf(__uint_as_float(r[i] & 0xFFFF0000u), q[2 * i + 1], acc[(2 * i + 1) & 3]);
-    }
-  }
-};
-template <>
-struct LaneVec<2> {  // bf16, 4 elems / 8 B
-  static constexpr int E = 4;
-  static constexpr int BYTES = 8;
-  uint32_t r[2];
-  __device__ __forceinline__ void load(const uint8_t* p) {  // p: shared memory
-    uint2 v = *reinterpret_cast<const uint2*>(p);
-    r[0] = v.x; r[1] = v.y;
-  }
-  __device__ __forceinline__ void zero() { r[0] = r[1] = 0; }
-  __device__ __forceinline__ void fma(const float* q, float* acc) const {
-    acc[0] = fmaf(__uint_as_float(r[0] << 16), q[0], acc[0]);
-    acc[1] = fmaf(__uint_as_float(r[0] & 0xFFFF0000u), q[1], acc[1]);
-    acc[2] = fmaf(__uint_as_float(r[1] << 16), q[2], acc[2]);
-    acc[3] = fmaf(__uint_as_float(r[1] & 0xFFFF0000u), q[3], acc[3]);
-  }
-};
-
-template <int MODE, int NV>
-struct ScanCfg {
-  using V = LaneVec<MODE>;
-  static constexpr uint32_t ROWB = NV * 32 * V::BYTES;  // bytes per (padded) row
-  static constexpr uint32_t U0 = kStageTarget / (kWarps * ROWB);
-  static constexpr uint32_t U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);  // rows per consumer warp per stage
-  static constexpr uint32_t RPS = kWarps * U;                   // rows per stage
-  static constexpr uint32_t STAGE_BYTES = RPS * ROWB;
-  static constexpr uint32_t S0 = kInFlight / STAGE_BYTES;
-  static constexpr uint32_t STAGES = S0 < 2 ? 2 : (S0 > 8 ? 8 : S0);
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + kCap * sizeof(ckey_t);
-};
-
-// SMALLK (k <= 32): every consumer warp keeps its own sorted top-32 in registers
-// (lane i holds the i-th best key); a row that beats the warp's k-th key is
-// inserted with one ballot and one shuffle.  No shared-memory traffic, no
-// barriers and no re-selection stalls while streaming.  Larger k use the
-// CTA-level shared-memory accumulator (TopK).
-template <int MODE, int NV, bool SMALLK>
-__global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams p) {
-  using Cfg = ScanCfg<MODE, NV>;
-  using V = LaneVec<MODE>;
-  constexpr int E = V::E;
-  constexpr int U = Cfg::U;
-  constexpr uint32_t kBurst = 1024;                       // max pushes per check interval
-  constexpr uint32_t kCheckEvery = kBurst / Cfg::RPS;     // tiles between checks
-  static_assert(kCheckEvery >= 1, "stage too large");
-  static_assert(kCap >= kMaxK + 2 * kBurst, "candidate buffer too small");
-
-  extern __shared__ __align__(128) uint8_t smem[];
-  ckey_t* s_buf = reinterpret_cast<ckey_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  __shared__ __align__(8) uint64_t s_full[Cfg::STAGES];
-  __shared__ __align__(8) uint64_t s_empty[Cfg::STAGES];
-  __shared__ uint64_t s_tile[Cfg::STAGES];  // which tile a stage holds (~0 = no more tiles)
-  __shared__ uint32_t s_cnt;
-  __shared__ ckey_t s_thr;
-  __shared__ uint32_t s_last;
-  __shared__ uint32_t s_pos[kMaxGrid];
-  __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
-
-  const uint32_t lane = threadIdx.x & 31;
-  const uint64_t n = p.n_rows;
-  const uint64_t tiles = (n + Cfg::RPS - 1) / Cfg::RPS;
-
-  if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], kWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (threadIdx.x < 32) {
-    // ===== producer warp: one lane streams row tiles into the ring =====
-    // Tiles are handed out dynamically (one global atomic per 24-32 KB tile, fetched
-    // one tile ahead so its latency hides behind the empty-slot wait): SMs that
-    // stream faster simply take more tiles, which removes the ~5% finish-time
-    // spread of a static round-robin split.
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      uint64_t tile = blockIdx.x;
-      uint64_t nxt = (uint64_t)atomicAdd(p.done + 1, 1u) + gridDim.x;
-      while (tile < tiles) {
-        mbar_wait(&s_empty[s], ph ^ 1);
-        const uint64_t row0 = tile * Cfg::RPS;
-        const uint64_t rows = (n - row0 < Cfg::RPS) ? (n - row0) : Cfg::RPS;
-        const uint32_t bytes = (uint32_t)(rows * Cfg::ROWB);
-        s_tile[s] = tile;
-        mbar_expect_tx(&s_full[s], bytes);
-        bulk_g2s(smem + (size_t)s * Cfg::STAGE_BYTES, p.rows + row0 * Cfg::ROWB, bytes, &s_full[s]);
-        tile = nxt;
-        nxt = (uint64_t)atomicAdd(p.done + 1, 1u) + gridDim.x;
-        if (++s == Cfg::STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      }
-      mbar_wait(&s_empty[s], ph ^ 1);
-      s_tile[s] = ~0ull;       // end-of-stream marker
-      mbar_arrive(&s_full[s]);
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  const uint32_t ctid = threadIdx.x - 32, warp = ctid >> 5;
-  TopK tk{s_buf, &s_cnt, &s_thr, kCap, Group{ctid, kConsumers, 1}, s_hist};
-  tk.init();
-  float q[NV * E];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int e = 0; e < E; ++e) q[v * E + e] = __ldg(p.query + (v * 32 + lane) * E + e);
-  tk.g.sync();
-  TRACE(0);
-
-  const uint32_t k = p.k;
-  ckey_t thr = 0;
-  ckey_t slot = 0, wthr = 0;  // SMALLK: this lane's entry of the warp's sorted list / its k-th key
-  uint32_t it = 0, s = 0, ph = 0;
-  for (;; ++it) {
-    mbar_wait(&s_full[s], ph);
-    const uint64_t tile = s_tile[s];
-    if (tile == ~0ull) break;
-    const uint8_t* st = smem + (size_t)s * Cfg::STAGE_BYTES + (size_t)(warp * U) * Cfg::ROWB +
-                        (size_t)lane * V::BYTES;
-    V d[U][NV];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int v = 0; v < NV; ++v) d[u][v].load(st + (size_t)u * Cfg::ROWB + (size_t)v * 32 * V::BYTES);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);  // rows are in registers: hand the stage back
-    if (++s == Cfg::STAGES) {
-      s = 0;
-      ph ^= 1;
-    }
-    const uint64_t row0 = tile * Cfg::RPS + (uint64_t)warp * U;
-    float sc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int v = 0; v < NV; ++v) d[u][v].fma(q + v * E, acc);
-      sc[u] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
-    float mine = sc[0];
-#pragma unroll
-    for (int u = 1; u < U; ++u)
-      if (lane == u) mine = sc[u];
-    ckey_t mykey = 0;
-    if (lane < U && row0 + lane < n) {
-      const uint64_t r = row0 + lane;
-      const uint32_t bits = __float_as_uint(mine);
-      bool ok = finite_bits(bits);
-      if (ok && p.bitset) ok = (__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u;
-      float sc = mine;
-      if (ok && (p.sig.pipeline || p.sig.d_ctype)) {
-        // Store::search_filtered on device: SQL-style type/language filter, then the
-        // score fold base = clamp(cos,0,1); max(base,0)*note_boost; *importance; >= threshold
-        // (candidate.rs:420-562) applied BEFORE the top-k, in the reference's op order.
-        const float base = p.sig.pipeline ? fminf(fmaxf(mine, 0.f), 1.f) : mine;
-        // cheap upper bound first: a row that cannot beat the current k-th key needs no loads
-        const float ub = p.sig.pipeline
-                             ? __fmul_rn(__fmul_rn(base, p.sig.max_note_boost), p.sig.max_importance)
-                             : mine;
-        ok = make_key(ub, 0u) > (SMALLK ? wthr : thr);
-        if (ok && p.sig.d_ctype) {
-          const uint32_t ct = __ldg(p.sig.d_ctype + r), lg = __ldg(p.sig.d_lang + r);
-          ok = ((p.sig.type_mask[ct >> 6] >> (ct & 63)) & 1ull) && ((p.sig.lang_mask[lg >> 6] >> (lg & 63)) & 1ull);
-        }
-        if (ok && p.sig.pipeline) {
-          sc = base;
-          if (p.sig.d_note_boost) sc = __fmul_rn(fmaxf(sc, 0.f), __ldg(p.sig.d_note_boost + r));
-          else sc = fmaxf(sc, 0.f);
-          if (p.sig.d_importance) sc = __fmul_rn(sc, __ldg(p.sig.d_importance + r));
-          ok = sc >= p.sig.threshold;
-        }
-      }
-      if (ok) mykey = make_key(sc, (uint32_t)r);
-    }
-    if (SMALLK) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const ckey_t key = __shfl_sync(0xffffffffu, mykey, u);
-        if (key > wthr) {  // warp-uniform
-          const uint32_t pos = __popc(__ballot_sync(0xffffffffu, slot > key));
-          const ckey_t up = __shfl_up_sync(0xffffffffu, slot, 1);
-          slot = lane < pos ? slot : (lane == pos ? key : up);
-          wthr = __shfl_sync(0xffffffffu, slot, k - 1);
-        }
-      }
-      continue;
-    }
-    if (mykey > thr) tk.push(mykey);
-    if ((it % kCheckEvery) == kCheckEvery - 1) {
-      // consumer 0's view of the count may miss pushes of this interval that
-      // are still in flight in other warps (< kBurst), hence the 2*kBurst.
-      bool need = false;
-      if (ctid == 0) {
-        uint32_t c = s_cnt;
-        need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
-      }
-      if (tk.g.any(need)) {
-        tk.template select<kCap / kConsumers>(k);
-        thr = s_thr;
-      }
-    }
-  }
-  TRACE(1);
-  if (SMALLK) {
-    // combine the 8 warp lists: rank sort of 256 keys straight into the partial list
-    s_buf[ctid] = (lane < k) ? slot : 0;
-    tk.g.sync();
-    const ckey_t mine = s_buf[ctid];
-    if (mine != 0) {
-      uint32_t rank = 0;
-      for (uint32_t j = 0; j < kConsumers; ++j) rank += (s_buf[j] > mine) ? 1u : 0u;
-      if (rank < k) {
-        p.partial[(size_t)blockIdx.x * kMaxK + rank] = mine;
-        atomicAdd(&s_cnt, 1u);
-      }
-    }
-    tk.g.sync();
-    TRACE(2);
-    if (ctid == 0) p.partial_cnt[blockIdx.x] = s_cnt;
-  } else {
-    tk.compact(k);
-    TRACE(2);
-    const uint32_t mycnt = s_cnt;
-    for (uint32_t i = ctid; i < mycnt; i += kConsumers)
-      p.partial[(size_t)blockIdx.x * kMaxK + i] = s_buf[i];
-    if (ctid == 0) p.partial_cnt[blockIdx.x] = mycnt;
-  }
-  __threadfence();
-  tk.g.sync();
-  if (ctid == 0) {
-    uint32_t ticket = atomicAdd(p.done, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  tk.g.sync();
-  TRACE(3);
-  if (!s_last) return;
-  __threadfence();
-  if (p.peer.world == 0) {
-    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, p.out_scores, p.out_rows, p.out_n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
-  } else {
-    // Row-sharded corpus: the shard's list goes into this rank's own mailbox
-    // block and, by plain stores over NVLink, into every peer's; one release flag per peer
-    // publishes it; then wait for the peers' lists and merge — the all-gather and the merge
-    // ride in the tail of the scan, no collective call and no extra launch.
-    const PeerBlock own = peer_block(p.peer, p.peer.rank, p.peer.rank);
-    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, own.scores, own.rows, own.n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
-    const uint32_t n = *tk.cnt;  // sorted keys are still in tk.buf[0..n)
-    for (uint32_t e = ctid; e < p.peer.world * k; e += kConsumers) {
-      const uint32_t g = e / k, i = e - g * k;
-      if (g == p.peer.rank || i >= n) continue;
-      const PeerBlock pb = peer_block(p.peer, g, p.peer.rank);
-      const ckey_t key = s_buf[i];
-      pb.scores[i] = key_score(key);
-      pb.rows[i] = p.row_base + key_row(key);
-    }
-    if (ctid < p.peer.world && ctid != p.peer.rank) peer_block(p.peer, ctid, p.peer.rank).n[0] = n;
-    peer_signal(p.peer, tk.g);
-    if (peer_wait(p.peer, tk.g)) peer_merge_query(p.peer, tk.g, 0, k, p.out_scores, p.out_rows, p.out_n);
-    else peer_emit_empty(tk.g, k, p.out_scores, p.out_rows, p.out_n);
-  }
-  TRACE(4);
-  if (p.host_flag) {
-    // the result went straight into host-mapped memory: make it visible system-wide, then
-    // publish the completion word the host is polling (saves the D2H copies and the
-    // driver's stream-sync wake-up on the latency path)
-    __threadfence_system();
-    tk.g.sync();
-    if (ctid == 0) *reinterpret_cast<volatile uint32_t*>(p.host_flag) = p.seq;
-  }
-  if (ctid == 0) {
-    p.done[0] = 0;
-    p.done[1] = 0;
-  }
-}
 
 bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
   if (dim == 0 || dim > 2048) return false;
@@ -464,35 +69,11 @@ bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
   return true;
 }
 
-template <int MODE, int NV>
-static cudaError_t launch_nv(const ScanParams& p, int num_sms, cudaStream_t st) {
-  using Cfg = ScanCfg<MODE, NV>;
-  uint64_t tiles = (p.n_rows + Cfg::RPS - 1) / Cfg::RPS;
-  int grid = (int)(tiles < (uint64_t)num_sms ? tiles : (uint64_t)num_sms);
-  if (grid > (int)kMaxGrid) grid = kMaxGrid;
-  auto kern = (p.k <= 32) ? scan_topk_kernel<MODE, NV, true> : scan_topk_kernel<MODE, NV, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Cfg::SMEM);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, Cfg::SMEM, st>>>(p);
-  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-  return cudaGetLastError();
-}
-
-template <int MODE>
-static cudaError_t launch_mode(const ScanParams& p, int nv, int num_sms, cudaStream_t st) {
-  switch (nv) {
-    case 1: return launch_nv<MODE, 1>(p, num_sms, st);
-    case 2: return launch_nv<MODE, 2>(p, num_sms, st);
-    case 3: return launch_nv<MODE, 3>(p, num_sms, st);
-    case 4: return launch_nv<MODE, 4>(p, num_sms, st);
-    case 6: return launch_nv<MODE, 6>(p, num_sms, st);
-    case 8: return launch_nv<MODE, 8>(p, num_sms, st);
-    case 12: return launch_nv<MODE, 12>(p, num_sms, st);
-    case 16: return launch_nv<MODE, 16>(p, num_sms, st);
-  }
-  return cudaErrorInvalidValue;
-}
+// one translation unit per (row mode, top-k variant): scan_v_*.cu
+#define CQS_DECL_VARIANT(name) cudaError_t name(const ScanParams& p, int nv, int num_sms, cudaStream_t st)
+CQS_DECL_VARIANT(launch_scan_m0_small); CQS_DECL_VARIANT(launch_scan_m0_large);
+CQS_DECL_VARIANT(launch_scan_m1_small); CQS_DECL_VARIANT(launch_scan_m1_large);
+CQS_DECL_VARIANT(launch_scan_m2_small); CQS_DECL_VARIANT(launch_scan_m2_large);
 
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) {
   if (a.n_rows == 0 || a.k == 0 || a.k > kMaxK || a.n_rows > 0xFFFFFFFFull)
@@ -516,10 +97,11 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.host_flag = a.d_host_flag;
   p.seq = a.seq;
   if (a.peer) p.peer = *a.peer;
+  const bool small = a.k <= 32;  // per-warp register lists; larger k: shared-memory accumulator
   switch (a.layout.mode) {
-    case 0: return launch_mode<0>(p, a.layout.nv, num_sms, st);
-    case 1: return launch_mode<1>(p, a.layout.nv, num_sms, st);
-    case 2: return launch_mode<2>(p, a.layout.nv, num_sms, st);
+    case 0: return small ? launch_scan_m0_small(p, a.layout.nv, num_sms, st) : launch_scan_m0_large(p, a.layout.nv, num_sms, st);
+    case 1: return small ? launch_scan_m1_small(p, a.layout.nv, num_sms, st) : launch_scan_m1_large(p, a.layout.nv, num_sms, st);
+    case 2: return small ? launch_scan_m2_small(p, a.layout.nv, num_sms, st) : launch_scan_m2_large(p, a.layout.nv, num_sms, st);
   }
   return cudaErrorInvalidValue;
 }

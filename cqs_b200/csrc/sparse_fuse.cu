@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
     if (step == blockIdx.x) SPTRACE(2);
   }
   SPTRACE(3);
-  tk.compact(k);
+  topk_finish<kSpCap / kSpThreads>(tk, k);
   SPTRACE(4);
   const uint32_t mycnt = s.cnt;
   for (uint32_t i = tid; i < mycnt; i += kSpThreads)
