@@ -14,7 +14,7 @@ for storage in ("f32", "bf16"):
         x /= x.norm(dim=1, keepdim=True)
         ix.append_device(x.data_ptr(), m)
     ix.finalize()
-ix.set_timing(True)
+    ix.set_timing(True)
     q = np.random.default_rng(0).standard_normal(768).astype(np.float32); q /= np.linalg.norm(q)
     for k in (1, 20, 100, 500, 1024):
         ts = []
