@@ -183,7 +183,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_bout_n); cudaFree(s.d_bflags); cudaFree(s.d_maxnorm);
   cudaFree(s.d_bm_scores); cudaFree(s.d_bm_rows); cudaFree(s.d_bm_n);
   cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+  free_sparse(s.sparse);
   if (s.h_query) cudaFreeHost(s.h_query);
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
@@ -458,8 +458,7 @@ int cqs_b200_reopen(cqs_b200_index* ix) {
   for (auto& s : ix->shards) {
     cudaSetDevice(s.device);
     cudaStreamSynchronize(s.stream);
-    cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
-    s.sparse = SparseDev();
+    free_sparse(s.sparse);
     cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
     s.d_ctype = s.d_lang = nullptr;
     s.d_note_boost = s.d_importance = nullptr;
@@ -1220,6 +1219,51 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
 
 // ---- sparse ------------------------------------------------------------------
 
+// Static block index over the longest posting lists (SparseDev): lists longer than 256 postings,
+// longest first, as many as fit in a budget of 3 bytes per posting (25 % of the postings' own
+// footprint).  The per-query bounds pass then only has to look at the short lists.
+static int sparse_build_block_index(cqs_b200_index* ix, Shard& s) {
+  SparseDev& sp = s.sparse;
+  const uint32_t vocab = sp.vocab;
+  const uint32_t stride = (uint32_t)((s.n_rows + kSparseDocsPerBlock - 1) / kSparseDocsPerBlock) + 1;
+  std::vector<uint64_t> tptr((size_t)vocab + 1);
+  CK(ix, cudaMemcpy(tptr.data(), sp.d_tptr, sizeof(uint64_t) * tptr.size(), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<uint64_t, uint32_t>> lens;  // (length, token)
+  for (uint32_t t = 0; t < vocab; ++t)
+    if (tptr[t + 1] - tptr[t] > 256) lens.push_back({tptr[t + 1] - tptr[t], t});
+  std::sort(lens.begin(), lens.end(), [](const auto& a, const auto& b) { return a.first > b.first || (a.first == b.first && a.second < b.second); });
+  const uint64_t budget = std::max<uint64_t>(16ull << 20, 3 * sp.nnz);
+  const uint64_t max_slots = budget / ((uint64_t)stride * sizeof(uint32_t));
+  const uint32_t n_slots = (uint32_t)std::min<uint64_t>(lens.size(), max_slots);
+  if (n_slots == 0) return CQS_B200_OK;
+  std::vector<int32_t> slot_of(vocab, -1);
+  std::vector<uint32_t> toks(n_slots);
+  for (uint32_t i = 0; i < n_slots; ++i) {
+    slot_of[lens[i].second] = (int32_t)i;
+    toks[i] = lens[i].second;
+  }
+  uint32_t* d_toks = nullptr;
+  cudaError_t e = cudaMalloc((void**)&sp.d_slot_of, sizeof(int32_t) * vocab);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&sp.d_block_index, sizeof(uint32_t) * (size_t)n_slots * stride);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_toks, sizeof(uint32_t) * n_slots);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sp.d_slot_of, slot_of.data(), sizeof(int32_t) * vocab, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_toks, toks.data(), sizeof(uint32_t) * n_slots, cudaMemcpyHostToDevice, s.stream);
+  sp.n_slots = n_slots;
+  sp.index_stride = stride;
+  for (uint32_t r0 = 0; e == cudaSuccess && r0 < n_slots; r0 += 1024)
+    e = launch_sparse_block_index(sp, d_toks + r0, std::min<uint32_t>(1024, n_slots - r0), r0, s.n_rows, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cudaFree(d_toks);
+  if (e != cudaSuccess) {
+    // the index is an accelerator only: drop it and keep the postings usable
+    cudaGetLastError();
+    cudaFree(sp.d_slot_of); cudaFree(sp.d_block_index);
+    sp.d_slot_of = nullptr; sp.d_block_index = nullptr; sp.n_slots = 0; sp.index_stride = 0;
+    if (e != cudaErrorMemoryAllocation) CK(ix, e);
+  }
+  return CQS_B200_OK;
+}
+
 // Build the token-major postings from a doc-major CSR that already sits on the device
 // (SpladeIndex::build, src/splade/index.rs:177-221, as a stable counting sort — sparse_build.cu).
 static int sparse_build_on_device(cqs_b200_index* ix, Shard& s, const uint64_t* d_indptr, const uint32_t* d_tok,
@@ -1261,11 +1305,11 @@ static int sparse_build_on_device(cqs_b200_index* ix, Shard& s, const uint64_t* 
     return fail(CQS_B200_ERR_INVALID, err == 1 ? "a token id is >= vocab %u" : "a doc lists a token twice (vocab %u)", vocab);
   }
   cleanup();
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+  free_sparse(s.sparse);
   sp.vocab = vocab;
   sp.nnz = nnz;
   s.sparse = sp;
-  return CQS_B200_OK;
+  return sparse_build_block_index(ix, s);
 }
 
 int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
@@ -1426,11 +1470,11 @@ int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected
     cudaFree(sp.d_tptr); cudaFree(sp.d_doc); cudaFree(sp.d_post);
     CK(ix, e);
   }
-  cudaFree(s.sparse.d_tptr); cudaFree(s.sparse.d_doc); cudaFree(s.sparse.d_post);
+  free_sparse(s.sparse);
   sp.vocab = h.vocab;
   sp.nnz = h.nnz;
   s.sparse = sp;
-  return CQS_B200_OK;
+  return sparse_build_block_index(ix, s);
 }
 
 // test hook: download the built postings (tptr [vocab+1], doc [nnz], weight [nnz])

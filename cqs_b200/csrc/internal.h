@@ -121,7 +121,19 @@ struct SparseDev {
   void* d_post = nullptr;       // [nnz] (doc, weight bits) pairs (accumulate pass)
   uint32_t vocab = 0;
   uint64_t nnz = 0;
+  // Static block index (built once at attach / load): for the longest posting lists, where every
+  // 256-doc block starts inside the list — what the per-query bounds pass would otherwise find by
+  // streaming the list's doc ids.  slot_of[token] = row of the table or -1.
+  int32_t* d_slot_of = nullptr;     // [vocab]
+  uint32_t* d_block_index = nullptr;  // [n_slots][index_stride]
+  uint32_t n_slots = 0;
+  uint32_t index_stride = 0;        // n_blocks + 1 at build time
 };
+void free_sparse(SparseDev& sp);
+// Builds the static block index for `n_tok` tokens (`d_tokens`, <= 1024 per call) into rows
+// [row0, row0 + n_tok) of sp.d_block_index.
+cudaError_t launch_sparse_block_index(const SparseDev& sp, const uint32_t* d_tokens, uint32_t n_tok,
+                                      uint32_t row0, uint64_t n_docs, cudaStream_t stream);
 struct SparseArgs {
   SparseDev sp;
   uint64_t n_docs;

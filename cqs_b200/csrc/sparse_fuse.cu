@@ -48,6 +48,7 @@ struct BoundsParams {
   uint32_t q_nnz;
   uint32_t n_blocks;
   uint32_t* bounds;  // [q_nnz][n_blocks + 1]
+  const int32_t* slot_of;  // nullable: tokens with slot_of[t] >= 0 have a static row and are skipped
 };
 constexpr uint32_t kBoundsChunk = 8192;  // postings per streaming work unit
 constexpr uint32_t kBoundsShort = 256;   // lists up to this long are binary-searched per block instead
@@ -60,7 +61,10 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
     uint64_t b0 = 0, b1 = 0;
-    if (t < p.vocab) { b0 = __ldg(p.tptr + t); b1 = __ldg(p.tptr + t + 1); }
+    if (t < p.vocab && !(p.slot_of && __ldg(p.slot_of + t) >= 0)) {
+      b0 = __ldg(p.tptr + t);
+      b1 = __ldg(p.tptr + t + 1);
+    }
     const uint64_t len = b1 - b0;
     s_base[i] = b0;
     s_len[i] = (uint32_t)len;
@@ -149,6 +153,8 @@ struct SparseParams {
   uint32_t q_nnz;
   const uint32_t* bounds;
   uint32_t n_blocks;
+  const int32_t* slot_of;        // nullable: static block index (see SparseDev)
+  const uint32_t* block_index;
   const uint32_t* bitset;
   uint32_t k;
   uint64_t row_base;
@@ -167,6 +173,7 @@ struct SpSmem {
   float acc[kSpWarps][kSpBlock];         //  4 KB
   uint8_t touched[kSpWarps][kSpBlock];   //  1 KB
   uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
+  const uint32_t* brow[kSpMaxQ];         //  8 KB  its block-boundary row (static index or this query's bounds)
   float qw[kSpMaxQ];                     //  4 KB
   uint32_t pos[kMaxGrid];                //  4 KB
   uint32_t hist[kSelBuckets + 96];       //  8 KB  select() histogram
@@ -191,15 +198,17 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}, s.hist};
   tk.init();
+  const uint32_t stride = p.n_blocks + 1;
   for (uint32_t i = tid; i < p.q_nnz; i += kSpThreads) {
     const uint32_t t = __ldg(p.q_tok + i);
     s.base[i] = (t < p.vocab) ? __ldg(p.tptr + t) : 0;
     s.qw[i] = __ldg(p.q_w + i);
+    const int32_t slot = (p.slot_of && t < p.vocab) ? __ldg(p.slot_of + t) : -1;
+    s.brow[i] = slot >= 0 ? p.block_index + (size_t)slot * stride : p.bounds + (size_t)i * stride;
   }
   __syncthreads();
   SPTRACE(0);
   const uint32_t k = p.k;
-  const uint32_t stride = p.n_blocks + 1;
   const uint32_t n_steps = (p.n_blocks + kSpWarps - 1) / kSpWarps;
   float* acc = s.acc[warp];
   uint8_t* touched = s.touched[warp];
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
         // slice [lo, hi) of 32 query tokens at once (one token per lane)
         uint32_t lo = 0, hi = 0;
         if (i0 + lane < p.q_nnz) {
-          const uint32_t* row = p.bounds + (size_t)(i0 + lane) * stride + blk;
+          const uint32_t* row = s.brow[i0 + lane] + blk;
           lo = __ldg(row);
           hi = __ldg(row + 1);
         }
@@ -310,12 +319,17 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = cudaMemsetAsync(a.d_bounds, 0, sparse_bounds_bytes(a.n_docs, a.q_nnz), st);
   if (e != cudaSuccess) return e;
-  BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds};
+  // the static block index only applies while the corpus still has the block count it was built for
+  const bool use_index = a.sp.d_slot_of && a.sp.d_block_index && a.sp.index_stride == n_blocks + 1;
+  BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds,
+                  use_index ? a.sp.d_slot_of : nullptr};
   sparse_bounds_kernel<<<sms * 6, 256, 0, st>>>(bp);
   SparseParams p;
   p.tptr = a.sp.d_tptr; p.post = (const uint2*)a.sp.d_post; p.vocab = a.sp.vocab;
   p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
   p.bounds = a.d_bounds; p.n_blocks = n_blocks;
+  p.slot_of = use_index ? a.sp.d_slot_of : nullptr;
+  p.block_index = use_index ? a.sp.d_block_index : nullptr;
   p.bitset = a.d_bitset; p.k = a.k; p.row_base = a.row_base;
   p.partial = a.d_partial; p.partial_cnt = a.d_partial_cnt; p.done = a.d_done;
   p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
@@ -328,6 +342,31 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   if (e != cudaSuccess) return e;
   sparse_search_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
   g_kernel_launches.fetch_add(2, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+void free_sparse(SparseDev& sp) {
+  cudaFree(sp.d_tptr); cudaFree(sp.d_doc); cudaFree(sp.d_post);
+  cudaFree(sp.d_slot_of); cudaFree(sp.d_block_index);
+  sp = SparseDev();
+}
+
+// The static block index is the bounds pass run once, at build time, over the longest lists.
+cudaError_t launch_sparse_block_index(const SparseDev& sp, const uint32_t* d_tokens, uint32_t n_tok,
+                                      uint32_t row0, uint64_t n_docs, cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  if (n_tok > kSpMaxQ || !sp.d_block_index) return cudaErrorInvalidValue;
+  const uint32_t n_blocks = (uint32_t)((n_docs + kSpBlock - 1) / kSpBlock);
+  if (sp.index_stride != n_blocks + 1) return cudaErrorInvalidValue;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint32_t* rows = sp.d_block_index + (size_t)row0 * sp.index_stride;
+  cudaError_t e = cudaMemsetAsync(rows, 0, (size_t)n_tok * sp.index_stride * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  BoundsParams bp{sp.d_tptr, sp.d_doc, sp.vocab, d_tokens, n_tok, n_blocks, rows, nullptr};
+  sparse_bounds_kernel<<<sms * 6, 256, 0, st>>>(bp);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 

@@ -347,3 +347,29 @@ def test_sparse_persistence_generation_and_checksum(cqs, tmp_path):
     got = ix2.search_sparse_rows(qt, qw, 50)                            # a refused load leaves the old index in place
     assert np.array_equal(got[0], want[0])
     ix2.close()
+
+
+@pytest.mark.parametrize("n_docs,vocab,mean_nnz", [(40_000, 30522, 60), (70_001, 600, 25)])
+def test_sparse_search_with_static_block_index_vs_oracle(cqs, n_docs, vocab, mean_nnz):
+    """Long posting lists take their block boundaries from the static index built at attach time,
+    short ones from the per-query bounds pass; the scores stay bit-exact and the order identical."""
+    rng = np.random.default_rng(n_docs)
+    indptr, tok, w = _zipf_csr(rng, n_docs, vocab, mean_nnz)
+    ix = cqs.B200Index(8)
+    ix.append(None, O.fast_unit_rows(n_docs, 8, seed=1)); ix.finalize()
+    ix.sparse_attach(indptr, tok, w, vocab)
+    for trial in range(6):
+        qn = int(rng.integers(1, 64))
+        head = rng.choice(min(vocab, 40), size=min(qn, 8), replace=False)           # the heaviest tokens
+        tail = rng.choice(vocab, size=qn, replace=False)
+        qt = np.unique(np.concatenate([head, tail]))[:64].astype(np.uint32)
+        rng.shuffle(qt)                                                               # query order matters for f32 sums
+        qw = (rng.random(qt.shape[0]) + 0.05).astype(f32)
+        mask = rng.random(n_docs) > 0.5 if trial % 2 else None
+        bs = None if mask is None else O.mask_to_bitset(mask)
+        for k in (20, 500):
+            o_rows, o_sc = O.sparse_search_csr(indptr, tok, w, qt, qw, n_docs, k, mask)
+            g_rows, g_sc = ix.search_sparse_rows(qt, qw, k, bs)
+            assert g_rows.astype(np.int64).tolist() == o_rows.tolist()
+            assert np.array_equal(bits(g_sc), bits(o_sc))
+    ix.close()
