@@ -848,6 +848,21 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   return release_scratch(ix, scr, st);
 }
 
+// Device buffers of the batch entry points, allocated on first use (each one on its own: the
+// exact path and the tensor-core path share the query and result buffers).
+static int ensure_batch_buffers(cqs_b200_index* ix, Shard& s, bool tensor_path) {
+  const uint32_t ld = ix->layout.ld;
+  if (!s.d_bq) CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
+  if (!s.d_bout_scores) CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+  if (!s.d_bout_rows) CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+  if (!s.d_bout_n) CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
+  if (tensor_path) {
+    if (!s.d_bscratch) CK(ix, cudaMalloc(&s.d_bscratch, batch_scratch_bytes(kBatchMaxQ, ld)));
+    if (!s.d_bflags) CK(ix, cudaMalloc((void**)&s.d_bflags, sizeof(uint32_t) * kBatchMaxQ));
+  }
+  return 0;
+}
+
 // nq single-query scans, one launch each, issued round-robin on kLanes lanes (`st` and the
 // shard's own lane streams) so the tail of launch i — list merge and, with `peer`, the
 // cross-shard exchange — overlaps the streaming phase of the following launches.  Everything stays on
@@ -942,12 +957,7 @@ static int search_batch_exact(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   Shard& s = ix->shards[0];
   CK(ix, cudaSetDevice(s.device));
   const uint32_t ld = ix->layout.ld;
-  if (!s.d_bq) CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
-  if (!s.d_bout_scores) {
-    CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
-  }
+  if (int rcb = ensure_batch_buffers(ix, s, /*tensor_path=*/false)) return rcb;
   std::vector<float> padded((size_t)nq * ld, 0.f);
   std::vector<uint8_t> bad(nq, 0);
   for (uint32_t i = 0; i < nq; ++i) {
@@ -1026,14 +1036,7 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   Shard& s = ix->shards[0];
   CK(ix, cudaSetDevice(s.device));
   const uint32_t ld = ix->layout.ld;
-  if (!s.d_bq) {
-    CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
-    CK(ix, cudaMalloc(&s.d_bscratch, batch_scratch_bytes(kBatchMaxQ, ld)));
-    CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
-    CK(ix, cudaMalloc((void**)&s.d_bflags, sizeof(uint32_t) * kBatchMaxQ));
-  }
+  if (int rcb = ensure_batch_buffers(ix, s, /*tensor_path=*/true)) return rcb;
   // pad queries to the row stride; a non-finite query yields an empty result
   // (src/cagra.rs:458-470): it is scanned as a zero vector and blanked afterwards
   std::vector<float> padded((size_t)nq * ld, 0.f);

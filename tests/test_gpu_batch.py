@@ -148,3 +148,23 @@ def test_bf16_f32_storage_is_exact_f32_and_recall(cqs):
     assert_topk_parity(r_m[3], s_m[3], o_rows, o_sc, full)
     for ix in (ix32, ixm, ix16):
         ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first", ["exact", "tensor"])
+def test_exact_and_tensor_batch_paths_share_one_index(first):
+    """A small batch (< 8 queries: pipelined exact scans) and a large one (tensor cores) on the same
+    bf16 index, in either order: both allocate their device buffers lazily and share some of them."""
+    import cqs_b200
+    n, dim, k = 6000, 768, 20
+    rows = O.fast_unit_rows(n, dim, seed=5)
+    ix = cqs_b200.B200Index(dim, storage="bf16")
+    ix.append(None, rows); ix.finalize()
+    small = O.fast_unit_rows(5, dim, seed=6)
+    big = O.fast_unit_rows(24, dim, seed=7)
+    for qs in ((small, big) if first == "exact" else (big, small)):
+        r, s, nn = ix.search_batch_rows(qs, k)
+        for i in range(qs.shape[0]):
+            a, b = ix.search_rows(qs[i], k)
+            assert int(nn[i]) == k and np.array_equal(r[i], a) and np.array_equal(s[i].view(np.uint32), b.view(np.uint32))
+    ix.close()
