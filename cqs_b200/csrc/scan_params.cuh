@@ -26,6 +26,9 @@ struct ScanParams {
   ScanSignals sig;            // structured filter + per-row signals (sig.pipeline / sig.d_ctype gate them)
   uint32_t* host_flag;        // optional: host-mapped word that receives `seq` once the result is written
   uint32_t seq;
+  uint32_t chunk = 1;         // tiles per big work unit (filled in by the launcher)
+  uint64_t n_big = 0;         // number of big work units; the remaining tiles are handed out one by one
+  uint32_t chunk_override = 0;  // development aid: CQS_B200_CHUNK
   PeerCtx peer;               // peer.world != 0: exchange the local list with the other shards and emit the GLOBAL top-k
 };
 

@@ -36,6 +36,7 @@
 //     part of the reference's scoring fold run inside the same loop, before
 //     the top-k (Store::search_filtered semantics).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "internal.h"
@@ -97,6 +98,8 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.host_flag = a.d_host_flag;
   p.seq = a.seq;
   if (a.peer) p.peer = *a.peer;
+  static const uint32_t chunk_env = getenv("CQS_B200_CHUNK") ? (uint32_t)atoi(getenv("CQS_B200_CHUNK")) : 0;
+  p.chunk_override = chunk_env;
   const bool small = a.k <= 32;  // per-warp register lists; larger k: shared-memory accumulator
   switch (a.layout.mode) {
     case 0: return small ? launch_scan_m0_small(p, a.layout.nv, num_sms, st) : launch_scan_m0_large(p, a.layout.nv, num_sms, st);
