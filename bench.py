@@ -467,6 +467,8 @@ def main():
     pb_rows, pb_sc, pb_n = (b_rows.ctypes.data_as(C.c_void_p), b_sc.ctypes.data_as(C.c_void_p),
                             b_n.ctypes.data_as(C.c_void_p))
 
+    batch_call = args.storage == "f32"
+
     def step_e2e(s: int):
         """One public batch call per step: Q host queries in, Q host top-k lists out (H2D of the
         queries, Q scan launches, D2H of the results, all inside the call)."""
@@ -479,6 +481,15 @@ def main():
             h_pin.copy_(m_sc, non_blocking=True)
             h_pin_r.copy_(m_rw, non_blocking=True)
             torch.cuda.synchronize()
+        elif not batch_call:
+            # bf16 storage: a batch call would switch to the tensor-core algorithm, which is a different
+            # workload (configs[2]); stay with one blocking single-query call per query
+            for i in range(Q):
+                qi = C.c_void_p(q_base + (base + i) * DIM * 4)
+                if pg is not None:
+                    check(search_sh(ix._h, pg._h, qi, K, None, p_rows, p_sc, p_n))
+                else:
+                    check(search(ix._h, qi, K, None, p_rows, p_sc, p_n))
         elif pg is not None:
             check(lib.cqs_b200_search_batch_sharded(ix._h, pg._h, qp, Q, K, None, pb_rows, pb_sc, pb_n))
         else:
@@ -549,8 +560,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
                     "d2h_bytes_per_step": Q * K * 12 + (Q * 4 if (world == 1 or pg is not None) else 0)},
             "gpu_launches": int(launches),
-            "e2e_call": ("cqs_b200_search_batch" if world == 1 else "cqs_b200_search_batch_sharded" if pg is not None
-                         else "search_device + all_gather + merge") + f", one call per step of {Q} queries",
+            "e2e_call": (("cqs_b200_search_batch" if world == 1 else "cqs_b200_search_batch_sharded" if pg is not None
+                          else "search_device + all_gather + merge") + f", one call per step of {Q} queries")
+                        if (batch_call or (world > 1 and pg is None)) else
+                        (("cqs_b200_search" if world == 1 else "cqs_b200_search_sharded") + ", one blocking call per query"),
             "p50_ms_single_query_call": float(np.median(lat) * 1e3) if lat else None,
             "p95_ms_single_query_call": float(np.percentile(lat, 95) * 1e3) if lat else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
