@@ -878,15 +878,15 @@ static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, 
   lanes[0] = st;
   for (uint32_t l = 1; l < kLanes; ++l) lanes[l] = s.lane_stream[l - 1];
   bool forked[kLanes] = {};
-  bool fork_recorded = false;
+  // fork point = everything already queued on `st` (the queries' upload); recorded BEFORE the
+  // first launch so that the other lanes do not wait for lane 0's first kernel
+  if (nq > 1) CK(ix, cudaEventRecord(s.ev_fork, st));
   uint32_t li = 0;
   for (uint32_t i = 0; i < nq; ++i) {
     if (skip && skip[i]) continue;
     const uint32_t l = li % kLanes;
     cudaStream_t ln = lanes[l];
     if (l && !forked[l]) {
-      if (!fork_recorded) CK(ix, cudaEventRecord(s.ev_fork, st));
-      fork_recorded = true;
       CK(ix, cudaStreamWaitEvent(ln, s.ev_fork, 0));
       forked[l] = true;
     }
