@@ -10,6 +10,7 @@
 // Header-only; link with libcqs_b200.so.  No arithmetic happens here.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -73,6 +74,40 @@ inline size_t cap_k_to_backend(const VectorIndex& idx, size_t k) {  // src/searc
   auto cap = idx.max_k();
   return (cap && k > *cap) ? *cap : k;
 }
+
+// A rank's handle on the peer-memory exchange of a row-sharded corpus (include/cqs_b200.h, "row-sharded
+// corpora WITHOUT a collective call").  One process per GPU: create(), send handle() to the other ranks over
+// any channel, connect() with all handles in rank order.
+class PeerGroup {
+ public:
+  static std::unique_ptr<PeerGroup> create(int device, uint32_t world, uint32_t rank, uint32_t max_elems = 0) {
+    std::unique_ptr<PeerGroup> g(new PeerGroup());
+    if (cqs_b200_peer_create(device, world, rank, max_elems, &g->h_) != CQS_B200_OK) return nullptr;
+    g->world_ = world;
+    return g;
+  }
+  ~PeerGroup() { cqs_b200_peer_destroy(h_); }
+  PeerGroup(const PeerGroup&) = delete;
+  PeerGroup& operator=(const PeerGroup&) = delete;
+  std::array<uint8_t, CQS_B200_PEER_HANDLE_BYTES> handle() const {
+    std::array<uint8_t, CQS_B200_PEER_HANDLE_BYTES> h{};
+    cqs_b200_peer_handle(h_, h.data());
+    return h;
+  }
+  bool connect(const std::vector<std::array<uint8_t, CQS_B200_PEER_HANDLE_BYTES>>& all) {
+    if (all.size() != world_) return false;
+    std::vector<uint8_t> flat;
+    for (auto& h : all) flat.insert(flat.end(), h.begin(), h.end());
+    return cqs_b200_peer_connect(h_, flat.data()) == CQS_B200_OK;
+  }
+  bool healthy() const { return cqs_b200_peer_status(h_) == 0; }
+  cqs_b200_peer* raw() const { return h_; }
+
+ private:
+  PeerGroup() = default;
+  cqs_b200_peer* h_ = nullptr;
+  uint32_t world_ = 0;
+};
 
 class B200Index final : public VectorIndex {
  public:
@@ -153,6 +188,22 @@ class B200Index final : public VectorIndex {
       return out;
     }
     for (size_t i = 0; i < queries.size(); ++i) out[i] = to_results(rows.data() + i * k, scores.data() + i * k, n[i]);
+    return out;
+  }
+
+  // This index holds ONE shard of a row-sharded corpus (cqs_b200_set_row_base): VectorIndex::search over
+  // the whole corpus.  Every rank must make the same call; each gets the global top-k as (global row,
+  // score) — the chunk-id strings of other shards live with their owners, so rows are returned as they are.
+  std::vector<std::pair<uint64_t, float>> search_sharded_rows(const PeerGroup& peer, const Embedding& query, size_t k) const {
+    std::vector<std::pair<uint64_t, float>> out;
+    if (k == 0 || k > CQS_B200_MAX_K || query.size() != dim_ || is_poisoned()) return out;
+    std::vector<uint64_t> rows(k); std::vector<float> scores(k); uint32_t n = 0;
+    if (cqs_b200_search_sharded(h_, peer.raw(), query.data(), (uint32_t)k, nullptr, rows.data(), scores.data(), &n) != CQS_B200_OK) {
+      log_error("search_sharded");
+      return out;
+    }
+    for (uint32_t i = 0; i < n; ++i)
+      if (std::isfinite(scores[i])) out.push_back({rows[i], scores[i]});
     return out;
   }
 
