@@ -367,15 +367,21 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
-    P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
     diag_no_exchange = world > 1 and args.transport == "none"   # diagnostic only: shards scanned, lists never merged
     d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
     d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
     d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
     pg = None
+    transport_note = None
     if world > 1 and args.transport == "peer":
         from cqs_b200.sharded import PeerGroup
-        pg = PeerGroup.from_dist(dist, local)   # CUDA IPC mailboxes; handles swapped over the process group
+        # CUDA IPC mailboxes; handles swapped over the process group.  If any rank cannot set them up
+        # (no peer access / IPC in this container) every rank falls back to the all-gather transport.
+        pg = PeerGroup.from_dist(dist, local, strict=False)
+        if pg is None:
+            args.transport = "nccl"
+            transport_note = "peer-memory setup failed on this box; fell back to all_gather_into_tensor + merge kernel"
+    P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
     if world > 1:
         g_sc = torch.empty((world, Q, K), dtype=torch.float32, device=dev)
         g_rw = torch.empty((world, Q, K), dtype=torch.int64, device=dev)
@@ -549,6 +555,7 @@ def main():
                                    f"(BASELINE configs[1]), row-sharded over {world} GPU(s)",
                        "queries_per_step": Q, "rows_per_gpu": n_local,
                        "launch_lanes": P, "per_rank_ms_timed_region": per_rank_ms,
+                       **({"transport_note": transport_note} if transport_note else {}),
                        **({"DIAGNOSTIC": "transport none: per-shard lists are never merged; not a search result"}
                           if diag_no_exchange else {}),
                        "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",

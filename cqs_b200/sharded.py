@@ -69,13 +69,42 @@ class PeerGroup:
         check(lib.cqs_b200_peer_connect_local(arr, len(groups)))
 
     @classmethod
-    def from_dist(cls, dist, device: int, max_elems: int = 0) -> "PeerGroup":
-        """One process per GPU under torch.distributed: create, swap handles, connect."""
-        g = cls(device, dist.get_world_size(), dist.get_rank(), max_elems)
-        if g.world > 1:
-            handles = [None] * g.world
+    def from_dist(cls, dist, device: int, max_elems: int = 0, strict: bool = True) -> Optional["PeerGroup"]:
+        """One process per GPU under torch.distributed: create, swap handles, connect.
+
+        Every step is followed by an agreement (an all-gather of per-rank success) so that a failure on
+        one rank — no peer access, CUDA IPC unavailable in the container — never leaves the others stuck
+        in a collective.  strict: raise on failure; otherwise return None on EVERY rank (the caller
+        falls back to the all-gather transport)."""
+        world = dist.get_world_size()
+
+        def agree(ok: bool, why: str):
+            flags = [None] * world
+            dist.all_gather_object(flags, (bool(ok), why))
+            bad = [f"rank {r}: {w}" for r, (o, w) in enumerate(flags) if not o]
+            return (not bad), "; ".join(bad)
+
+        g, why = None, ""
+        try:
+            g = cls(device, world, dist.get_rank(), max_elems)
+        except Exception as e:  # noqa: BLE001 - reported to all ranks
+            why = repr(e)
+        ok, msg = agree(g is not None, why)
+        if ok and world > 1:
+            handles = [None] * world
             dist.all_gather_object(handles, g.handle())
-            g.connect(handles)
+            why = ""
+            try:
+                g.connect(handles)
+            except Exception as e:  # noqa: BLE001
+                why = repr(e)
+            ok, msg = agree(not why, why)
+        if not ok:
+            if g is not None:
+                g.close()
+            if strict:
+                raise RuntimeError("peer group setup failed: " + msg)
+            return None
         return g
 
     def set_timeout_ms(self, ms: int) -> None:

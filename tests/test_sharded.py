@@ -274,3 +274,39 @@ def test_exact_batch_is_pipelined_single_queries(dim, storage):
         assert d_rw[i].cpu().numpy().view(np.uint64).tolist() == a.tolist()
         assert np.array_equal(d_sc[i].cpu().numpy().view(np.uint32), b.view(np.uint32))
     ix.close()
+
+
+def _peer_setup_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from cqs_b200.sharded import PeerGroup
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # no CUDA device here: creating the mailbox fails on every rank; the ranks must AGREE on the failure
+    # (no rank may be left waiting in the handle exchange) and report it the way the caller asked
+    res = PeerGroup.from_dist(dist, 0, strict=False)
+    raised = False
+    try:
+        PeerGroup.from_dist(dist, 0, strict=True)
+    except RuntimeError as e:
+        raised = "peer group setup failed" in str(e) and "rank 0" in str(e) and "rank 1" in str(e)
+    out[rank] = (res is None) and raised
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_peer_setup_failure_is_agreed_not_hung():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA (the failure path)")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_peer_setup_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
