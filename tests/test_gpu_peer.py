@@ -340,3 +340,57 @@ def test_two_gpus_sharded_hybrid_equals_unsharded():
         assert groups[g].status() == 0
         groups[g].close(); shards[g].close()
     whole.close()
+
+
+def test_two_gpus_sharded_batch_with_exact_fallback():
+    """Near-duplicate rows inside one shard: that shard's tensor-core candidate pool cannot be proven
+    complete for the matching queries, they are re-run through the exact scan and patched into the
+    shard's lists BEFORE the exchange; the merged result must still equal the unsharded exact answer."""
+    _need_gpus(2)
+    import ctypes as C
+    import cqs_b200
+    from cqs_b200.capi import lib
+    from cqs_b200.sharded import PeerGroup, shard_range, search_batch_sharded
+    G = 2
+    rng = np.random.default_rng(5)
+    n, dim, k = 80_000, 768, 20
+    rows = O.fast_unit_rows(n, dim, seed=41)
+    base = rows[7].copy()
+    for j in range(300):                                   # all inside shard 0 (rows < 40,000)
+        v = base + rng.standard_normal(dim).astype(f32) * f32(2e-5)
+        rows[100 + j * 100] = v / np.linalg.norm(v)
+    q = O.fast_unit_rows(32, dim, seed=42)
+    q[0] = base
+    q[1] = rows[100]
+    whole = cqs_b200.B200Index(dim, storage="bf16", devices=[0])
+    whole.append(None, rows); whole.finalize()
+    shards, groups = [], []
+    for g in range(G):
+        row0, nl = shard_range(n, G, g)
+        ix = cqs_b200.B200Index(dim, storage="bf16", devices=[g], row_base=row0)
+        ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        shards.append(ix); groups.append(PeerGroup(g, G, g))
+    PeerGroup.connect_local(groups)
+    res = [None] * G
+
+    def run(g):
+        res[g] = search_batch_sharded(shards[g], groups[g], q, k)
+
+    th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    lib.cqs_b200_debug_batch_reruns.restype = C.c_uint32
+    lib.cqs_b200_debug_batch_reruns.argtypes = [C.c_void_p]
+    assert lib.cqs_b200_debug_batch_reruns(shards[0]._h) >= 1      # the fallback really ran on shard 0
+    for qi in range(32):
+        a, b = whole.search_rows(q[qi], k)
+        for g in range(G):
+            r, s, nn = res[g]
+            assert int(nn[qi]) == k and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32)), (qi, g)
+    for g in range(G):
+        assert groups[g].status() == 0
+        groups[g].close(); shards[g].close()
+    whole.close()
