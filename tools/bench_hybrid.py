@@ -67,3 +67,11 @@ qt, qw = sparse_query()
 print(f"hybrid pool-500 e2e p50 {np.median(lat_h[5:])*1e3:.3f} ms | dense-500 alone {np.median(lat_d[5:])*1e3:.3f} ms | "
       f"sparse-500 alone {np.median(lat_s[5:])*1e3:.3f} ms (kernel {ks*1e3:.0f} us; query touches ~{post[qt].sum()*8/1e6:.1f} MB of postings)")
 print("rows returned:", r["rows"].shape[0], "in both legs:", int((r["present"] == 3).sum()))
+# CPU baseline of the sparse leg + fusion on the host cores (bounded sample: the first 300k docs)
+from tools.cpu_sparse_baseline import time_cpu_sparse
+ns = min(n, 300_000)
+e_end = int(indptr[ns])
+cpu = time_cpu_sparse(indptr[:ns + 1], tok[:e_end], w[:e_end], vocab, [sparse_query() for _ in range(8)], 500,
+                      [(int(a), float(b)) for a, b in zip(*ix.search_rows(q, 500))])
+print(f"CPU port, first {ns} docs ({e_end/1e6:.1f}M postings): index build {cpu['build_s']:.1f} s, sparse leg p50 "
+      f"{cpu['sparse_ms_p50']:.2f} ms on 1 core, fusion (numpy restatement) {cpu['fuse_ms']:.2f} ms")
