@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,15 @@ static int fail(int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   t_last_error = buf;
+  return code;
+}
+
+// t_last_error itself may be what failed to allocate: fall back to a static message
+static int api_exception(int code, const char* msg) noexcept {
+  try {
+    t_last_error = msg;
+  } catch (...) {
+  }
   return code;
 }
 
@@ -104,6 +114,7 @@ struct Shard {
   uint8_t* d_hout = nullptr;    // device alias of h_out
   uint32_t seq = 0;             // completion sequence number of the latency path
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;  // whole batch pipeline (cqs_b200_set_timing)
   unsigned long long* d_trace = nullptr;  // development aid (CQS_B200_TRACE=1)
   // batched tensor-core path (bf16 storage), allocated on first use
   float* d_bq = nullptr;          // [kBatchMaxQ][ld] padded f32 queries
@@ -143,10 +154,25 @@ struct cqs_b200_index {
   float last_kernel_ms = 0.f;
   bool timing = false;   // record CUDA events around the dominant kernel (cqs_b200_set_timing)
   float max_note_boost = 1.f, max_importance = 1.f;
-  uint32_t last_batch_reruns = 0;  // queries the batched path sent to the exact kernel (cumulative)
-  float last_batch_ms = 0.f;       // device time of the most recent tensor-core batch pipeline
+  uint32_t batch_reruns_total = 0;  // queries the batched path sent to the exact kernel (cumulative)
+  uint32_t last_batch_reruns = 0;   // ... by the most recent batch call
+  // Device time of the most recent tensor-core batch call, CUDA events on the shard's stream from
+  // "queries resident" to "last kernel done": candidate scan + rescoring + the exact re-runs of
+  // unproven queries + (sharded) the gather/merge exchange, summed over the call's <= 1024-query chunks.
+  float last_batch_ms = 0.f;
   std::vector<Shard> shards;
 };
+
+// Every extern "C" entry point is a function-try-block closed by API_CATCH: a host allocation
+// failure (std::vector / std::string) or any other C++ exception becomes an error code instead
+// of unwinding through the C ABI into the Rust caller ("never throws, never aborts").
+#define API_CATCH                                                                          \
+  catch (const std::bad_alloc&) {                                                          \
+    return api_exception(CQS_B200_ERR_OOM, "host allocation failed");                      \
+  }                                                                                        \
+  catch (...) {                                                                            \
+    return api_exception(CQS_B200_ERR_INVALID, "unexpected C++ exception");                \
+  }
 
 #define CK(ix, expr)                                                                       \
   do {                                                                                     \
@@ -188,6 +214,8 @@ static void free_shard(Shard& s) {
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.ev_b0) cudaEventDestroy(s.ev_b0);
+  if (s.ev_b1) cudaEventDestroy(s.ev_b1);
   if (s.ev_fork) cudaEventDestroy(s.ev_fork);
   for (auto& e : s.ev_join) if (e) cudaEventDestroy(e);
   for (auto& st : s.lane_stream) if (st) cudaStreamDestroy(st);
@@ -236,6 +264,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaHostGetDevicePointer((void**)&s.d_hout, s.h_out, 0));
   CK(ix, cudaEventCreate(&s.ev0));
   CK(ix, cudaEventCreate(&s.ev1));
+  CK(ix, cudaEventCreate(&s.ev_b0));
+  CK(ix, cudaEventCreate(&s.ev_b1));
   if (getenv("CQS_B200_TRACE")) {
     CK(ix, cudaMalloc((void**)&s.d_trace, sizeof(unsigned long long) * kMaxGrid * 8));
     CK(ix, cudaMemset(s.d_trace, 0, sizeof(unsigned long long) * kMaxGrid * 8));
@@ -270,7 +300,7 @@ static int grow_shard(cqs_b200_index* ix, Shard& s, uint64_t want_rows) {
 extern "C" {
 
 int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, int storage,
-                    cqs_b200_index** out) {
+                    cqs_b200_index** out) try {
   if (!out) return fail(CQS_B200_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (n_dev < 1 || n_dev > 64) return fail(CQS_B200_ERR_INVALID, "n_dev must be in 1..64");
@@ -313,7 +343,7 @@ int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, 
   }
   *out = ix;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 void cqs_b200_destroy(cqs_b200_index* ix) {
   if (!ix) return;
@@ -321,7 +351,7 @@ void cqs_b200_destroy(cqs_b200_index* ix) {
   delete ix;
 }
 
-int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows) {
+int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is finalized");
@@ -331,6 +361,13 @@ int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows) {
   rps = (rps + 31) / 32 * 32;  // shard boundaries on bitset word boundaries
   if (rps > 0xFFFFFFFFull) return fail(CQS_B200_ERR_INVALID, "more than 2^32-1 rows per device");
   ix->reserved = n_rows;
+  if (nd == 1) {
+    // one device: a capacity hint only — the shard regrows on demand, so reopen + append
+    // (the TieredIndex::extend analogue) keeps working on built and loaded indexes
+    return grow_shard(ix, ix->shards[0], n_rows);
+  }
+  // several devices: the shard boundaries are fixed here; appends beyond nd * rps are
+  // rejected (re-shard by rebuilding the index with a larger reserve)
   ix->rows_per_shard = rps;
   for (uint64_t i = 0; i < nd; ++i) {
     ix->shards[i].first_row = i * rps;
@@ -338,14 +375,14 @@ int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows) {
     if (rc) return rc;
   }
   return CQS_B200_OK;
-}
+} API_CATCH
 
-int cqs_b200_set_row_base(cqs_b200_index* ix, uint64_t row_base) {
+int cqs_b200_set_row_base(cqs_b200_index* ix, uint64_t row_base) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   ix->row_base = row_base;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, bool on_device) {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
@@ -412,14 +449,14 @@ static int append_impl(cqs_b200_index* ix, const float* rows, uint64_t n_rows, b
   return CQS_B200_OK;
 }
 
-int cqs_b200_append_rows_f32(cqs_b200_index* ix, const float* rows, uint64_t n_rows) {
+int cqs_b200_append_rows_f32(cqs_b200_index* ix, const float* rows, uint64_t n_rows) try {
   return append_impl(ix, rows, n_rows, false);
-}
-int cqs_b200_append_rows_f32_device(cqs_b200_index* ix, const float* d_rows, uint64_t n_rows) {
+} API_CATCH
+int cqs_b200_append_rows_f32_device(cqs_b200_index* ix, const float* d_rows, uint64_t n_rows) try {
   return append_impl(ix, d_rows, n_rows, true);
-}
+} API_CATCH
 
-int cqs_b200_finalize(cqs_b200_index* ix) {
+int cqs_b200_finalize(cqs_b200_index* ix) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
@@ -446,9 +483,9 @@ int cqs_b200_finalize(cqs_b200_index* ix) {
   }
   ix->finalized = true;
   return CQS_B200_OK;
-}
+} API_CATCH
 
-int cqs_b200_reopen(cqs_b200_index* ix) {
+int cqs_b200_reopen(cqs_b200_index* ix) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   ix->finalized = false;
@@ -465,7 +502,7 @@ int cqs_b200_reopen(cqs_b200_index* ix) {
   }
   ix->max_note_boost = ix->max_importance = 1.f;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 static bool query_is_finite(const float* q, uint32_t n) {
   for (uint32_t i = 0; i < n; ++i)
@@ -564,13 +601,15 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
 // Poll the completion word the kernel writes into mapped host memory; fall back to the
 // stream status every so often so a faulted kernel cannot hang the caller.
 static int wait_host_flag(cqs_b200_index* ix, Shard& s) {
-  volatile uint32_t* flag = (volatile uint32_t*)(s.h_out + kOffFlag);
-  for (uint64_t spin = 0; *flag != s.seq; ++spin) {
+  // acquire load: the result words in h_out that the caller reads next must not be
+  // speculated ahead of the flag (matters on weakly ordered hosts, e.g. Grace)
+  const uint32_t* flag = (const uint32_t*)(s.h_out + kOffFlag);
+  for (uint64_t spin = 0; __atomic_load_n(flag, __ATOMIC_ACQUIRE) != s.seq; ++spin) {
     if ((spin & 0xFFF) == 0xFFF) {
       CK(ix, cudaSetDevice(s.device));
       cudaError_t e = cudaStreamQuery(s.stream);
       if (e == cudaSuccess) {
-        if (*flag != s.seq) {
+        if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) != s.seq) {
           ix->poisoned.store(1);
           return fail(CQS_B200_ERR_CUDA, "scan finished without publishing its result");
         }
@@ -663,9 +702,9 @@ static int search_impl(cqs_b200_index* ix, const float* query, uint32_t k, const
 }
 
 int cqs_b200_search(cqs_b200_index* ix, const float* query, uint32_t k, const uint32_t* bitset,
-                    uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+                    uint64_t* out_rows, float* out_scores, uint32_t* out_n) try {
   return search_impl(ix, query, k, bitset, nullptr, out_rows, out_scores, out_n);
-}
+} API_CATCH
 
 static int upload_rows_u8(cqs_b200_index* ix, uint8_t* Shard::*field, const uint8_t* src, uint64_t n) {
   for (auto& s : ix->shards) {
@@ -692,7 +731,7 @@ static int upload_rows_f32(cqs_b200_index* ix, float* Shard::*field, const float
 }
 
 int cqs_b200_set_row_meta(cqs_b200_index* ix, const uint8_t* chunk_type, const uint8_t* lang,
-                          uint64_t n_rows) {
+                          uint64_t n_rows) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
@@ -702,10 +741,10 @@ int cqs_b200_set_row_meta(cqs_b200_index* ix, const uint8_t* chunk_type, const u
   int rc = upload_rows_u8(ix, &Shard::d_ctype, chunk_type, n_rows);
   if (rc) return rc;
   return upload_rows_u8(ix, &Shard::d_lang, lang, n_rows);
-}
+} API_CATCH
 
 int cqs_b200_set_row_signals(cqs_b200_index* ix, const float* note_boost, const float* importance,
-                             uint64_t n_rows) {
+                             uint64_t n_rows) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   if (!ix->finalized) return fail(CQS_B200_ERR_INVALID, "index is not finalized");
@@ -728,12 +767,12 @@ int cqs_b200_set_row_signals(cqs_b200_index* ix, const float* note_boost, const 
   int rc = upload_rows_f32(ix, &Shard::d_note_boost, note_boost);
   if (rc) return rc;
   return upload_rows_f32(ix, &Shard::d_importance, importance);
-}
+} API_CATCH
 
 int cqs_b200_search_filtered(cqs_b200_index* ix, const float* query, uint32_t limit,
                              float threshold, const uint64_t* type_mask, const uint64_t* lang_mask,
                              int enable_demotion, uint64_t* out_rows, float* out_scores,
-                             uint32_t* out_n) {
+                             uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   const bool have_meta = !ix->shards.empty() && ix->shards[0].d_ctype != nullptr;
@@ -750,11 +789,11 @@ int cqs_b200_search_filtered(cqs_b200_index* ix, const float* query, uint32_t li
   sig.d_importance = enable_demotion ? reinterpret_cast<const float*>(1) : nullptr;
   int rc = search_impl(ix, query, limit, nullptr, &sig, out_rows, out_scores, out_n);
   return rc;
-}
+} API_CATCH
 
 int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
                            const uint32_t* d_bitset, float* d_out_scores, uint64_t* d_out_rows,
-                           uint32_t* d_out_n, void* stream) {
+                           uint32_t* d_out_n, void* stream) try {
   int rc = check_searchable(ix);
   if (rc) return rc;
   if (!d_query || !d_out_scores || !d_out_rows || !d_out_n)
@@ -783,12 +822,12 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   CK(ix, launch_scan_single(a, s.num_sms, st));
   return release_scratch(ix, scr, st);
-}
+} API_CATCH
 
 int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t* d_rows,
                                uint32_t n_lists, uint32_t n_queries, uint32_t k,
                                float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
-                               void* stream) {
+                               void* stream) try {
   if (!d_scores || !d_rows || !d_out_scores || !d_out_rows || !d_out_n)
     return fail(CQS_B200_ERR_INVALID, "NULL argument");
   if (k == 0 || (uint64_t)n_lists * k > 8192)
@@ -798,9 +837,18 @@ int cqs_b200_merge_topk_device(int device, const float* d_scores, const uint64_t
   MergeArgs a{d_scores, d_rows, n_lists, n_queries, k, d_out_scores, d_out_rows, d_out_n};
   CK(none, launch_merge_topk(a, (cudaStream_t)stream));
   return CQS_B200_OK;
-}
+} API_CATCH
 
 // ---- row-sharded corpus over NVLink peer memory (peer.cu / peer.cuh) ----------
+// A timed-out exchange leaves the ranks' sequence numbers out of step: every later sharded search
+// on this group fails.  VectorIndex::is_poisoned() is the reference's only recovery hook
+// (src/index.rs:203-205 -> the daemon drops and rebuilds the index, cli/batch/view.rs:737-767), so
+// the failure is surfaced there: the index that ran the search is poisoned together with the group.
+static void peer_failed(cqs_b200_index* ix, cqs_b200_peer* peer) {
+  peer->failed.store(1);
+  ix->poisoned.store(1);
+}
+
 static int check_peer(cqs_b200_index* ix, cqs_b200_peer* peer) {
   if (!peer) return fail(CQS_B200_ERR_INVALID, "peer is NULL");
   if (ix->shards.size() != 1)
@@ -808,14 +856,17 @@ static int check_peer(cqs_b200_index* ix, cqs_b200_peer* peer) {
   if (peer->device != ix->shards[0].device)
     return fail(CQS_B200_ERR_INVALID, "peer group and index live on different devices");
   if (!peer->connected) return fail(CQS_B200_ERR_INVALID, "peer group is not connected");
-  if (peer->failed.load()) return fail(CQS_B200_ERR_POISONED, "peer group failed earlier; rebuild it");
+  if (peer->failed.load()) {
+    ix->poisoned.store(1);
+    return fail(CQS_B200_ERR_POISONED, "peer group failed earlier; rebuild it");
+  }
   if (ix->shards[0].n_rows == 0) return fail(CQS_B200_ERR_INVALID, "empty shard");
   return 0;
 }
 
 int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_query,
                                    uint32_t k, const uint32_t* d_bitset, float* d_out_scores,
-                                   uint64_t* d_out_rows, uint32_t* d_out_n, void* stream) {
+                                   uint64_t* d_out_rows, uint32_t* d_out_n, void* stream) try {
   int rc = check_searchable(ix);
   if (rc) return rc;
   if (!d_query || !d_out_scores || !d_out_rows || !d_out_n)
@@ -846,7 +897,7 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   CK(ix, launch_scan_single(a, s.num_sms, st));
   CK(ix, peer_mark(peer, st, /*exclusive=*/false));
   return release_scratch(ix, scr, st);
-}
+} API_CATCH
 
 // Device buffers of the batch entry points, allocated on first use (each one on its own: the
 // exact path and the tensor-core path share the query and result buffers).
@@ -866,7 +917,7 @@ static int ensure_batch_buffers(cqs_b200_index* ix, Shard& s, bool tensor_path) 
 // nq single-query scans, one launch each, issued round-robin on kLanes lanes (`st` and the
 // shard's own lane streams) so the tail of launch i — list merge and, with `peer`, the
 // cross-shard exchange — overlaps the streaming phase of the following launches.  Everything stays on
-// the device; `st` is joined with the second lane before returning.  d_queries: f32
+// the device; `st` is joined with the other lanes before returning.  d_queries: f32
 // [nq][q_stride]; `skip` (nullable): queries that are not launched (non-finite).  Caller
 // holds ix->mu (and peer->mu).
 static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, const float* d_queries,
@@ -924,7 +975,7 @@ static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, 
 int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_queries,
                                 uint32_t nq, uint32_t k, const uint32_t* d_bitset,
                                 float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
-                                void* stream) {
+                                void* stream) try {
   int rc = check_searchable(ix);
   if (rc) return rc;
   if (nq == 0) return CQS_B200_OK;
@@ -943,7 +994,7 @@ int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const f
   cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
   return launch_scan_lanes(ix, s, peer, d_queries, ix->dim, nq, k, d_bitset, d_out_scores, d_out_rows,
                            d_out_n, nullptr, st);
-}
+} API_CATCH
 
 // Exact (CUDA-core) batch: host queries in, host results out, one H2D, nq pipelined launches,
 // one D2H.  Used by cqs_b200_search_batch on f32 storage / small batches and by its sharded
@@ -984,7 +1035,7 @@ static int search_batch_exact(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   if (peer) CK(ix, cudaMemcpyAsync(&status, peer->d_status, sizeof status, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaStreamSynchronize(s.stream));
   if (status) {
-    peer->failed.store(1);
+    peer_failed(ix, peer);
     return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
   }
   for (uint32_t i = 0; i < nq; ++i) out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
@@ -993,7 +1044,7 @@ static int search_batch_exact(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
 
 int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query, uint32_t k,
                             const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
-                            uint32_t* out_n) {
+                            uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   int rc = check_searchable(ix);
   if (rc) return rc;
@@ -1018,7 +1069,7 @@ int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float
     uint32_t st = 0;
     CK(ix, cudaMemcpy(&st, peer->d_status, sizeof st, cudaMemcpyDeviceToHost));
     if (st) {
-      peer->failed.store(1);
+      peer_failed(ix, peer);
       return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this search)");
     }
   }
@@ -1026,7 +1077,7 @@ int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float
   memcpy(out_rows, s.h_out + kOffRows, sizeof(uint64_t) * n);
   *out_n = n;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 // Tensor-core path for one chunk of <= kBatchMaxQ queries on a single-device bf16 index.
 static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
@@ -1066,9 +1117,8 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
   a.d_flags = s.d_bflags;
   if (int rc2 = order_after_last(ix, s, s.stream)) return rc2;
-  if (ix->timing) CK(ix, cudaEventRecord(s.ev0, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev_b0, s.stream));
   CK(ix, launch_scan_batch(a, s.num_sms, s.stream));
-  if (ix->timing) CK(ix, cudaEventRecord(s.ev1, s.stream));
   if (int rc2 = mark_last(ix, s, s.stream)) return rc2;
   std::vector<uint32_t> flags(nq), ns(nq);
   CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
@@ -1076,10 +1126,6 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   CK(ix, cudaMemcpyAsync(ns.data(), s.d_bout_n, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaMemcpyAsync(flags.data(), s.d_bflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
   CK(ix, cudaStreamSynchronize(s.stream));
-  if (ix->timing) {
-    CK(ix, cudaEventElapsedTime(&ix->last_kernel_ms, s.ev0, s.ev1));
-    ix->last_batch_ms = ix->last_kernel_ms;
-  }
   for (uint32_t i = 0; i < nq; ++i) {
     out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
     if (flags[i] && !bad[i]) rerun->push_back(i);
@@ -1087,9 +1133,24 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   return CQS_B200_OK;
 }
 
+// Closes the bracket search_batch_tc opened (ev_b0) once the chunk's last kernel is queued.
+static int finish_batch_timing(cqs_b200_index* ix) {
+  if (!ix->timing) return 0;
+  std::lock_guard<std::mutex> g(ix->mu);
+  Shard& s = ix->shards[0];
+  CK(ix, cudaSetDevice(s.device));
+  CK(ix, cudaEventRecord(s.ev_b1, s.stream));
+  CK(ix, cudaEventSynchronize(s.ev_b1));
+  float ms = 0.f;
+  CK(ix, cudaEventElapsedTime(&ms, s.ev_b0, s.ev_b1));
+  ix->last_batch_ms += ms;
+  ix->last_kernel_ms = ix->last_batch_ms;
+  return 0;
+}
+
 int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq, uint32_t k,
                           const uint32_t* bitset, uint64_t* out_rows, float* out_scores,
-                          uint32_t* out_n) {
+                          uint32_t* out_n) try {
   int rc = check_searchable(ix);
   if (rc) return rc;
   if (nq && (!queries || !out_rows || !out_scores || !out_n))
@@ -1101,7 +1162,7 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
                            nq >= 8 && ix->n_rows < (1ull << 31);
   if (!tensor_path) {
     if (ix->shards.size() == 1 && nq > 1) {
-      // exact scans, pipelined: one H2D, nq launches on two lanes, one D2H
+      // exact scans, pipelined: one H2D, nq launches on kLanes (4) launch lanes, one D2H
       for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
         const uint32_t m = std::min(kBatchMaxQ, nq - q0);
         rc = search_batch_exact(ix, nullptr, queries + (size_t)q0 * ix->dim, m, k, bitset,
@@ -1117,6 +1178,8 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
     }
     return CQS_B200_OK;
   }
+  ix->last_batch_ms = 0.f;
+  ix->last_batch_reruns = 0;
   for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
     const uint32_t m = std::min(kBatchMaxQ, nq - q0);
     std::vector<uint32_t> rerun;
@@ -1131,13 +1194,15 @@ int cqs_b200_search_batch(cqs_b200_index* ix, const float* queries, uint32_t nq,
       if (rc) return rc;
     }
     ix->last_batch_reruns += (uint32_t)rerun.size();
+    ix->batch_reruns_total += (uint32_t)rerun.size();
+    if ((rc = finish_batch_timing(ix))) return rc;
   }
   return CQS_B200_OK;
-}
+} API_CATCH
 
 int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* queries,
                                   uint32_t nq, uint32_t k, const uint32_t* bitset,
-                                  uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+                                  uint64_t* out_rows, float* out_scores, uint32_t* out_n) try {
   int rc = check_searchable(ix);
   if (rc) return rc;
   if (nq && (!queries || !out_rows || !out_scores || !out_n))
@@ -1152,7 +1217,7 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
   const bool tensor_path = ix->storage != CQS_B200_STORAGE_F32 && nq >= 8 && ix->n_rows < (1ull << 31);
   if (!tensor_path) {
     // every rank takes this branch together (same nq, same storage): one fused
-    // scan + exchange per query, pipelined on two lanes
+    // scan + exchange per query, pipelined on kLanes (4) launch lanes
     for (uint32_t q0 = 0; q0 < nq; q0 += kBatchMaxQ) {
       const uint32_t m = std::min(kBatchMaxQ, nq - q0);
       rc = search_batch_exact(ix, peer, queries + (size_t)q0 * ix->dim, m, k, bitset,
@@ -1161,6 +1226,8 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
     }
     return CQS_B200_OK;
   }
+  ix->last_batch_ms = 0.f;
+  ix->last_batch_reruns = 0;
   // exchange granularity: as many queries as fit the mailbox (identical on every rank)
   const uint32_t q_per_x = std::min<uint32_t>(std::min(kBatchMaxQ, kPeerMaxQ), peer->cap / k);
   for (uint32_t q0 = 0; q0 < nq; q0 += q_per_x) {
@@ -1180,6 +1247,7 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
       if (rc) return rc;
     }
     ix->last_batch_reruns += (uint32_t)rerun.size();
+    ix->batch_reruns_total += (uint32_t)rerun.size();
     std::lock_guard<std::mutex> g(ix->mu);
     std::lock_guard<std::mutex> gp(peer->mu);
     Shard& s = ix->shards[0];
@@ -1203,6 +1271,7 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
                       s.d_bm_scores, s.d_bm_rows, s.d_bm_n, peer->d_ticket};
     CK(ix, launch_peer_gather_merge(pc, ga, s.num_sms, s.stream));
     CK(ix, peer_mark(peer, s.stream, /*exclusive=*/true));
+    if (ix->timing) CK(ix, cudaEventRecord(s.ev_b1, s.stream));
     std::vector<uint32_t> ns(m);
     uint32_t status = 0;
     CK(ix, cudaMemcpyAsync(osc, s.d_bm_scores, sizeof(float) * (size_t)m * k, cudaMemcpyDeviceToHost, s.stream));
@@ -1210,15 +1279,21 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
     CK(ix, cudaMemcpyAsync(ns.data(), s.d_bm_n, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s.stream));
     CK(ix, cudaMemcpyAsync(&status, peer->d_status, sizeof status, cudaMemcpyDeviceToHost, s.stream));
     CK(ix, cudaStreamSynchronize(s.stream));
+    if (ix->timing) {
+      float ms = 0.f;
+      CK(ix, cudaEventElapsedTime(&ms, s.ev_b0, s.ev_b1));
+      ix->last_batch_ms += ms;
+      ix->last_kernel_ms = ix->last_batch_ms;
+    }
     if (status) {
-      peer->failed.store(1);
+      peer_failed(ix, peer);
       for (uint32_t i = 0; i < m; ++i) out_n[q0 + i] = 0;
       return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
     }
     for (uint32_t i = 0; i < m; ++i) out_n[q0 + i] = bad[i] ? 0 : std::min(ns[i], k);
   }
   return CQS_B200_OK;
-}
+} API_CATCH
 
 // ---- sparse ------------------------------------------------------------------
 
@@ -1316,7 +1391,7 @@ static int sparse_build_on_device(cqs_b200_index* ix, Shard& s, const uint64_t* 
 }
 
 int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uint32_t* tok,
-                           const float* w, uint32_t vocab) {
+                           const float* w, uint32_t vocab) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   if (!indptr || vocab == 0) return fail(CQS_B200_ERR_INVALID, "NULL indptr / zero vocab");
   std::lock_guard<std::mutex> g(ix->mu);
@@ -1350,10 +1425,10 @@ int cqs_b200_sparse_attach(cqs_b200_index* ix, const uint64_t* indptr, const uin
   int rc = sparse_build_on_device(ix, s, d_indptr, d_tok, d_w, nnz, vocab);
   free_in();
   return rc;
-}
+} API_CATCH
 
 int cqs_b200_sparse_attach_device(cqs_b200_index* ix, const uint64_t* d_indptr, const uint32_t* d_tok,
-                                  const float* d_w, uint64_t nnz, uint32_t vocab) {
+                                  const float* d_w, uint64_t nnz, uint32_t vocab) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   if (!d_indptr || vocab == 0 || (nnz && (!d_tok || !d_w))) return fail(CQS_B200_ERR_INVALID, "NULL argument / zero vocab");
   std::lock_guard<std::mutex> g(ix->mu);
@@ -1368,7 +1443,7 @@ int cqs_b200_sparse_attach_device(cqs_b200_index* ix, const uint64_t* d_indptr, 
   CK(ix, cudaMemcpy(&ends[1], d_indptr + s.n_rows, sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (ends[0] != 0 || ends[1] != nnz) return fail(CQS_B200_ERR_INVALID, "indptr[0] != 0 or indptr[n_rows] != nnz");
   return sparse_build_on_device(ix, s, d_indptr, d_tok, d_w, nnz, vocab);
-}
+} API_CATCH
 
 // ---- SPLADE persistence (SpladeIndex::save / ::load, src/splade/index.rs:308-560) ----
 // Same contract as the reference's "SPDX" file: a 64-byte header carrying a format version, the
@@ -1391,7 +1466,7 @@ static_assert(sizeof(SparseFileHeader) == 64, "header must be 64 bytes");
 uint64_t checksum_update(uint64_t h, const uint8_t* p, size_t n);
 }  // namespace
 
-int cqs_b200_sparse_save(cqs_b200_index* ix, const char* path, uint64_t generation) {
+int cqs_b200_sparse_save(cqs_b200_index* ix, const char* path, uint64_t generation) try {
   if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->shards.size() != 1) return fail(CQS_B200_ERR_UNSUPPORTED, "single-device index only");
@@ -1422,9 +1497,9 @@ int cqs_b200_sparse_save(cqs_b200_index* ix, const char* path, uint64_t generati
     return fail(CQS_B200_ERR_INVALID, "writing %s failed", path);
   }
   return CQS_B200_OK;
-}
+} API_CATCH
 
-int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected_generation) {
+int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected_generation) try {
   if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
@@ -1441,13 +1516,20 @@ int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected
   if (memcmp(h.magic, "CQSB2SPX", 8) != 0 || h.version != 1) return bad("bad magic / version");
   if (h.generation != expected_generation) return bad("stale generation");
   if (h.n_docs != s.n_rows) return bad("chunk count differs from the index");
-  if (h.vocab == 0 || h.nnz > (1ull << 36)) return bad("implausible header");
+  // the header is untrusted until the checksum passes: bound it and match it against the file
+  // size BEFORE anything is sized from it (a damaged vocab / nnz must not drive a 500 GB vector)
+  if (h.vocab == 0 || h.vocab > 56320 || h.nnz > (1ull << 36)) return bad("implausible header");
+  {
+    if (fseek(f, 0, SEEK_END) != 0) return bad("cannot seek");
+    const long fsize = ftell(f);
+    const uint64_t want = sizeof h + 8ull * ((uint64_t)h.vocab + 1) + 8ull * h.nnz;
+    if (fsize < 0 || (uint64_t)fsize != want) return bad("size does not match the header");
+    if (fseek(f, (long)sizeof h, SEEK_SET) != 0) return bad("cannot seek");
+  }
   std::vector<uint64_t> tptr((size_t)h.vocab + 1);
   std::vector<uint2> post(std::max<uint64_t>(h.nnz, 1));
   if (fread(tptr.data(), sizeof(uint64_t), tptr.size(), f) != tptr.size()) return bad("truncated");
   if (h.nnz && fread(post.data(), sizeof(uint2), h.nnz, f) != h.nnz) return bad("truncated");
-  uint8_t extra;
-  if (fread(&extra, 1, 1, f) == 1) return bad("trailing bytes");
   uint64_t ck = checksum_update(0xcbf29ce484222325ull, (const uint8_t*)&h, 40);
   ck = checksum_update(ck, (const uint8_t*)tptr.data(), sizeof(uint64_t) * tptr.size());
   ck = checksum_update(ck, (const uint8_t*)post.data(), sizeof(uint2) * h.nnz);
@@ -1478,10 +1560,10 @@ int cqs_b200_sparse_load(cqs_b200_index* ix, const char* path, uint64_t expected
   sp.nnz = h.nnz;
   s.sparse = sp;
   return sparse_build_block_index(ix, s);
-}
+} API_CATCH
 
 // test hook: download the built postings (tptr [vocab+1], doc [nnz], weight [nnz])
-int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t* doc, float* w) {
+int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t* doc, float* w) try {
   if (!ix || ix->shards.size() != 1 || !ix->shards[0].sparse.d_tptr) return CQS_B200_ERR_INVALID;
   Shard& s = ix->shards[0];
   cudaSetDevice(s.device);
@@ -1499,7 +1581,7 @@ int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t*
     }
   }
   return cudaGetLastError() == cudaSuccess ? CQS_B200_OK : CQS_B200_ERR_CUDA;
-}
+} API_CATCH
 
 static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
                          uint32_t q_nnz, uint32_t k, const uint32_t* d_bits) {
@@ -1527,7 +1609,7 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
 
 int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const float* q_w,
                            uint32_t q_nnz, uint32_t k, const uint32_t* bitset, uint64_t* out_rows,
-                           float* out_scores, uint32_t* out_n) {
+                           float* out_scores, uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   int rc = check_searchable(ix);
   if (rc) return rc;
@@ -1563,7 +1645,7 @@ int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const floa
   memcpy(out_rows, hr, sizeof(uint64_t) * n);
   *out_n = n;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 static int copy_fused_out(cqs_b200_index* ix, Shard& s, uint32_t cap, uint64_t* out_rows,
                           float* out_fused, float* out_dense, float* out_sparse_raw,
@@ -1669,7 +1751,7 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
     uint32_t st = 0;
     CK(ix, cudaMemcpy(&st, peer->d_status, sizeof st, cudaMemcpyDeviceToHost));
     if (st) {
-      peer->failed.store(1);
+      peer_failed(ix, peer);
       *out_n = 0;
       return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this search)");
     }
@@ -1682,26 +1764,26 @@ int cqs_b200_search_hybrid(cqs_b200_index* ix, const float* query, const uint32_
                            const float* q_w, uint32_t q_nnz, float alpha, uint32_t pool_k,
                            const uint32_t* bitset, uint64_t* out_rows, float* out_fused,
                            float* out_dense, float* out_sparse_raw, uint8_t* out_present,
-                           uint32_t* out_n) {
+                           uint32_t* out_n) try {
   return search_hybrid_impl(ix, nullptr, query, q_tok, q_w, q_nnz, alpha, pool_k, bitset, out_rows,
                             out_fused, out_dense, out_sparse_raw, out_present, out_n);
-}
+} API_CATCH
 
 int cqs_b200_search_hybrid_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float* query,
                                    const uint32_t* q_tok, const float* q_w, uint32_t q_nnz,
                                    float alpha, uint32_t pool_k, const uint32_t* bitset,
                                    uint64_t* out_rows, float* out_fused, float* out_dense,
-                                   float* out_sparse_raw, uint8_t* out_present, uint32_t* out_n) {
+                                   float* out_sparse_raw, uint8_t* out_present, uint32_t* out_n) try {
   if (!peer) return fail(CQS_B200_ERR_INVALID, "peer is NULL");
   return search_hybrid_impl(ix, peer, query, q_tok, q_w, q_nnz, alpha, pool_k, bitset, out_rows,
                             out_fused, out_dense, out_sparse_raw, out_present, out_n);
-}
+} API_CATCH
 
 int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* dense_scores,
                         uint32_t n_dense, const uint64_t* sparse_rows, const float* sparse_scores,
                         uint32_t n_sparse, float alpha, uint32_t pool_k, uint64_t* out_rows,
                         float* out_fused, float* out_dense, float* out_sparse_raw,
-                        uint8_t* out_present, uint32_t* out_n) {
+                        uint8_t* out_present, uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   if (!out_rows || !out_fused || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
   if (n_dense > kMaxK || n_sparse > kMaxK || pool_k > 2 * kMaxK)
@@ -1767,10 +1849,10 @@ int cqs_b200_fuse_pools(int device, const uint64_t* dense_rows, const float* den
   rc = body();
   cudaFree(d);
   return rc;
-}
+} API_CATCH
 
 int cqs_b200_rrf_fuse(int device, const uint64_t* ids, const uint32_t* list_len, uint32_t n_lists,
-                      float k, uint32_t limit, uint64_t* out_ids, float* out_scores, uint32_t* out_n) {
+                      float k, uint32_t limit, uint64_t* out_ids, float* out_scores, uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   if (!out_ids || !out_scores || !out_n) return fail(CQS_B200_ERR_INVALID, "NULL argument");
   if (n_lists == 0 || limit == 0) return CQS_B200_OK;
@@ -1809,10 +1891,10 @@ int cqs_b200_rrf_fuse(int device, const uint64_t* ids, const uint32_t* list_len,
   int rc = body();
   cudaFree(d);
   return rc;
-}
+} API_CATCH
 
 int cqs_b200_search_typed(cqs_b200_index* ix, const float* query, uint32_t k, const uint64_t* type_mask,
-                          const uint64_t* lang_mask, uint64_t* out_rows, float* out_scores, uint32_t* out_n) {
+                          const uint64_t* lang_mask, uint64_t* out_rows, float* out_scores, uint32_t* out_n) try {
   if (out_n) *out_n = 0;
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   if (!type_mask && !lang_mask) return search_impl(ix, query, k, nullptr, nullptr, out_rows, out_scores, out_n);
@@ -1823,11 +1905,11 @@ int cqs_b200_search_typed(cqs_b200_index* ix, const float* query, uint32_t k, co
   if (lang_mask) memcpy(sig.lang_mask, lang_mask, 32);
   sig.pipeline = 0;  // raw cosine, filter only
   return search_impl(ix, query, k, nullptr, &sig, out_rows, out_scores, out_n);
-}
+} API_CATCH
 
 int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, uint32_t dim,
                              const float* queries, uint32_t nq, float threshold, int32_t* out_cat,
-                             float* out_margin) {
+                             float* out_margin) try {
   if (nq == 0) return CQS_B200_OK;
   if (!centroids || !queries || !out_cat || !out_margin || n_c == 0 || dim == 0)
     return fail(CQS_B200_ERR_INVALID, "NULL / empty argument");
@@ -1851,7 +1933,7 @@ int cqs_b200_route_centroids(int device, const float* centroids, uint32_t n_c, u
   rc = body();
   cudaFree(d_c); cudaFree(d_q); cudaFree(d_m); cudaFree(d_cat);
   return rc;
-}
+} API_CATCH
 
 // ---- persistence -----------------------------------------------------------------------
 
@@ -1881,7 +1963,7 @@ uint64_t checksum_update(uint64_t h, const uint8_t* p, size_t n) {
 }
 }  // namespace
 
-int cqs_b200_save(cqs_b200_index* ix, const char* path) {
+int cqs_b200_save(cqs_b200_index* ix, const char* path) try {
   if (!ix || !path) return fail(CQS_B200_ERR_INVALID, "NULL argument");
   std::lock_guard<std::mutex> g(ix->mu);
   if (ix->poisoned.load()) return fail(CQS_B200_ERR_POISONED, "index is poisoned");
@@ -1921,9 +2003,9 @@ int cqs_b200_save(cqs_b200_index* ix, const char* path) {
     return fail(CQS_B200_ERR_INVALID, "writing %s failed", path);
   }
   return CQS_B200_OK;
-}
+} API_CATCH
 
-int cqs_b200_load(const char* path, const int* device_ids, int n_dev, cqs_b200_index** out) {
+int cqs_b200_load(const char* path, const int* device_ids, int n_dev, cqs_b200_index** out) try {
   if (!out) return fail(CQS_B200_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (!path) return fail(CQS_B200_ERR_INVALID, "path is NULL");
@@ -1980,7 +2062,7 @@ int cqs_b200_load(const char* path, const int* device_ids, int n_dev, cqs_b200_i
   }
   *out = ix;
   return CQS_B200_OK;
-}
+} API_CATCH
 
 // ---- introspection ---------------------------------------------------------
 
@@ -1988,34 +2070,35 @@ uint64_t cqs_b200_len(const cqs_b200_index* ix) { return ix ? ix->n_rows : 0; }
 uint32_t cqs_b200_dim(const cqs_b200_index* ix) { return ix ? ix->dim : 0; }
 uint32_t cqs_b200_max_k(const cqs_b200_index*) { return kMaxK; }
 int cqs_b200_is_poisoned(const cqs_b200_index* ix) { return ix ? ix->poisoned.load() : 0; }
-int cqs_b200_scores_are_cosine(const cqs_b200_index* ix) {
+int cqs_b200_scores_are_cosine(const cqs_b200_index* ix) try {
   return ix && ix->storage != CQS_B200_STORAGE_BF16 && ix->metric == CQS_B200_METRIC_COSINE;
-}
+} API_CATCH
 const char* cqs_b200_name(void) { return "B200"; }
 const char* cqs_b200_last_error(void) { return t_last_error.c_str(); }
 uint64_t cqs_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 float cqs_b200_last_kernel_ms(cqs_b200_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
-int cqs_b200_set_timing(cqs_b200_index* ix, int enable) {
+int cqs_b200_set_timing(cqs_b200_index* ix, int enable) try {
   if (!ix) return fail(CQS_B200_ERR_INVALID, "index is NULL");
   std::lock_guard<std::mutex> g(ix->mu);
   ix->timing = enable != 0;
   return CQS_B200_OK;
-}
+} API_CATCH
 // development aids, not declared in the public header
-uint32_t cqs_b200_debug_batch_reruns(cqs_b200_index* ix) { return ix ? ix->last_batch_reruns : 0; }
-int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) {
+uint32_t cqs_b200_debug_batch_reruns(cqs_b200_index* ix) { return ix ? ix->batch_reruns_total : 0; }
+uint32_t cqs_b200_debug_last_batch_reruns(cqs_b200_index* ix) { return ix ? ix->last_batch_reruns : 0; }
+int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) try {
   if (!ix || ix->shards.empty() || !ix->shards[0].d_bflags) return CQS_B200_ERR_INVALID;
   cudaSetDevice(ix->shards[0].device);
   return cudaMemcpy(out, ix->shards[0].d_bflags, 4 * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
-}
+} API_CATCH
 float cqs_b200_debug_last_batch_ms(cqs_b200_index* ix) { return ix ? ix->last_batch_ms : 0.f; }
 float cqs_b200_debug_max_row_norm(cqs_b200_index* ix) { return ix && !ix->shards.empty() ? ix->shards[0].max_row_norm : -1.f; }
 // copies the trace stamps of shard 0
-int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) {
+int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) try {
   if (!ix || ix->shards.empty() || !ix->shards[0].d_trace) return CQS_B200_ERR_INVALID;
   cudaSetDevice(ix->shards[0].device);
   return cudaMemcpy(out, ix->shards[0].d_trace, sizeof(unsigned long long) * n_words,
                     cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
-}
+} API_CATCH
 
 }  // extern "C"

@@ -122,7 +122,7 @@ struct SparseDev {
   uint32_t vocab = 0;
   uint64_t nnz = 0;
   // Static block index (built once at attach / load): for the longest posting lists, where every
-  // 256-doc block starts inside the list — what the per-query bounds pass would otherwise find by
+  // 64-doc block (kSparseDocsPerBlock) starts inside the list — what the per-query bounds pass would otherwise find by
   // streaming the list's doc ids.  slot_of[token] = row of the table or -1.
   int32_t* d_slot_of = nullptr;     // [vocab]
   uint32_t* d_block_index = nullptr;  // [n_slots][index_stride]

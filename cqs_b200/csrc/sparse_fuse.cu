@@ -18,7 +18,7 @@
 // for the bounds pass) sorted by doc ascending — the order
 // SpladeIndex::build produces (index.rs:197-203).  A query touches only
 // sum_t |postings(t)| * 8 bytes, versus the whole 8*nnz bytes of a doc-major
-// scan.  Docs are processed in blocks of 256 owned by one warp (accumulators in
+// scan.  Docs are processed in blocks of kSparseDocsPerBlock (64) owned by one warp (accumulators in
 // shared memory); a first pass streams the doc ids of the touched lists once to
 // find where every block starts in every query token's list, the second applies
 // the tokens IN QUERY ORDER (the reference's accumulation order,
@@ -33,10 +33,10 @@ constexpr int kSpThreads = 512;          // 16 warps, 2 CTAs per SM
 constexpr int kSpWarps = kSpThreads / 32;
 constexpr uint32_t kSpCap = 4096;        // top-k accumulator slots
 constexpr uint32_t kSpMaxQ = 1024;       // max query nnz
-constexpr uint32_t kSpBlock = kSparseDocsPerBlock;  // docs owned by one warp at a time (256)
+constexpr uint32_t kSpBlock = kSparseDocsPerBlock;  // docs owned by one warp at a time (64)
 
-// ---- pass 1: where does every 256-doc block start inside every query token's list? ----
-// bounds[i][j] = number of postings of query token i with doc < j*256 (j = 0..n_blocks).
+// ---- pass 1: where does every 64-doc block start inside every query token's list? ----
+// bounds[i][j] = number of postings of query token i with doc < j*64 (j = 0..n_blocks).
 // Found by streaming the doc ids of the touched lists once (no dependent binary-search
 // chains): the thread that sees the first posting of a block writes the offsets of that
 // block and of the empty blocks before it.  bounds is zero-filled beforehand (empty lists).

@@ -17,7 +17,10 @@
  *     equals the reference's "(score desc, id asc)"
  *     (src/search/scoring/candidate.rs:303-329).
  *   - any CUDA failure sets a sticky poison bit (`cqs_b200_is_poisoned`),
- *     the analogue of src/cagra.rs:276,472-489 / src/index.rs:203-205.
+ *     the analogue of src/cagra.rs:276,472-489 / src/index.rs:203-205.  A failed
+ *     cross-shard exchange (a peer rank that never answered) poisons the index that
+ *     ran the search as well, so the daemon's is_poisoned() -> rebuild hook
+ *     (src/cli/batch/view.rs:737-767) covers the sharded path too.
  *   - an index handle is internally serialised by one mutex
  *     (src/cagra.rs:263) and may be shared across threads.
  *   - score of a row = f32 dot(query, row) (== cosine for the unit-norm
@@ -61,7 +64,11 @@ typedef struct cqs_b200_index cqs_b200_index; /* opaque */
  * this process (n_dev > 1 requires cqs_b200_reserve before the first append). */
 int cqs_b200_create(const int* device_ids, int n_dev, uint32_t dim, int metric, int storage,
                     cqs_b200_index** out);
-/* Pre-size for n_rows total rows (avoids regrowth; mandatory for n_dev > 1). */
+/* Pre-size for n_rows total rows.  n_dev == 1: a capacity hint only (avoids regrowth; the
+ * index still grows past it, so cqs_b200_reopen + append works on built and loaded indexes).
+ * n_dev > 1: mandatory, and it fixes the shard boundaries — appends beyond
+ * n_dev * ceil32(n_rows / n_dev) rows fail with CQS_B200_ERR_INVALID (rebuild with a larger
+ * reserve to re-shard). */
 int cqs_b200_reserve(cqs_b200_index* ix, uint64_t n_rows);
 /* Global row number of local row 0.  Used when one process holds one shard of a
  * corpus that is row-sharded across processes; reported rows
@@ -259,9 +266,9 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
                                    uint32_t k, const uint32_t* d_bitset, float* d_out_scores,
                                    uint64_t* d_out_rows, uint32_t* d_out_n, void* stream);
 /* nq exact single-query scans with everything on the device: one launch per query,
- * issued alternately on two launch lanes (`stream` and an internal one) so the tail of
- * one launch (list merge, cross-shard exchange) overlaps the streaming phase of the
- * next; `stream` is joined with the internal lane before the call returns
+ * issued round-robin on four launch lanes (`stream` and three internal streams, each with its
+ * own scratch set) so the tail of one launch (list merge, cross-shard exchange) overlaps the
+ * streaming phase of the next three; `stream` is joined with the internal lanes before the call returns
  * (asynchronous).  d_queries f32 [nq][dim]; outputs [nq][k] / [nq].  peer == NULL: this
  * index alone; otherwise the GLOBAL top-k over the sharded corpus on every rank. */
 int cqs_b200_search_many_device(cqs_b200_index* ix, cqs_b200_peer* peer, const float* d_queries,

@@ -348,6 +348,67 @@ def test_extend_after_reopen(cqs):
     ix.close()
 
 
+@pytest.mark.parametrize("storage", ["f32", "bf16"])
+def test_extend_after_build_and_after_load(cqs, tmp_path, storage):
+    """INTEGRATION.md §6 (watch loop): an index that was built (reserve + append) or loaded from
+    disk is extended in place — reopen, append, finalize — and then answers over all rows.
+    `cqs_b200_reserve` is a capacity hint on one device, not a cap."""
+    from cqs_b200.capi import lib, check
+    n0, n1, dim = 3000, 1777, 768
+    emb = O.fast_unit_rows(n0 + n1, dim, seed=71)
+    ids = [f"c{i:06d}" for i in range(n0 + n1)]
+    corpus = emb if storage == "f32" else O.bf16_to_f32(O.f32_to_bf16_rne(emb))
+    built = cqs.B200Index.build(ids[:n0], emb[:n0], storage=storage)          # calls reserve(n0)
+    path = str(tmp_path / "ix.b200")
+    built.save(path)
+    loaded = cqs.B200Index.load(path)                                         # load reserves n0 too
+    assert loaded is not None
+    for ix in (built, loaded):
+        check(lib.cqs_b200_reopen(ix._h))
+        ix.append(ids[n0:], emb[n0:])
+        ix.finalize()
+        assert len(ix) == n0 + n1
+        for qi in (n0 + 5, 17):
+            q = emb[qi]
+            g_rows, g_sc = ix.search_rows(q, 10)
+            full = O.dense_scores(corpus, q)
+            o_rows, o_sc = O.topk_rows(full, 10)
+            assert g_rows[0] == qi
+            assert_topk_parity(g_rows, g_sc, o_rows, o_sc, full)
+        ix.close()
+
+
+def test_index_score_reuse_matches_recompute(cqs, config1, index1):
+    """src/search/query.rs:2061-2170 (test_index_score_reuse_matches_recompute): a backend may only
+    answer index_scores_are_cosine() == true if the scores it returns equal a recomputed
+    cosine_similarity(query, stored embedding) to < 1e-6 — that is what lets
+    search_filtered_with_index skip the BLOB re-fetch (query.rs:1152-1172).  Checked for f32
+    storage on self-matches (score ~ 1, the worst case for an absolute bound), near-duplicates
+    and ordinary queries, k = 500 (the production pool)."""
+    rows, queries = config1
+    assert index1.index_scores_are_cosine()
+    worst = 0.0
+    for qi in list(range(0, 40)) + [100, 150, 217]:
+        q = queries[qi]
+        g_rows, g_sc = index1.search_rows(q, 500)
+        recomputed = np.asarray([O.cosine_similarity(q, rows[int(r)]) for r in g_rows], f32)
+        worst = max(worst, float(np.max(np.abs(g_sc.astype(np.float64) - recomputed.astype(np.float64)))))
+    assert worst < 1e-6, worst
+    # bf16-only storage scores the ROUNDED rows: not the f32 cosine, so it must say so
+    ixb = cqs.B200Index(768, storage="bf16")
+    ixb.append(None, rows[:2000]); ixb.finalize()
+    assert not ixb.index_scores_are_cosine()
+    ixb.close()
+    # bf16 + f32 master: results come from the f32 rows
+    ixm = cqs.B200Index(768, storage="bf16+f32")
+    ixm.append(None, rows[:2000]); ixm.finalize()
+    assert ixm.index_scores_are_cosine()
+    g_rows, g_sc = ixm.search_rows(queries[3], 50)
+    rec = np.asarray([O.cosine_similarity(queries[3], rows[int(r)]) for r in g_rows], f32)
+    assert np.max(np.abs(g_sc.astype(np.float64) - rec.astype(np.float64))) < 1e-6
+    ixm.close()
+
+
 @pytest.mark.parametrize("storage", ["f32", "bf16", "bf16+f32"])
 def test_save_load_roundtrip_and_corruption(cqs, tmp_path, storage):
     """Persistence conventions of src/cagra.rs:963-1652: checksummed blob + id sidecar,

@@ -3,10 +3,13 @@ exchange + merge that rides in the kernels must give, on EVERY rank, exactly the
 unsharded answer (same rows, bit-identical scores, reference order
 (score desc, id asc) — candidate.rs:321-329).
 
-One GPU is enough for: the fused tail with world = 1, and the stand-alone
-gather+merge kernel with the ranks emulated on one device (separate streams).
-The fused scan with world > 1 needs the ranks on different GPUs (a scan CTA
-that waits for a peer holds its SM): those tests skip below 2 GPUs."""
+One GPU is enough for every test here: with fewer than 2 GPUs the ranks are EMULATED on
+one device (one index + one peer group + one host thread or process per rank, all on
+cuda:0; the mailboxes are then plain same-device memory).  That is deadlock-free: a scan
+CTA that waits for a peer holds one SM, the other rank's persistent CTAs pull their tiles
+from the remaining SMs and every non-waiting CTA terminates on its own (and a rank that
+never shows up becomes a timeout, not a hang).  With >= 2 GPUs the same tests put every
+rank on its own GPU and the exchange crosses NVLink."""
 import ctypes as C
 import os
 import socket
@@ -131,20 +134,46 @@ def test_missing_rank_times_out_instead_of_hanging():
         g.close()
 
 
-def _need_gpus(n):
+def test_peer_failure_reaches_is_poisoned():
+    """A rank that never shows up: the sharded search times out, returns an error, and the failure is
+    visible through VectorIndex::is_poisoned() — the reference's only recovery hook
+    (src/index.rs:203-205 -> daemon rebuild, src/cli/batch/view.rs:737-767)."""
+    import cqs_b200
+    from cqs_b200.capi import B200Error
+    from cqs_b200.sharded import PeerGroup, search_sharded
+    rows = O.fast_unit_rows(5000, 768, seed=3)
+    ix = cqs_b200.B200Index(768, row_base=0)
+    ix.append(None, rows); ix.finalize()
+    groups = [PeerGroup(0, 2, g) for g in range(2)]
+    PeerGroup.connect_local(groups)
+    groups[0].set_timeout_ms(200)
+    assert not ix.is_poisoned()
+    with pytest.raises(B200Error):
+        search_sharded(ix, groups[0], rows[1], 20)           # rank 1 never searches
+    assert ix.is_poisoned()                                   # -> the shim's is_poisoned() -> rebuild
+    assert ix.search(rows[1], 5) == []                        # every later call: error -> empty Vec
+    with pytest.raises(B200Error):
+        search_sharded(ix, groups[0], rows[1], 20)
+    for g in groups:
+        g.close()
+    ix.close()
+
+
+def _rank_devices(max_ranks=4):
+    """Device of every rank: one GPU each when the box has several, else 2 ranks emulated on cuda:0."""
     import torch
-    if torch.cuda.device_count() < n:
-        pytest.skip(f"needs {n} GPUs")
+    n = torch.cuda.device_count()
+    return list(range(min(n, max_ranks))) if n >= 2 else [0, 0]
 
 
 @pytest.mark.parametrize("storage", ["f32", "bf16"])
-def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
-    _need_gpus(2)
+def test_ranks_in_process_fused_scan_exchange_merge(storage):
     import torch
     import cqs_b200
     from cqs_b200.capi import lib, check
     from cqs_b200.sharded import PeerGroup, shard_range, search_sharded, search_batch_sharded
-    G = min(torch.cuda.device_count(), 4)
+    devs = _rank_devices()
+    G = len(devs)
     n, dim, k, Q = 120_011, 768, 20, 12
     rows = O.fast_unit_rows(n, dim, seed=31)
     rows[17] = rows[n - 3]                                   # cross-shard exact tie
@@ -155,21 +184,21 @@ def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
     shards, groups = [], []
     for g in range(G):
         row0, nl = shard_range(n, G, g)
-        ix = cqs_b200.B200Index(dim, storage=storage, devices=[g], row_base=row0)
+        ix = cqs_b200.B200Index(dim, storage=storage, devices=[devs[g]], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
         shards.append(ix)
-        groups.append(PeerGroup(g, G, g))
+        groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
     # (a) asynchronous device entry: one launch per (rank, query), nothing else
     outs = []
     for g in range(G):
-        dev = torch.device("cuda", g)
+        dev = torch.device("cuda", devs[g])
         outs.append((torch.from_numpy(queries).to(dev), torch.empty((Q, k), dtype=torch.float32, device=dev),
                      torch.empty((Q, k), dtype=torch.int64, device=dev), torch.empty((Q,), dtype=torch.int32, device=dev)))
     for g in range(G):
-        torch.cuda.synchronize(g)
+        torch.cuda.synchronize(devs[g])
     # two launch lanes per rank: the exchange of query i overlaps the scan of query i+1
-    lanes = [[torch.cuda.Stream(device=torch.device("cuda", g)) for _ in range(2)] for g in range(G)]
+    lanes = [[torch.cuda.Stream(device=torch.device("cuda", devs[g])) for _ in range(2)] for g in range(G)]
     for qi in range(Q):
         for g in range(G):
             d_q, d_s, d_r, d_n = outs[g]
@@ -177,7 +206,7 @@ def test_two_gpus_in_process_fused_scan_exchange_merge(storage):
                                                      C.c_void_p(d_s[qi].data_ptr()), C.c_void_p(d_r[qi].data_ptr()),
                                                      C.c_void_p(d_n[qi].data_ptr()), C.c_void_p(lanes[g][qi % 2].cuda_stream)))
     for g in range(G):
-        torch.cuda.synchronize(g)
+        torch.cuda.synchronize(devs[g])
     for qi in range(Q):
         a, b = whole.search_rows(queries[qi], k)
         for g in range(G):
@@ -235,7 +264,8 @@ def _ipc_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.cuda.set_device(rank)
+    dev = rank % torch.cuda.device_count()     # one GPU: both processes share cuda:0 (IPC works there too)
+    torch.cuda.set_device(dev)
     n, dim, k, Q = 90_001, 768, 20, 40
     rows = O.fast_unit_rows(n, dim, seed=51)
     rows[5] = rows[n - 2]
@@ -244,11 +274,11 @@ def _ipc_worker(rank, world, port, out):
     ok = True
     for storage in ("f32", "bf16"):
         row0, nl = shard_range(n, world, rank)
-        ix = cqs_b200.B200Index(dim, storage=storage, devices=[rank], row_base=row0)
+        ix = cqs_b200.B200Index(dim, storage=storage, devices=[dev], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
-        whole = cqs_b200.B200Index(dim, storage=storage, devices=[rank])
+        whole = cqs_b200.B200Index(dim, storage=storage, devices=[dev])
         whole.append(None, rows); whole.finalize()
-        pg = PeerGroup.from_dist(dist, rank)                 # CUDA IPC handles over all_gather_object
+        pg = PeerGroup.from_dist(dist, dev)                  # CUDA IPC handles over all_gather_object
         for qi in range(Q):
             a, b = whole.search_rows(queries[qi], k)
             c, d = search_sharded(ix, pg, queries[qi], k)
@@ -265,7 +295,6 @@ def _ipc_worker(rank, world, port, out):
 
 
 def test_two_processes_cuda_ipc_mailboxes():
-    _need_gpus(2)
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()
@@ -280,14 +309,13 @@ def test_two_processes_cuda_ipc_mailboxes():
     assert out[0] and out[1]
 
 
-def test_two_gpus_sharded_hybrid_equals_unsharded():
+def test_ranks_sharded_hybrid_equals_unsharded():
     """Dense pool from the scan's own exchange + sparse pool through the gather+merge kernel + the same
     fusion on every rank == cqs_b200_search_hybrid on the whole corpus (src/search/query.rs:914-1005)."""
-    _need_gpus(2)
-    import torch
     import cqs_b200
     from cqs_b200.sharded import PeerGroup, shard_range
-    G = min(torch.cuda.device_count(), 4)
+    devs = _rank_devices()
+    G = len(devs)
     rng = np.random.default_rng(77)
     n, dim, vocab, pool = 24_000, 768, 3000, 500
     rows = O.fast_unit_rows(n, dim, seed=77, clustered=True)
@@ -301,11 +329,11 @@ def test_two_gpus_sharded_hybrid_equals_unsharded():
     shards, groups = [], []
     for g in range(G):
         row0, nl = shard_range(n, G, g)
-        ix = cqs_b200.B200Index(dim, devices=[g], row_base=row0)
+        ix = cqs_b200.B200Index(dim, devices=[devs[g]], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
         lo, hi = int(indptr[row0]), int(indptr[row0 + nl])
         ix.sparse_attach(indptr[row0:row0 + nl + 1] - indptr[row0], tok[lo:hi], w[lo:hi], vocab)
-        shards.append(ix); groups.append(PeerGroup(g, G, g))
+        shards.append(ix); groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
     cases = []
     for trial in range(6):
@@ -342,16 +370,16 @@ def test_two_gpus_sharded_hybrid_equals_unsharded():
     whole.close()
 
 
-def test_two_gpus_sharded_batch_with_exact_fallback():
+def test_ranks_sharded_batch_with_exact_fallback():
     """Near-duplicate rows inside one shard: that shard's tensor-core candidate pool cannot be proven
     complete for the matching queries, they are re-run through the exact scan and patched into the
     shard's lists BEFORE the exchange; the merged result must still equal the unsharded exact answer."""
-    _need_gpus(2)
     import ctypes as C
     import cqs_b200
     from cqs_b200.capi import lib
     from cqs_b200.sharded import PeerGroup, shard_range, search_batch_sharded
     G = 2
+    devs = _rank_devices(2)
     rng = np.random.default_rng(5)
     n, dim, k = 80_000, 768, 20
     rows = O.fast_unit_rows(n, dim, seed=41)
@@ -367,9 +395,9 @@ def test_two_gpus_sharded_batch_with_exact_fallback():
     shards, groups = [], []
     for g in range(G):
         row0, nl = shard_range(n, G, g)
-        ix = cqs_b200.B200Index(dim, storage="bf16", devices=[g], row_base=row0)
+        ix = cqs_b200.B200Index(dim, storage="bf16", devices=[devs[g]], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
-        shards.append(ix); groups.append(PeerGroup(g, G, g))
+        shards.append(ix); groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
     res = [None] * G
 

@@ -349,6 +349,37 @@ def test_sparse_persistence_generation_and_checksum(cqs, tmp_path):
     ix2.close()
 
 
+def test_sparse_load_survives_damaged_headers(cqs, tmp_path):
+    """A damaged header must make the load fail cleanly (-> rebuild, src/splade/index.rs:308-560),
+    never size a buffer from it: vocab / nnz fields are bounded and matched against the file size
+    before anything is allocated."""
+    import struct
+    rng = np.random.default_rng(6)
+    n_docs, vocab = 500, 300
+    indptr, tok, w = _zipf_csr(rng, n_docs, vocab, 12)
+    ix = cqs.B200Index(8)
+    ix.append(None, O.fast_unit_rows(n_docs, 8, seed=1)); ix.finalize()
+    ix.sparse_attach(indptr, tok, w, vocab)
+    path = str(tmp_path / "splade.bin")
+    ix.sparse_save(path, generation=7)
+    good = open(path, "rb").read()
+    # header: magic[8] version u32 vocab u32 generation u64 n_docs u64 nnz u64 checksum u64 pad[16]
+    for off, fmt, val in ((12, "<I", 0xFFFFFFFF), (12, "<I", 56321), (12, "<I", 0), (32, "<Q", 1 << 36),
+                          (32, "<Q", (1 << 36) + 1), (32, "<Q", 0)):
+        raw = bytearray(good)
+        struct.pack_into(fmt, raw, off, val)
+        open(path, "wb").write(bytes(raw))
+        assert not ix.sparse_load(path, expected_generation=7)
+    open(path, "wb").write(good + b"\0")
+    assert not ix.sparse_load(path, expected_generation=7)              # trailing byte
+    open(path, "wb").write(good[:40])
+    assert not ix.sparse_load(path, expected_generation=7)              # short header
+    open(path, "wb").write(good)
+    assert ix.sparse_load(path, expected_generation=7)
+    assert not ix.is_poisoned()
+    ix.close()
+
+
 @pytest.mark.parametrize("n_docs,vocab,mean_nnz", [(40_000, 30522, 60), (70_001, 600, 25)])
 def test_sparse_search_with_static_block_index_vs_oracle(cqs, n_docs, vocab, mean_nnz):
     """Long posting lists take their block boundaries from the static index built at attach time,

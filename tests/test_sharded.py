@@ -130,18 +130,18 @@ def test_emulated_shards_device_merge_equals_unsharded(storage):
 @pytest.mark.gpu
 def test_in_process_multi_device_index_equals_single():
     """cqs_b200_create(device_ids, n_dev > 1): the form the single-process daemon would use —
-    contiguous row blocks per device, host merge.  Needs >= 2 GPUs (skipped otherwise)."""
+    contiguous row blocks per device, host merge.  On a 1-GPU box the shards are two blocks on
+    cuda:0 (same code path: per-shard launch, host-mapped results, host merge)."""
     import torch
     import cqs_b200
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
     n, dim = 30_011, 768
     rows = O.fast_unit_rows(n, dim, seed=91)
     rows[5] = rows[n - 2]
     one = cqs_b200.B200Index(dim, devices=[0])
     one.append(None, rows); one.finalize()
     nd = min(torch.cuda.device_count(), 4)
-    multi = cqs_b200.B200Index(dim, devices=list(range(nd)))
+    devices = list(range(nd)) if nd >= 2 else [0, 0, 0]
+    multi = cqs_b200.B200Index(dim, devices=devices)
     multi.reserve(n)
     multi.append(None, rows[:10_000]); multi.append(None, rows[10_000:])
     multi.finalize()
