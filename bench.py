@@ -1,19 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the cqs retrieval hot path on B200.
+"""bench.py — benchmark of the cqs retrieval hot path on B200, every BASELINE.json config in ONE line.
 
-Workload (BASELINE.json configs[1]): exact top-20 of ONE query at a time over
-1,000,000 x 768 f32 unit-norm chunk embeddings (3.072 GB, >> 126 MB L2, so no
-flush between iterations).  A *step* = one batch of Q single-query searches.
-`value` = queries/s with corpus AND queries resident in HBM (device-timed, CUDA
-events on the launching stream); `e2e` = the same metric through the C-ABI call
-the Rust shim binds (`cqs_b200_search`: host query in, host top-k out,
-H2D/D2H inside the timed region).  With N > 1 ranks the same corpus is
-row-sharded (strong scaling): every rank scans its shard, the per-shard
-top-k are merged with one all-gather per step.
+`python bench.py --gpus N --steps K --warmup W` prints one JSON line.  Its top level is the
+headline, BASELINE configs[1]: exact top-20 of ONE query at a time over 1,000,000 x 768 f32
+unit-norm chunk embeddings (3.072 GB >> 126 MB L2, so no flush between iterations), row-sharded
+over the N ranks (strong scaling).  A *step* = one batch of Q = 64*N single-query searches.
+`value` = queries/s with corpus AND queries resident in HBM (CUDA events on the launching
+stream); `e2e` = the same metric through the C-ABI call the Rust shim binds (host buffers,
+H2D/D2H inside the timed region).
 
-`--impl reference` times the reference's own CPU algorithm (the C port in
-oracle/, all host threads, one query per thread as in src/search/query.rs:469)
-on a bounded sample of the same workload.
+`extra` is a list of complete sub-records (metric, value, ms_per_step, clocks, roofline, e2e,
+cpu_baseline, parity vs the CPU port on the same data) for the other configs:
+
+  N = 1 : single_k500 (production pool size, src/limits.rs:315-320), hybrid_1M (configs[4]:
+          dense + SPLADE + per-category alpha, pool 500), hybrid_1M_clustered, batch_10M
+          (configs[2]: 10M x 768 bf16, 1024-query tcgen05 batches + f32 rescoring),
+          batch_10M_clustered, and the N = 1 point of the weak-scaling pair below.
+  all N : sharded_single / sharded_batch (configs[3]: 12.5M x 768 bf16 rows PER GPU — 100M rows
+          at N = 8 — single query and 1024-query batches, exchange over NVLink peer memory).
+
+Parity in every record: a CPU oracle (oracle/cqs_oracle.c, the C port of the reference's brute
+force) scores the SAME rows block by block while they are generated (each rank its own shard;
+shard lists are merged with the reference's order rule), and the GPU answers of the parity
+queries are compared with it: `ids_identical_queries`, plus recall@20 against the un-rounded f32
+corpus for bf16 storage.  The oracle runs outside every timed region.
+
+`--impl reference` times the reference's own CPU algorithm (the C port in oracle/, all host
+threads, one query per thread as in src/search/query.rs:469) on the headline workload.
+`--records a,b,c` restricts the extra records (default: all that apply to N); `--records none`
+prints the headline alone.
 """
 import argparse
 import ctypes as C
@@ -32,8 +47,16 @@ sys.path.insert(0, ROOT)
 DIM = 768
 K = 20
 N_ROWS = 1_000_000
+BLK = 100_000
 METRIC = "queries_per_s_exact_top20_1Mx768_f32"
 UNIT = "queries/s"
+WORKLOAD = f"exact top-{K}, single query at a time, {N_ROWS}x{DIM} f32 (BASELINE configs[1])"
+SHARD_ROWS = 12_500_000          # configs[3]: 100M rows over 8 GPUs
+BATCH_ROWS = 10_000_000          # configs[2]
+BATCH_Q = 1024
+VOCAB = 30522
+ALPHAS = [0.85, 0.60, 1.00, 0.80, 0.10, 0.80, 0.00, 0.70, 0.80]   # src/search/router.rs:126-175, the 9 categories
+EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
 def peaks():
@@ -43,6 +66,14 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peaks():
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(mp["bf16_tflops_sustained"]), float(mp["bf16_tflops"]), "measured cuBLAS bf16 (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1412.0, 1668.9, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -104,12 +135,22 @@ class ClockSampler:
 # stdout carries exactly ONE line, the JSON result: file descriptor 1 is pointed at stderr for
 # the whole run (NCCL prints its version banner on stdout, torchrun its OMP notice), and the
 # result is written to the saved descriptor at the end.
-_RESULT_FD = os.dup(1)
-os.dup2(2, 1)
+_RESULT_FD = None
+
+
+def claim_stdout() -> None:
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: dict) -> None:
-    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
+def log(*a):
+    print(f"[bench {time.strftime('%H:%M:%S')}]", *a, file=sys.stderr, flush=True)
 
 
 def ncu_traffic(key: str):
@@ -120,529 +161,1025 @@ def ncu_traffic(key: str):
         return None
 
 
-def make_queries(nq: int, seed: int) -> np.ndarray:
+# ---- synthetic data ------------------------------------------------------------------------
+# uniform  : uniform[-1,1) L2-normalised — the distribution of the reference recipe
+#            (examples/exp_level_scale.rs:200-224); top-20 scores ~0.15, no near ties.
+# clustered: 256 random unit centres + Gaussian noise of norm ~0.6, renormalised:
+#            same-cluster cosine ~0.7, dense score neighbourhoods -> near ties, exact-fallback
+#            re-runs in the batch path, and a corpus on which HNSW recall means something.
+_CENTRES = {}
+
+
+def centres_np():
+    if "np" not in _CENTRES:
+        rng = np.random.default_rng(0xC1057E8)
+        c = rng.standard_normal((256, DIM)).astype(np.float32)
+        c /= np.linalg.norm(c, axis=1, keepdims=True)
+        _CENTRES["np"] = np.ascontiguousarray(c, np.float32)
+    return _CENTRES["np"]
+
+
+def make_queries(nq: int, seed: int, mode: str = "uniform") -> np.ndarray:
     rng = np.random.default_rng(seed)
-    q = rng.uniform(-1, 1, size=(nq, DIM)).astype(np.float32)
+    if mode == "clustered":
+        c = centres_np()
+        q = c[rng.integers(0, 256, size=nq)] + rng.standard_normal((nq, DIM)).astype(np.float32) * np.float32(0.6 / np.sqrt(DIM))
+    else:
+        q = rng.uniform(-1, 1, size=(nq, DIM)).astype(np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     return np.ascontiguousarray(q, np.float32)
 
 
-def gen_rows_torch(torch, dev, row0: int, n: int):
-    """Synthetic unit rows, uniform[-1,1) L2-normalised (the reference recipe's
-    distribution, examples/exp_level_scale.rs:200-224), generated on device per
-    100k-row block from a block-indexed seed so any shard can be produced alone."""
-    BLK = 100_000
-    out = []
-    b0, b1 = row0 // BLK, (row0 + n - 1) // BLK
-    for b in range(b0, b1 + 1):
-        g = torch.Generator(device=dev)
-        g.manual_seed(0x9E3779B9 + b)
+def gen_block(torch, dev, b: int, mode: str = "uniform"):
+    """Rows [b*BLK, (b+1)*BLK) of the synthetic corpus, f32 on the device, from a block-indexed seed
+    (any shard can be produced alone, on any rank)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x9E3779B9 + b + (0x51ED27 if mode == "clustered" else 0))
+    if mode == "clustered":
+        key = ("dev", str(dev))
+        if key not in _CENTRES:
+            _CENTRES[key] = torch.from_numpy(centres_np()).to(dev)
+        pick = torch.randint(0, 256, (BLK,), generator=g, device=dev)
+        x = _CENTRES[key][pick] + torch.randn((BLK, DIM), generator=g, device=dev, dtype=torch.float32) * (0.6 / DIM ** 0.5)
+    else:
         x = torch.rand((BLK, DIM), generator=g, device=dev, dtype=torch.float32) * 2 - 1
-        x /= x.norm(dim=1, keepdim=True)
-        lo, hi = max(row0, b * BLK) - b * BLK, min(row0 + n, (b + 1) * BLK) - b * BLK
-        out.append(x[lo:hi].contiguous())
+    x /= x.norm(dim=1, keepdim=True)
+    return x
+
+
+def stored_view(torch, x, storage: str):
+    """The corpus the index answers for, as f32 values: the rows themselves (f32, bf16+f32 master),
+    or the RNE-rounded bf16 rows (bf16 storage: the rounded matrix IS the corpus)."""
+    if storage == "bf16":
+        return x.to(torch.bfloat16).to(torch.float32)
+    return x
+
+
+class BlockOracle:
+    """CPU oracle fed block by block while the corpus is generated: the C port of the reference's
+    brute force (oracle/cqs_oracle.c; f64-accumulated dot = src/math.rs:17-22, BoundedScoreHeap
+    order) on each block, running top-k merged with the reference's order rule.  Test
+    infrastructure: it only ever runs outside the timed regions."""
+
+    def __init__(self, queries: np.ndarray, k: int, threads: int, use_f64: bool = True):
+        from oracle import c_oracle as CO
+        self.CO, self.q, self.k, self.threads, self.use_f64 = CO, np.ascontiguousarray(queries, np.float32), k, threads, use_f64
+        nq = self.q.shape[0]
+        self.rows = np.full((nq, k), EMPTY, np.uint64)
+        self.scores = np.full((nq, k), -np.inf, np.float32)
+        self.cpu_s = 0.0
+        self.rows_fed = 0
+
+    def feed(self, block: np.ndarray, row0: int):
+        from cqs_b200.sharded import merge_topk_host
+        t0 = time.perf_counter()
+        r, s, n = self.CO.brute_force_batch(block, self.q, self.k, use_f64=self.use_f64, threads=self.threads)
+        self.cpu_s += time.perf_counter() - t0
+        self.rows_fed += block.shape[0]
+        for i in range(self.q.shape[0]):
+            m = int(n[i])
+            sc = np.concatenate([self.scores[i], s[i, :m]])
+            rw = np.concatenate([self.rows[i], r[i, :m] + np.uint64(row0)])
+            ms, mr = merge_topk_host(sc, rw, self.k)
+            self.scores[i] = -np.inf
+            self.rows[i] = EMPTY
+            self.scores[i, :ms.shape[0]] = ms
+            self.rows[i, :mr.shape[0]] = mr
+
+    def snapshot(self):
+        return self.rows.copy(), self.scores.copy(), self.cpu_s, self.rows_fed
+
+
+def compare_lists(g_rows, g_sc, o_rows, o_sc, rel=1e-5):
+    """One query: (ids identical, mismatches explained by oracle near-ties, max relative score error)."""
+    g_rows = np.asarray(g_rows).astype(np.uint64)
+    o_rows = np.asarray(o_rows).astype(np.uint64)
+    ok = o_rows != EMPTY
+    o_rows, o_sc = o_rows[ok], np.asarray(o_sc, np.float32)[ok]
+    n = min(g_rows.shape[0], o_rows.shape[0])
+    if g_rows.shape[0] != o_rows.shape[0]:
+        return False, False, float("inf")
+    if n == 0:
+        return True, True, 0.0
+    err = float(np.max(np.abs(np.asarray(g_sc[:n], np.float64) - o_sc[:n].astype(np.float64)) /
+                       np.maximum(np.abs(o_sc[:n].astype(np.float64)), 1e-30)))
+    same = bool(np.array_equal(g_rows[:n], o_rows[:n]))
+    if same:
+        return True, True, err
+    # a different id is only acceptable inside a near-tie of ORACLE scores (north star: ids identical
+    # wherever adjacent scores are separated by more than the tolerance)
+    near = True
+    for i in np.nonzero(g_rows[:n] != o_rows[:n])[0]:
+        # the oracle's score at this rank and at a neighbouring rank must be within the tolerance of each other
+        lo, hi = max(i - 1, 0), min(i + 1, n - 1)
+        b = float(o_sc[i])
+        near &= min(abs(float(o_sc[lo]) - b) if lo != i else np.inf,
+                    abs(float(o_sc[hi]) - b) if hi != i else np.inf) <= 2 * max(rel * abs(b), 1e-7)
+    return False, bool(near), err
+
+
+def parity_summary(results, oracle_rows, oracle_scores):
+    """results: list of (rows, scores) per parity query."""
+    ident = near = 0
+    worst = 0.0
+    for i, (r, s) in enumerate(results):
+        a, b, e = compare_lists(r, s, oracle_rows[i], oracle_scores[i])
+        ident += int(a)
+        near += int((not a) and b)
+        if np.isfinite(e):
+            worst = max(worst, e)
+    n = len(results)
+    return {"ids_identical_queries": f"{ident}/{n}", "near_tie_only_mismatches": near,
+            "max_rel_score_err": worst, "score_tolerance": 1e-5,
+            "ok": bool(ident + near == n and worst <= 1e-5)}
+
+
+def recall_at_k(results, exact_rows):
+    hit = tot = 0
+    for i, (r, _) in enumerate(results):
+        ex = set(int(x) for x in exact_rows[i] if x != EMPTY)
+        hit += len(ex & set(int(x) for x in r))
+        tot += len(ex)
+    return hit / max(tot, 1)
+
+
+# ---- context ---------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def make_ctx(args):
+    import torch
+    c = Ctx()
+    c.torch = torch
+    c.args = args
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    c.dev = torch.device("cuda", c.local)
+    torch.cuda.set_device(c.dev)
+    c.dist = None
+    if c.world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=c.dev)
+        c.dist = dist
+    c.cpu_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", c.world))))
+    c.stream = torch.cuda.Stream(device=c.dev)   # a dedicated (non-default) stream: the library treats
+    torch.cuda.set_stream(c.stream)              # stream == NULL as "use the index's own stream"
+    return c
+
+
+def barrier(c):
+    if c.world > 1:
+        c.dist.barrier()
+    c.torch.cuda.synchronize()
+
+
+def max_over_ranks(c, vals):
+    if c.world == 1:
+        return [float(v) for v in vals]
+    t = c.torch.tensor(list(vals), device=c.dev, dtype=c.torch.float64)
+    c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu().tolist()]
+
+
+def gather_objects(c, obj):
+    if c.world == 1:
+        return [obj]
+    out = [None] * c.world
+    c.dist.all_gather_object(out, obj)
     return out
 
 
+def fill_index(c, ix, storage, row0, n_local, mode, oracles=(), host=None):
+    """Generator: appends this rank's rows [row0, row0 + n_local) to `ix`, generated on the device
+    block by block; every block is also handed to the CPU oracles (list of (BlockOracle,
+    'exact' | 'stored')) and, optionally, kept on the host.  Yields the local row count so far."""
+    torch = c.torch
+    pin = [torch.empty((BLK, DIM), dtype=torch.float32).pin_memory() for _ in range(2)] if oracles else None
+    done = 0
+    for b in range(row0 // BLK, (row0 + n_local - 1) // BLK + 1):
+        x = gen_block(torch, c.dev, b, mode)
+        lo, hi = max(row0, b * BLK) - b * BLK, min(row0 + n_local, (b + 1) * BLK) - b * BLK
+        x = x[lo:hi].contiguous()
+        ix.append_device(x.data_ptr(), x.shape[0])
+        if host is not None:
+            host.append(x.cpu().numpy())
+        views = {}
+        for orc, which in oracles:
+            if which not in views:
+                v = x if which == "exact" else stored_view(torch, x, storage)
+                buf = pin[len(views)][: x.shape[0]]
+                buf.copy_(v)
+                torch.cuda.synchronize()
+                views[which] = buf.numpy()
+            orc.feed(views[which], row0 + done)
+        done += x.shape[0]
+        del x
+        yield done
+    torch.cuda.empty_cache()
+
+
+def build_index(c, storage, n_total, mode, oracles=(), keep_host=False):
+    """This rank's shard of an n_total-row corpus (contiguous blocks in chunk-id order)."""
+    import cqs_b200
+    from cqs_b200.sharded import shard_range
+    row0, n_local = shard_range(n_total, c.world, c.rank)
+    ix = cqs_b200.B200Index(DIM, storage=storage, devices=[c.local], row_base=row0)
+    ix.reserve(n_local)
+    host = [] if keep_host else None
+    for _ in fill_index(c, ix, storage, row0, n_local, mode, oracles, host):
+        pass
+    return ix, row0, n_local, (np.concatenate(host) if host else None)
+
+
+# ---- single-query timing (headline, k = 500, sharded_single) ------------------------------------
+def time_single(c, ix, pg, queries, k, Q, steps, warmup, transport="peer", pipeline=4):
+    """Device-resident timing: a step = Q single-query scans, one kernel launch each (4 launch
+    lanes inside ONE cqs_b200_search_many_device call); CUDA events on the launching stream,
+    max over ranks.  Then the same through the C ABI with host buffers (e2e) and the latency
+    of the blocking single-query call."""
+    from cqs_b200.capi import lib, check
+    torch, dev, world = c.torch, c.dev, c.world
+    stream = c.stream
+    sp = C.c_void_p(stream.cuda_stream)
+    nq_total = Q * (steps + warmup)
+    assert queries.shape[0] >= nq_total
+    d_queries = torch.from_numpy(queries[:nq_total]).to(dev)
+    d_sc = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    d_rw = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
+    nccl = world > 1 and transport == "nccl"
+    diag = world > 1 and transport == "none"
+    if nccl or diag:
+        g_sc = torch.empty((world, Q, k), dtype=torch.float32, device=dev)
+        g_rw = torch.empty((world, Q, k), dtype=torch.int64, device=dev)
+        m_sc, m_rw, m_n = torch.empty_like(d_sc), torch.empty_like(d_rw), torch.empty_like(d_n)
+    P = 1 if (nccl or diag) else pipeline
+
+    def step_device(s):
+        q0 = d_queries.data_ptr() + s * Q * DIM * 4
+        if P > 1:
+            check(lib.cqs_b200_search_many_device(ix._h, pg._h if pg is not None else None, C.c_void_p(q0), Q, k, None,
+                                                  C.c_void_p(d_sc.data_ptr()), C.c_void_p(d_rw.data_ptr()),
+                                                  C.c_void_p(d_n.data_ptr()), sp))
+            return
+        for i in range(Q):
+            fn = lib.cqs_b200_search_sharded_device if pg is not None else None
+            if fn is not None:
+                check(fn(ix._h, pg._h, C.c_void_p(q0 + i * DIM * 4), k, None, C.c_void_p(d_sc.data_ptr() + i * k * 4),
+                         C.c_void_p(d_rw.data_ptr() + i * k * 8), C.c_void_p(d_n.data_ptr() + i * 4), sp))
+            else:
+                check(lib.cqs_b200_search_device(ix._h, C.c_void_p(q0 + i * DIM * 4), k, None,
+                                                 C.c_void_p(d_sc.data_ptr() + i * k * 4),
+                                                 C.c_void_p(d_rw.data_ptr() + i * k * 8),
+                                                 C.c_void_p(d_n.data_ptr() + i * 4), sp))
+        if nccl:
+            c.dist.all_gather_into_tensor(g_sc, d_sc)
+            c.dist.all_gather_into_tensor(g_rw, d_rw)
+            check(lib.cqs_b200_merge_topk_device(c.local, C.c_void_p(g_sc.data_ptr()), C.c_void_p(g_rw.data_ptr()),
+                                                 world, Q, k, C.c_void_p(m_sc.data_ptr()),
+                                                 C.c_void_p(m_rw.data_ptr()), C.c_void_p(m_n.data_ptr()), sp))
+
+    for s in range(warmup):
+        step_device(s)
+    barrier(c)
+    launches0 = lib.cqs_b200_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(c.local)
+    clk.__enter__()
+    barrier(c)
+    e0.record(stream)
+    for s in range(steps):
+        step_device(warmup + s)           # the library joins its lanes back into `stream`
+    e1.record(stream)
+    barrier(c)
+    ms_local = e0.elapsed_time(e1)
+    launches = lib.cqs_b200_kernel_launches() - launches0
+    per_rank_ms = [ms_local]
+    if world > 1:
+        allms = torch.empty((world,), device=dev)
+        c.dist.all_gather_into_tensor(allms, torch.tensor([ms_local], device=dev))
+        per_rank_ms = [float(x) for x in allms.cpu().tolist()]
+    ms = max(per_rank_ms)
+
+    # ---- end to end through the C ABI with host buffers ----
+    q_base = queries.ctypes.data
+    b_rows = np.empty((Q, k), np.uint64)
+    b_sc = np.empty((Q, k), np.float32)
+    b_n = np.zeros(Q, np.uint32)
+    pb = (b_rows.ctypes.data_as(C.c_void_p), b_sc.ctypes.data_as(C.c_void_p), b_n.ctypes.data_as(C.c_void_p))
+    o_rows, o_sc, o_n = np.empty(k, np.uint64), np.empty(k, np.float32), C.c_uint32(0)
+    po = (o_rows.ctypes.data_as(C.c_void_p), o_sc.ctypes.data_as(C.c_void_p), C.byref(o_n))
+    batch_call = ix.storage == "f32" and not (nccl or diag)
+    if nccl or diag:
+        h_q = torch.from_numpy(queries[:nq_total]).pin_memory()
+        h_s = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+        h_r = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+
+    def step_e2e(s):
+        base = s * Q
+        qp = C.c_void_p(q_base + base * DIM * 4)
+        if nccl or diag:
+            d_queries[base:base + Q].copy_(h_q[base:base + Q], non_blocking=True)
+            step_device(s)
+            h_s.copy_(m_sc if nccl else d_sc, non_blocking=True)
+            h_r.copy_(m_rw if nccl else d_rw, non_blocking=True)
+            torch.cuda.synchronize()
+        elif not batch_call:
+            # bf16 storage: a batch call would switch to the tensor-core algorithm (a different
+            # workload); stay with one blocking single-query call per query
+            for i in range(Q):
+                qi = C.c_void_p(q_base + (base + i) * DIM * 4)
+                if pg is not None:
+                    check(lib.cqs_b200_search_sharded(ix._h, pg._h, qi, k, None, *po))
+                else:
+                    check(lib.cqs_b200_search(ix._h, qi, k, None, *po))
+        elif pg is not None:
+            check(lib.cqs_b200_search_batch_sharded(ix._h, pg._h, qp, Q, k, None, *pb))
+        else:
+            check(lib.cqs_b200_search_batch(ix._h, qp, Q, k, None, *pb))
+
+    for s in range(warmup):
+        step_e2e(s)
+    barrier(c)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step_e2e(warmup + s)
+    barrier(c)
+    e2e_s = time.perf_counter() - t0
+    clk.__exit__()
+    lat = []
+    if not (nccl or diag):
+        for rep, nl in enumerate((16, min(nq_total, 128))):
+            lat.clear()
+            for i in range(nl):
+                qi = C.c_void_p(q_base + i * DIM * 4)
+                t0 = time.perf_counter()
+                if pg is not None:
+                    rc = lib.cqs_b200_search_sharded(ix._h, pg._h, qi, k, None, *po)
+                else:
+                    rc = lib.cqs_b200_search(ix._h, qi, k, None, *po)
+                lat.append(time.perf_counter() - t0)
+                check(rc)
+    (e2e_s,) = max_over_ranks(c, [e2e_s])
+    nq_timed = Q * steps
+    e2e_call = ("search_device + all_gather + merge" if (nccl or diag) else
+                (("cqs_b200_search_batch" if pg is None else "cqs_b200_search_batch_sharded") + f", one call per step of {Q} queries")
+                if batch_call else
+                (("cqs_b200_search" if pg is None else "cqs_b200_search_sharded") + ", one blocking call per query"))
+    return {"ms": ms, "per_rank_ms": per_rank_ms, "launches": int(launches), "clocks": clk.summary(),
+            "value": nq_timed / (ms / 1e3), "e2e_value": nq_timed / e2e_s, "nq_timed": nq_timed, "lanes": P,
+            "e2e_call": e2e_call, "batch_call": batch_call,
+            "p50_ms": float(np.median(lat) * 1e3) if lat else None,
+            "p95_ms": float(np.percentile(lat, 95) * 1e3) if lat else None}
+
+
+def single_record(c, t, *, metric, n_total, n_local, storage, k, Q, steps, warmup, workload, scaling, data, transport_note=None,
+                  traffic_key=None):
+    peak, peak_src = peaks()
+    elem = 4 if storage == "f32" else 2
+    alg_bytes = n_local * DIM * elem                       # per launch (one query over this rank's shard)
+    avg_launch_s = (t["ms"] / 1e3) / t["nq_timed"]
+    achieved = alg_bytes / avg_launch_s / 1e9
+    pg_used = c.world > 1
+    return {
+        "metric": metric, "value": t["value"], "unit": UNIT, "n_gpus": c.world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t["ms"] / steps, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": storage if storage != "bf16" else "bf16 rows x f32 query -> f32", "data": data,
+        "config": {"workload": workload, "queries_per_step": Q, "k": k, "row_sharded_over_gpus": c.world,
+                   "rows_total": n_total, "rows_per_gpu": n_local, "launch_lanes": t["lanes"],
+                   "per_rank_ms_timed_region": t["per_rank_ms"],
+                   **({"transport_note": transport_note} if transport_note else {}),
+                   "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",
+                   "collective": "none" if not pg_used else
+                                 "none: every scan kernel stores its top-k into the peers' mailboxes over NVLink, "
+                                 "waits for theirs and merges in its own tail (csrc/peer.cuh)"},
+        "clocks": t["clocks"],
+        "e2e": {"value": t["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
+                "d2h_bytes_per_step": Q * k * 12 + Q * 4},
+        "gpu_launches": t["launches"],
+        "e2e_call": t["e2e_call"],
+        "p50_ms_single_query_call": t["p50_ms"], "p95_ms_single_query_call": t["p95_ms"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(traffic_key) if traffic_key else None, "peak_source": peak_src,
+                     "kernel": "scan_topk_kernel", "algorithmic_bytes_per_launch": alg_bytes,
+                     "avg_launch_us": avg_launch_s * 1e6,
+                     "avg_launch_is": "timed region / launches = launch interval (CUDA events on the launching "
+                                      "stream); with 4 launch lanes the tail of a launch overlaps the next ones",
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "aggregate_GBs_all_gpus": achieved * c.world},
+    }
+
+
+def sharded_parity(c, ix, pg, queries, k, local_oracle, exact_oracle=None):
+    """In-run parity for a (possibly row-sharded) corpus.  Every rank: its LOCAL top-k
+    (cqs_b200_search on the shard) vs the CPU oracle of ITS shard; then the GLOBAL answer
+    (sharded search; plain search at N = 1) vs the merge of the per-shard oracle lists."""
+    from cqs_b200.sharded import merge_topk_host, search_sharded
+    P = queries.shape[0]
+    local = [ix.search_rows(queries[i], k) for i in range(P)]
+    loc = parity_summary(local, local_oracle.rows, local_oracle.scores)
+    all_loc = gather_objects(c, (local_oracle.rows, local_oracle.scores, loc["ok"]))
+    g_rows = np.full((P, k), EMPTY, np.uint64)
+    g_sc = np.full((P, k), -np.inf, np.float32)
+    for i in range(P):
+        s, r = merge_topk_host(np.stack([a[1][i] for a in all_loc]), np.stack([a[0][i] for a in all_loc]), k)
+        g_sc[i, :s.shape[0]] = s
+        g_rows[i, :r.shape[0]] = r
+    if pg is not None:
+        glob = [search_sharded(ix, pg, queries[i], k) for i in range(P)]
+    else:
+        glob = local
+    out = parity_summary(glob, g_rows, g_sc)
+    out["oracle"] = ("C port of the reference brute force (oracle/cqs_oracle.c, f64-accumulated dot), run on the same rows "
+                     "block by block during generation" + ("; per-shard lists merged with the reference order rule" if c.world > 1 else ""))
+    out["parity_queries"] = P
+    out["ranks_with_local_topk_ok"] = f"{sum(int(a[2]) for a in all_loc)}/{c.world}"
+    if exact_oracle is not None:
+        all_ex = gather_objects(c, (exact_oracle.rows, exact_oracle.scores))
+        e_rows = np.full((P, k), EMPTY, np.uint64)
+        for i in range(P):
+            s, r = merge_topk_host(np.stack([a[1][i] for a in all_ex]), np.stack([a[0][i] for a in all_ex]), k)
+            e_rows[i, :r.shape[0]] = r
+        out[f"recall_at_{k}_vs_f32_exact"] = recall_at_k(glob, e_rows)
+    return out, (g_rows, g_sc)
+
+
+# ---- batch (tensor-core) records ---------------------------------------------------------------
+def time_batch(c, ix, pg, queries, k, nq, steps, warmup):
+    """A step = one nq-query batch through the C ABI with host buffers (cqs_b200_search_batch /
+    _search_batch_sharded).  value: device time of the whole batch pipeline per call (candidate
+    scan, rescoring, exact re-runs, cross-shard gather/merge), CUDA events on the library's
+    stream, max over ranks; e2e: wall clock around the calls."""
+    from cqs_b200.capi import lib
+    from cqs_b200.sharded import search_batch_sharded
+    lib.cqs_b200_debug_last_batch_ms.restype = C.c_float
+    lib.cqs_b200_debug_last_batch_ms.argtypes = [C.c_void_p]
+    lib.cqs_b200_debug_last_batch_reruns.restype = C.c_uint32
+    lib.cqs_b200_debug_last_batch_reruns.argtypes = [C.c_void_p]
+    ix.set_timing(True)
+
+    def step(s):
+        q = queries[s * nq:(s + 1) * nq]
+        if pg is not None:
+            return search_batch_sharded(ix, pg, q, k)
+        return ix.search_batch_rows(q, k)
+
+    for s in range(warmup):
+        step(s)
+    barrier(c)
+    launches0 = lib.cqs_b200_kernel_launches()
+    clk = ClockSampler(c.local)
+    clk.__enter__()
+    dev_ms, reruns = 0.0, 0
+    barrier(c)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        step(warmup + s)
+        dev_ms += lib.cqs_b200_debug_last_batch_ms(ix._h)
+        reruns += lib.cqs_b200_debug_last_batch_reruns(ix._h)
+    barrier(c)
+    e2e_s = time.perf_counter() - t0
+    clk.__exit__()
+    launches = lib.cqs_b200_kernel_launches() - launches0
+    ix.set_timing(False)
+    dev_ms, e2e_s = max_over_ranks(c, [dev_ms, e2e_s])
+    all_reruns = gather_objects(c, int(reruns))
+    return {"dev_ms": dev_ms, "e2e_s": e2e_s, "launches": int(launches), "clocks": clk.summary(),
+            "reruns_per_rank": all_reruns, "step": step}
+
+
+def batch_record(c, t, *, name, n_total, n_local, storage, k, nq, steps, warmup, workload, scaling, data, traffic_key=None):
+    sus, burst, src = tensor_peaks()
+    flop = 2.0 * nq * n_local * DIM                      # per batch pipeline, per GPU
+    tf = flop / (t["dev_ms"] / steps / 1e3) / 1e12
+    world = c.world
+    footprint = n_local * DIM * {"bf16": 2, "bf16+f32": 6, "f32": 4}.get(storage, 2)
+    return {
+        "record": name,
+        "metric": f"queries_per_s_exact_top{k}_{n_total}x{DIM}_{storage}_batch{nq}",
+        "value": nq * steps / (t["dev_ms"] / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": t["dev_ms"] / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "bf16 x bf16 -> f32 (tcgen05), candidates re-scored in f32", "data": data,
+        "config": {"workload": workload, "queries_per_step": nq, "k": k, "rows_total": n_total, "rows_per_gpu": n_local,
+                   "row_sharded_over_gpus": world, "storage": storage, "hbm_footprint_bytes_per_gpu": footprint,
+                   "l2": f"per-GPU shard {n_local * DIM * 2 / 1e6:.0f} MB > 126 MB L2: no flush needed",
+                   "collective": "none" if world == 1 else "one gather+merge kernel per batch over NVLink peer memory (csrc/peer.cu)",
+                   "value_is": "device time of the whole batch pipeline per call — candidate scan, rescoring, exact re-runs "
+                               "of unproven queries, cross-shard gather/merge — CUDA events on the library's stream, max over ranks"},
+        "clocks": t["clocks"],
+        "e2e": {"value": nq * steps / t["e2e_s"], "unit": UNIT, "ms_per_batch": t["e2e_s"] / steps * 1e3,
+                "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12 + nq * 8},
+        "gpu_launches": t["launches"],
+        "batch_reruns": {"per_rank_total_over_timed_steps": t["reruns_per_rank"],
+                         "note": "queries whose candidate pool could not be proven complete and were re-run through the "
+                                 "exact single-query kernel; their time is inside value"},
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": sus, "unit": "TFLOP/s", "frac": tf / sus,
+                     "traffic": ncu_traffic(traffic_key) if traffic_key else None, "peak_source": src + ", sustained figure",
+                     "kernel": "scan_batch_kernel (+ threshold updates, rescore, re-runs)",
+                     "frac_of_burst_peak": tf / burst, "frac_of_nominal_2250": tf / 2250.0,
+                     "algorithmic_flop_per_launch": flop, "aggregate_TFLOPs_all_gpus": tf * world},
+    }
+
+
+def batch_parity(c, t, queries, nq, k, stored_rows, stored_scores, exact_rows=None):
+    """The batch call's answers for the parity queries (the first P queries of batch 0) vs the CPU oracle."""
+    P = stored_rows.shape[0]
+    r, s, n = t["step"](0)
+    res = [(r[i, :int(n[i])], s[i, :int(n[i])]) for i in range(P)]
+    out = parity_summary(res, stored_rows, stored_scores)
+    out["parity_queries"] = P
+    out["oracle"] = "C port of the reference brute force on the stored (bf16-rounded where storage is bf16) rows, f64-accumulated dot"
+    if exact_rows is not None:
+        out[f"recall_at_{k}_vs_f32_exact"] = recall_at_k(res, exact_rows)
+    return out
+
+
+# ---- hybrid record ----------------------------------------------------------------------------
+def gen_sparse_device(torch, dev, n, mean_nnz=200, seed=5):
+    """Doc-major CSR on the device: nnz ~ Poisson(200) clipped [20, 400], token ids
+    Zipf(1.1) without replacement inside a doc, ascending; weights log1p(relu(N(.8,.5))) > .01
+    (src/splade/mod.rs:721-727, :405-413)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    p = 1.0 / torch.arange(1, VOCAB + 1, device=dev, dtype=torch.float64) ** 1.1
+    cdf = torch.cumsum(p / p.sum(), 0).float()
+    W = int(mean_nnz * 1.6)
+    toks, ws, cnts = [], [], []
+    for b in range(0, n, 50_000):
+        m = min(50_000, n - b)
+        want = torch.clamp(torch.poisson(torch.full((m,), float(mean_nnz), device=dev), generator=g), 20, min(400, W)).long()
+        t = torch.searchsorted(cdf, torch.rand((m, W), device=dev, generator=g)).clamp_(0, VOCAB - 1)
+        t, _ = torch.sort(t, dim=1)
+        dup = torch.zeros_like(t, dtype=torch.bool)
+        dup[:, 1:] = t[:, 1:] == t[:, :-1]
+        rank = torch.cumsum((~dup).long(), 1)
+        w = torch.log1p(torch.relu(torch.randn((m, W), device=dev, generator=g) * 0.5 + 0.8))
+        keep = (~dup) & (rank <= want[:, None]) & (w > 0.01)
+        toks.append(t[keep].to(torch.int32))
+        ws.append(w[keep].to(torch.float32))
+        cnts.append(keep.sum(1))
+    tok = torch.cat(toks)
+    w = torch.cat(ws)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(torch.cat(cnts), 0)
+    return indptr, tok, w, cdf.cpu().numpy()
+
+
+def sparse_queries(rng, cdf_h, n, q_nnz):
+    out = []
+    for _ in range(n):
+        t = np.unique(np.searchsorted(cdf_h, rng.random(q_nnz * 2)).clip(0, VOCAB - 1))[:q_nnz]
+        out.append((t.astype(np.uint32), np.log1p(np.maximum(rng.normal(0.8, 0.5, t.shape[0]), 0.02)).astype(np.float32)))
+    return out
+
+
+def hybrid_record(c, ix, rows_host, sp, mode, steps, warmup, name):
+    """configs[4]: dense 1M x 768 f32 + SPLADE (30,522 vocab, ~200 nnz/doc), per-category alpha, pool 500.
+    A step = one cqs_b200_search_hybrid call (host query in, fused pool out)."""
+    from cqs_b200.capi import lib
+    from oracle import c_oracle as CO
+    from oracle import cqs_oracle as O
+    lib.cqs_b200_debug_last_batch_ms.restype = C.c_float
+    lib.cqs_b200_debug_last_batch_ms.argtypes = [C.c_void_p]
+    d_indptr, d_tok, d_w, cdf_h, h_indptr, h_tok, h_w, tok_count = sp
+    n = len(ix)
+    pool, q_nnz = 500, 64
+    t0 = time.perf_counter()
+    ix.sparse_attach_device(d_indptr.data_ptr(), d_tok.data_ptr(), d_w.data_ptr(), int(d_tok.shape[0]), VOCAB)
+    attach_s = time.perf_counter() - t0
+    rng = np.random.default_rng(17)
+    nqs = steps + warmup
+    dq = make_queries(nqs, 23, mode)
+    sq = sparse_queries(rng, cdf_h, nqs, q_nnz)
+    ix.set_timing(True)
+    for s in range(warmup):
+        ix.search_hybrid_rows(dq[s], sq[s][0], sq[s][1], ALPHAS[s % 9], pool)
+    c.torch.cuda.synchronize()
+    launches0 = lib.cqs_b200_kernel_launches()
+    clk = ClockSampler(c.local)
+    clk.__enter__()
+    dev_ms, lat, touched = 0.0, [], 0
+    t_all = time.perf_counter()
+    for s in range(warmup, nqs):
+        t0 = time.perf_counter()
+        ix.search_hybrid_rows(dq[s], sq[s][0], sq[s][1], ALPHAS[s % 9], pool)
+        lat.append(time.perf_counter() - t0)
+        dev_ms += lib.cqs_b200_debug_last_batch_ms(ix._h)
+        touched += int(tok_count[sq[s][0]].sum())
+    e2e_s = time.perf_counter() - t_all
+    clk.__exit__()
+    launches = lib.cqs_b200_kernel_launches() - launches0
+    ix.set_timing(False)
+    # ---- parity: dense pool vs the CPU port, sparse pool + fusion bit-exact ----
+    P = 4
+    union = np.unique(np.concatenate([sq[i][0] for i in range(P)]))
+    t0 = time.perf_counter()
+    sel = np.nonzero(np.isin(h_tok, union))[0]
+    sub_tok = h_tok[sel]
+    sub_doc = (np.searchsorted(h_indptr, sel, side="right") - 1).astype(np.uint32)
+    order = np.argsort(sub_tok, kind="stable")            # SpladeIndex::build for the touched tokens only
+    tptr = np.zeros(VOCAB + 1, np.uint64)
+    tptr[1:] = np.cumsum(np.bincount(sub_tok, minlength=VOCAB))
+    pdoc, pw = np.ascontiguousarray(sub_doc[order]), np.ascontiguousarray(h_w[sel][order])
+    build_s = time.perf_counter() - t0
+    dense_ok = sparse_ok = fused_ok = 0
+    cpu_dense_s = cpu_sparse_s = cpu_fuse_s = 0.0
+    worst = 0.0
+    for i in range(P):
+        a = ALPHAS[i % 9]
+        got = ix.search_hybrid_rows(dq[i], sq[i][0], sq[i][1], a, pool)
+        g_dr, g_ds = ix.search_rows(dq[i], pool)
+        g_sr, g_ss = ix.search_sparse_rows(sq[i][0], sq[i][1], pool)
+        t0 = time.perf_counter()
+        o_dr, o_ds, o_dn = CO.brute_force_batch(rows_host, dq[i:i + 1], pool, use_f64=True, threads=1)
+        cpu_dense_s += time.perf_counter() - t0
+        ident, near, err = compare_lists(g_dr, g_ds, o_dr[0, :int(o_dn[0])], o_ds[0, :int(o_dn[0])])
+        dense_ok += int(ident or near)
+        worst = max(worst, err if np.isfinite(err) else 1.0)
+        t0 = time.perf_counter()
+        o_sr, o_ss = CO.sparse_search(tptr, pdoc, pw, VOCAB, n, sq[i][0], sq[i][1], pool)
+        cpu_sparse_s += time.perf_counter() - t0
+        sparse_ok += int(g_sr.astype(np.int64).tolist() == o_sr.tolist() and
+                         np.array_equal(g_ss.view(np.uint32), o_ss.view(np.uint32)))
+        t0 = time.perf_counter()
+        want = O.fuse_hybrid(list(zip(g_dr.tolist(), g_ds.tolist())), list(zip(o_sr.tolist(), o_ss.tolist())), a, pool)
+        cpu_fuse_s += time.perf_counter() - t0
+        fused_ok += int(got["rows"].tolist() == [x["id"] for x in want] and
+                        np.array_equal(got["fused"].view(np.uint32),
+                                       np.asarray([x["fused"] for x in want], np.float32).view(np.uint32)))
+    peak, peak_src = peaks()
+    nt = nqs - warmup
+    alg_bytes = n * DIM * 4 + touched / nt * 12.0        # dense rows + (4 B doc ids + 8 B (doc, weight)) per touched posting
+    achieved = alg_bytes / (dev_ms / nt / 1e3) / 1e9
+    return {
+        "record": name,
+        "metric": f"queries_per_s_hybrid_dense_splade_alpha_{n}x{DIM}_f32_pool{pool}",
+        "value": nt / (dev_ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": nt, "warmup": warmup,
+        "ms_per_step": dev_ms / nt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic ({mode} dense rows; Zipf(1.1) SPLADE postings)",
+        "config": {"workload": f"hybrid: dense {n}x{DIM} f32 + SPLADE (vocab {VOCAB}, {int(d_tok.shape[0]) / n:.0f} nnz/doc, "
+                               f"{int(d_tok.shape[0]) / 1e6:.0f}M postings), query {q_nnz} tokens, per-category alpha, "
+                               f"pool {pool} (BASELINE configs[4])",
+                   "queries_per_step": 1, "pool_k": pool, "alphas": ALPHAS,
+                   "sparse_layout": "token-major postings (CSC), 4 B doc ids + 8 B (doc, weight) pairs; static block index for long lists",
+                   "postings_touched_per_query": touched / nt,
+                   "inverted_index_build_on_device_s": attach_s,
+                   "l2": "dense corpus 3072 MB > 126 MB L2: no flush needed",
+                   "value_is": "device time of one hybrid call (dense scan k=500, sparse bounds + accumulate, fusion), "
+                               "CUDA events on the library's stream"},
+        "clocks": clk.summary(),
+        "e2e": {"value": nt / e2e_s, "unit": UNIT, "p50_ms": float(np.median(lat) * 1e3),
+                "p95_ms": float(np.percentile(lat, 95) * 1e3),
+                "h2d_bytes_per_step": DIM * 4 + q_nnz * 8, "d2h_bytes_per_step": pool * 21 + 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("hybrid:1000000x768:f32:pool500"), "peak_source": peak_src,
+                     "kernel": "scan_topk_kernel (k=500) + sparse_bounds_kernel + sparse_search_kernel + fuse_pools_kernel",
+                     "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "parity": {"parity_queries": P, "dense_pool_ids_identical_or_near_tie": f"{dense_ok}/{P}",
+                   "dense_max_rel_score_err": worst, "sparse_pool_bit_exact": f"{sparse_ok}/{P}",
+                   "fused_pool_bit_exact_given_the_dense_pool": f"{fused_ok}/{P}",
+                   "ok": bool(dense_ok == P and sparse_ok == P and fused_ok == P and worst <= 1e-5),
+                   "oracle": "C port: brute force k=500 (f64 dot) + SpladeIndex::search_with_filter (src/splade/index.rs:223-291) "
+                             "on postings built by a stable sort of the touched tokens; fusion = numpy restatement of "
+                             "src/search/query.rs:914-1005"},
+        "cpu_baseline": {"value": 1.0 / ((cpu_dense_s + cpu_sparse_s + cpu_fuse_s) / P), "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{P} hybrid queries: dense brute force k={pool} over the full corpus {cpu_dense_s / P * 1e3:.0f} ms + "
+                                   f"sparse leg {cpu_sparse_s / P * 1e3:.1f} ms + fusion {cpu_fuse_s / P * 1e3:.1f} ms per query; "
+                                   f"partial inverted-index build (touched tokens only) {build_s:.1f} s not included"},
+    }
+
+
+# ---- reference arm ----------------------------------------------------------------------------
 def run_reference(args):
     """Reference arm: the oracle's C port of the brute-force path on host cores."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     from oracle import c_oracle as CO
     threads = CO.num_threads()
-    rng = np.random.default_rng(0x9E37)
     rows = np.empty((N_ROWS, DIM), np.float32)
-    for b in range(0, N_ROWS, 100_000):
-        blk = rng.random((min(100_000, N_ROWS - b), DIM), dtype=np.float32) * np.float32(2) - np.float32(1)
+    rng = np.random.default_rng(0x9E37)
+    for b in range(0, N_ROWS, BLK):
+        blk = rng.random((min(BLK, N_ROWS - b), DIM), dtype=np.float32) * np.float32(2) - np.float32(1)
         blk /= np.linalg.norm(blk, axis=1, keepdims=True)
         rows[b:b + blk.shape[0]] = blk
-    qper = max(threads, 1)  # one query per thread per step
-    queries = make_queries(qper * (args.steps + args.warmup), 11)
+    Q = args.queries_per_step or 64 * max(world, args.gpus)
+    queries = make_queries(Q * (args.steps + args.warmup), 7)
     for w in range(args.warmup):
-        CO.brute_force_batch(rows, queries[w * qper:(w + 1) * qper], K, use_f64=False, threads=threads)
+        CO.brute_force_batch(rows, queries[w * Q:(w + 1) * Q], K, use_f64=False, threads=threads)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        o = (args.warmup + s) * qper
-        CO.brute_force_batch(rows, queries[o:o + qper], K, use_f64=False, threads=threads)
+        o = (args.warmup + s) * Q
+        CO.brute_force_batch(rows, queries[o:o + Q], K, use_f64=False, threads=threads)
     dt = time.perf_counter() - t0
-    val = qper * args.steps / dt
-    sample = f"{qper} queries/step x {args.steps} steps over the full {N_ROWS}x{DIM} f32 corpus in RAM (no SQLite)"
+    val = Q * args.steps / dt
+    sample = f"{Q} queries/step x {args.steps} steps over the full {N_ROWS}x{DIM} f32 corpus in RAM (no SQLite), {threads} threads"
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"exact top-{K}, single query at a time, {N_ROWS}x{DIM} f32 (BASELINE configs[1])",
-                   "queries_per_step": qper},
+        "config": {"workload": WORKLOAD, "queries_per_step": Q, "k": K},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
-def run_batch(args):
-    """--workload batch: BASELINE configs[2] (10M x 768 bf16, 1024-query batches, top-20; N=1) and
-    configs[3]'s batch half (rows row-sharded over N GPUs; per-shard tensor-core scan + exact
-    rescoring, then ONE gather+merge kernel over NVLink peer memory).  A step = one batch through
-    the C ABI with host buffers (cqs_b200_search_batch / _search_batch_sharded)."""
-    import torch
-    import cqs_b200
-    from cqs_b200.capi import lib
-    from cqs_b200.sharded import PeerGroup, search_batch_sharded, shard_range
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    n_total = args.rows
-    row0, n_local = shard_range(n_total, world, rank)
-    nq = args.queries_per_step
-    ix = cqs_b200.B200Index(DIM, storage=args.storage, devices=[local], row_base=row0)
-    ix.reserve(n_local)
-    for blk in gen_rows_torch(torch, dev, row0, n_local):
-        ix.append_device(blk.data_ptr(), blk.shape[0])
-        del blk
-    ix.finalize()
-    ix.set_timing(True)
-    torch.cuda.empty_cache()
-    pg = PeerGroup.from_dist(dist, local, max_elems=nq * K) if world > 1 else None
-    lib.cqs_b200_debug_last_batch_ms.restype = C.c_float      # device ms of the last batch pipeline
-    lib.cqs_b200_debug_last_batch_ms.argtypes = [C.c_void_p]
-    queries = make_queries(nq * (args.steps + args.warmup), 7)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(s):
-        q = queries[s * nq:(s + 1) * nq]
-        if pg is not None:
-            return search_batch_sharded(ix, pg, q, K)
-        return ix.search_batch_rows(q, K)
-
-    for s in range(args.warmup):
-        step(s)
-    barrier()
-    launches0 = lib.cqs_b200_kernel_launches()
-    clk = ClockSampler(local)
-    clk.__enter__()
-    dev_ms = 0.0
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        last = step(args.warmup + s)
-        dev_ms += lib.cqs_b200_debug_last_batch_ms(ix._h)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clk.__exit__()
-    launches = lib.cqs_b200_kernel_launches() - launches0
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0].item()), float(t[1].item())
-    if rank == 0:
-        # sanity: the batch answer equals the single-query path on a few queries (N=1 only: the
-        # sharded single-query call is collective)
-        agree = None
-        if world == 1:
-            q = queries[(args.warmup + args.steps - 1) * nq:]
-            agree = sum(int(np.array_equal(last[0][i, :last[2][i]], ix.search_rows(q[i], K)[0])) for i in (0, 1, nq // 2, nq - 1))
-        peak_tf = 1668.9
-        src = "fallback"
-        try:
-            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak_tf, src = float(mp["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
-        flop = 2.0 * nq * n_local * DIM                      # per batch pipeline, per GPU
-        tf = flop / (dev_ms / args.steps / 1e3) / 1e12
-        emit({
-            "metric": f"queries_per_s_exact_top20_{n_total}x{DIM}_{args.storage}_batch{nq}",
-            "value": nq * args.steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (tcgen05), candidates re-scored in f32",
-            "data": "synthetic",
-            "config": {"workload": f"exact top-{K}, {nq}-query batches, {n_total}x{DIM} {args.storage} "
-                                   f"(BASELINE configs[2]/[3]), row-sharded over {world} GPU(s)",
-                       "rows_per_gpu": n_local,
-                       "l2": f"per-GPU shard {n_local * DIM * 2 / 1e6:.0f} MB > 126 MB L2: no flush needed",
-                       "collective": "none" if world == 1 else "one gather+merge kernel per batch over NVLink peer memory (csrc/peer.cu)",
-                       "value_is": "device time of the batch pipeline (CUDA events on the library's stream), max over ranks"},
-            "clocks": clk.summary(),
-            "e2e": {"value": nq * args.steps / e2e_s, "unit": UNIT, "ms_per_batch": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * K * 12 + nq * 8},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": ncu_traffic(f"scan_batch_kernel:{n_local}x{DIM}:{args.storage}:{nq}q"),
-                         "peak_source": src, "kernel": "scan_batch_kernel (+ threshold updates, rescore)",
-                         "frac_of_burst_peak": tf / 1668.9,
-                         "algorithmic_flop_per_launch": flop},
-            "batch_equals_single_query_path": None if agree is None else f"{agree}/4",
-        })
-    if pg is not None:
-        st = pg.status()
-        dist.barrier()
-        pg.close()
-        if st:
-            raise RuntimeError("peer exchange timed out during the run")
-    if world > 1:
-        dist.destroy_process_group()
-    ix.close()
+# ---- main ---------------------------------------------------------------------------------------
+ALL_RECORDS = ["single_k500", "hybrid_1M", "hybrid_1M_clustered", "batch_10M", "sharded_single", "sharded_batch",
+               "batch_10M_clustered"]
 
 
-def main():
+def build_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries-per-step", type=int, default=32)
-    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"])
-    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--queries-per-step", type=int, default=0, help="headline: queries per step (0 = 64 x N)")
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"], help="headline corpus storage")
+    ap.add_argument("--rows", type=int, default=N_ROWS, help="headline corpus rows")
+    ap.add_argument("--big-storage", default="bf16", choices=["bf16", "bf16+f32"],
+                    help="storage of the configs[2]/[3] corpora (10M / 12.5M-per-GPU rows)")
+    ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS, help="rows per GPU of the configs[3] records")
+    ap.add_argument("--batch-rows", type=int, default=BATCH_ROWS, help="rows of the configs[2] record (N = 1)")
+    ap.add_argument("--records", default="all", help="comma list out of: " + ",".join(ALL_RECORDS) + " | all | none")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl", "none"],
-                    help="N > 1: how the per-shard top-k lists are exchanged — 'peer' = inside the scan kernel "
+                    help="N > 1 headline: how the per-shard top-k lists are exchanged — 'peer' = inside the scan kernel "
                          "over NVLink peer memory (product path), 'nccl' = all_gather_into_tensor + merge kernel")
     ap.add_argument("--hnsw-rows", type=int, default=100_000,
                     help="rows of the corpus the CPU HNSW baseline is built on (0 = skip)")
-    ap.add_argument("--pipeline", type=int, default=4, choices=[1, 4],
-                    help="device-resident timing: 4 = one cqs_b200_search_many_device call per step, which issues "
-                         "the launches round-robin on the library's 4 launch lanes so the tail of one query's kernel "
-                         "(list merge, cross-shard exchange) overlaps the streaming phase of the next queries' kernels; "
-                         "1 = one call per query on one stream.  Every query is its own launch either way")
-    ap.add_argument("--workload", default="single", choices=["single", "batch"],
-                    help="single = BASELINE configs[1] (the headline, default); batch = configs[2]/[3]: "
-                         "1024-query tensor-core batches (use --rows 10000000 --storage bf16 --queries-per-step 1024)")
-    args = ap.parse_args()
+    ap.add_argument("--parity-queries", type=int, default=8)
+    return ap
+
+
+def main():
+    args = build_parser().parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
-    if args.workload == "batch":
-        if args.storage == "f32":
-            args.storage = "bf16"
-        return run_batch(args)
 
-    import torch
     import cqs_b200
     from cqs_b200.capi import lib, check
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    dist = None
+    from cqs_b200.sharded import PeerGroup, shard_range
+    c = make_ctx(args)
+    torch, world, rank = c.torch, c.world, c.rank
+    want = ALL_RECORDS if args.records == "all" else ([] if args.records == "none" else args.records.split(","))
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        want = [r for r in want if r in ("single_k500", "sharded_single", "sharded_batch")]
+    P = args.parity_queries
+    extra = []
+    t_start = time.perf_counter()
 
+    # ======== headline: configs[1] ========
     n_total = args.rows
-    per = (n_total + world - 1) // world
-    row0 = min(rank * per, n_total)
-    n_local = min(per, n_total - row0)
-    Q = args.queries_per_step
-
-    # ---- build this rank's shard (rows generated on device; not timed) ----
-    ix = cqs_b200.B200Index(DIM, storage=args.storage, devices=[local], row_base=row0)
-    ix.reserve(n_local)
-    keep_host = []
-    for blk in gen_rows_torch(torch, dev, row0, n_local):
-        ix.append_device(blk.data_ptr(), blk.shape[0])
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            keep_host.append(blk.cpu().numpy())
-        del blk
+    Q = args.queries_per_step or 64 * world
+    queries = make_queries(Q * (args.steps + args.warmup), 7)          # identical on every rank (same seed)
+    head_oracle = None if args.no_cpu_baseline else BlockOracle(queries[:P], K, c.cpu_threads)
+    need_host = rank == 0 and world == 1 and not args.no_cpu_baseline
+    ix, row0, n_local, rows_host = build_index(c, args.storage, n_total, "uniform",
+                                                oracles=[(head_oracle, "stored")] if head_oracle else (),
+                                                keep_host=not args.no_cpu_baseline)
     ix.finalize()
-    torch.cuda.empty_cache()
-
-    nq_total = Q * (args.steps + args.warmup)
-    queries = make_queries(nq_total, 7)          # identical on every rank (same seed)
-    d_queries = torch.from_numpy(queries).to(dev)
-    # a dedicated (non-default) stream: the library treats stream == NULL as "use the
-    # index's own stream", and CUDA events only see the stream they are recorded on
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    sp = C.c_void_p(stream.cuda_stream)
-    diag_no_exchange = world > 1 and args.transport == "none"   # diagnostic only: shards scanned, lists never merged
-    d_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
-    d_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
-    d_n = torch.empty((Q,), dtype=torch.int32, device=dev)
-    pg = None
-    transport_note = None
+    pg, transport_note = None, None
     if world > 1 and args.transport == "peer":
-        from cqs_b200.sharded import PeerGroup
         # CUDA IPC mailboxes; handles swapped over the process group.  If any rank cannot set them up
         # (no peer access / IPC in this container) every rank falls back to the all-gather transport.
-        pg = PeerGroup.from_dist(dist, local, strict=False)
+        pg = PeerGroup.from_dist(c.dist, c.local, max_elems=BATCH_Q * 64, strict=False)
         if pg is None:
             args.transport = "nccl"
             transport_note = "peer-memory setup failed on this box; fell back to all_gather_into_tensor + merge kernel"
-    P = 1 if (world > 1 and args.transport == "nccl") else args.pipeline
-    if world > 1:
-        g_sc = torch.empty((world, Q, K), dtype=torch.float32, device=dev)
-        g_rw = torch.empty((world, Q, K), dtype=torch.int64, device=dev)
-        m_sc = torch.empty((Q, K), dtype=torch.float32, device=dev)
-        m_rw = torch.empty((Q, K), dtype=torch.int64, device=dev)
-        m_n = torch.empty((Q,), dtype=torch.int32, device=dev)
+    log(f"headline corpus built ({n_local} rows/GPU), {time.perf_counter() - t_start:.0f}s")
+    t = time_single(c, ix, pg, queries, K, Q, args.steps, args.warmup, transport=args.transport)
+    head_metric = METRIC if (n_total == N_ROWS and args.storage == "f32") else f"queries_per_s_exact_top20_{n_total}x{DIM}_{args.storage}"
+    head_wl = WORKLOAD if (n_total == N_ROWS and args.storage == "f32") else \
+        f"exact top-{K}, single query at a time, {n_total}x{DIM} {args.storage}"
+    line = single_record(c, t, metric=head_metric, n_total=n_total, n_local=n_local, storage=args.storage, k=K, Q=Q,
+                         steps=args.steps, warmup=args.warmup, workload=head_wl, scaling="strong", data="synthetic",
+                         transport_note=transport_note, traffic_key=f"scan_topk_kernel:{n_local}x{DIM}:{args.storage}")
+    if world > 1 and args.transport != "peer":
+        line["config"]["collective"] = ("2 x all_gather_into_tensor per step (scores, rows) + merge kernel" if args.transport == "nccl"
+                                        else "DIAGNOSTIC transport none: per-shard lists are never merged; not a search result")
+    if head_oracle is not None and args.transport == "peer":
+        par, _ = sharded_parity(c, ix, pg, queries[:P], K, head_oracle)
+        line["parity"] = par
+    if need_host:
+        from oracle import c_oracle as CO
+        nb = 8
+        CO.brute_force_batch(rows_host, queries[:1], K, use_f64=False, threads=1)
+        t0 = time.perf_counter()
+        o_r, o_s, o_n = CO.brute_force_batch(rows_host, queries[:nb], K, use_f64=False, threads=1)
+        dt1 = time.perf_counter() - t0
+        thr = CO.num_threads()
+        nbt = max(2 * thr, 8)
+        t0 = time.perf_counter()
+        CO.brute_force_batch(rows_host, queries[:nbt], K, use_f64=False, threads=thr)
+        dtn = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": nb / dt1, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{nb} queries over the full {n_total}x{DIM} f32 corpus held in RAM (no SQLite), "
+                      f"1 thread as in src/search/query.rs:469; f32 SIMD dot",
+            "all_cores": {"value": nbt / dtn, "cores": thr, "queries": nbt}}
+        agree = sum(int(np.array_equal(ix.search_rows(queries[i], K)[0], o_r[i])) for i in range(nb))
+        line["cpu_baseline"]["ids_identical_queries"] = f"{agree}/{nb}"
+        if args.hnsw_rows > 0:
+            line["cpu_baseline"]["hnsw"] = hnsw_baseline(CO, rows_host, queries, args.hnsw_rows, n_total, thr,
+                                                         "uniform random rows")
+    else:
+        line["cpu_baseline"] = None
+    log(f"headline done: {line['value']:.0f} q/s, {time.perf_counter() - t_start:.0f}s")
 
-    def step_device(s: int):
-        """Q single-query scans, one kernel launch each, everything resident on the device.
-        P > 1: ONE library call per step (cqs_b200_search_many_device) issues the Q launches
-        round-robin on the library's launch lanes; N>1: every launch also pushes its top-k to the peers over
-        NVLink, waits for theirs and merges in its tail (transport 'peer').  P == 1: a call per
-        query on one stream; transport 'nccl': + one all-gather + merge kernel per step."""
-        base = s * Q
-        q0 = d_queries.data_ptr() + base * DIM * 4
-        if P > 1:
-            o_sc, o_rw, o_n = (m_sc, m_rw, m_n) if world > 1 else (d_sc, d_rw, d_n)
-            check(lib.cqs_b200_search_many_device(ix._h, pg._h if pg is not None else None, C.c_void_p(q0), Q, K, None,
-                                                  C.c_void_p(o_sc.data_ptr()), C.c_void_p(o_rw.data_ptr()),
-                                                  C.c_void_p(o_n.data_ptr()), sp))
-            return
-        if pg is not None:
-            for i in range(Q):
-                check(lib.cqs_b200_search_sharded_device(ix._h, pg._h, C.c_void_p(q0 + i * DIM * 4), K, None,
-                                                         C.c_void_p(m_sc.data_ptr() + i * K * 4),
-                                                         C.c_void_p(m_rw.data_ptr() + i * K * 8),
-                                                         C.c_void_p(m_n.data_ptr() + i * 4), sp))
-            return
-        for i in range(Q):
-            check(lib.cqs_b200_search_device(ix._h, C.c_void_p(q0 + i * DIM * 4), K, None,
-                                             C.c_void_p(d_sc.data_ptr() + i * K * 4),
-                                             C.c_void_p(d_rw.data_ptr() + i * K * 8),
-                                             C.c_void_p(d_n.data_ptr() + i * 4), sp))
-        if world > 1 and not diag_no_exchange:
-            dist.all_gather_into_tensor(g_sc, d_sc)
-            dist.all_gather_into_tensor(g_rw, d_rw)
-            check(lib.cqs_b200_merge_topk_device(local, C.c_void_p(g_sc.data_ptr()), C.c_void_p(g_rw.data_ptr()),
-                                                 world, Q, K, C.c_void_p(m_sc.data_ptr()),
-                                                 C.c_void_p(m_rw.data_ptr()), C.c_void_p(m_n.data_ptr()), sp))
+    # ======== single_k500: production pool size on the same corpus ========
+    if "single_k500" in want:
+        k5 = 500
+        steps5 = max(4, args.steps // 2)
+        t5 = time_single(c, ix, pg, queries, k5, Q, steps5, args.warmup, transport="peer")
+        r = single_record(c, t5, metric=f"queries_per_s_exact_top{k5}_{n_total}x{DIM}_{args.storage}", n_total=n_total,
+                          n_local=n_local, storage=args.storage, k=k5, Q=Q, steps=steps5, warmup=args.warmup,
+                          workload=f"exact top-{k5} (production pool, src/limits.rs:315-320), single query at a time, "
+                                   f"{n_total}x{DIM} {args.storage}", scaling="strong", data="synthetic")
+        r["record"] = "single_k500"
+        if head_oracle is not None and rows_host is not None:
+            o5 = BlockOracle(queries[:4], k5, c.cpu_threads)
+            o5.feed(rows_host if args.storage == "f32" else
+                    torch.from_numpy(rows_host).to(torch.bfloat16).to(torch.float32).numpy(), row0)
+            r["parity"], _ = sharded_parity(c, ix, pg, queries[:4], k5, o5)
+            cpu5 = max(gather_objects(c, o5.cpu_s))
+            r["cpu_baseline"] = {"value": 4 / cpu5, "unit": UNIT, "cores": c.cpu_threads * world, "kind": "port",
+                                 "sample": f"4 queries, k={k5}, full corpus ({world} shard(s) concurrently), f64 dot"}
+        extra.append(r)
+        log(f"single_k500 done, {time.perf_counter() - t_start:.0f}s")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ======== hybrid (N = 1) ========
+    sp = None
+    if world == 1 and ("hybrid_1M" in want or "hybrid_1M_clustered" in want):
+        d_indptr, d_tok, d_w, cdf_h = gen_sparse_device(torch, c.dev, n_local)
+        h_indptr, h_tok, h_w = d_indptr.cpu().numpy(), d_tok.cpu().numpy().astype(np.int64), d_w.cpu().numpy()
+        tok_count = np.bincount(h_tok, minlength=VOCAB)
+        sp = (d_indptr, d_tok, d_w, cdf_h, h_indptr, h_tok, h_w, tok_count)
+        log(f"sparse corpus: {h_tok.shape[0] / 1e6:.0f}M postings, {time.perf_counter() - t_start:.0f}s")
+    if world == 1 and "hybrid_1M" in want and rows_host is not None and args.storage == "f32":
+        extra.append(hybrid_record(c, ix, rows_host, sp, "uniform", steps=max(args.steps, 20), warmup=args.warmup, name="hybrid_1M"))
+        log(f"hybrid_1M done, {time.perf_counter() - t_start:.0f}s")
+    if pg is not None and pg.status() != 0:
+        raise RuntimeError("peer exchange timed out during the run")
+    ix.close()
+    del ix, rows_host
+    if world == 1 and "hybrid_1M_clustered" in want:
+        ixc, _, _, rows_c = build_index(c, "f32", n_total, "clustered", keep_host=True)
+        ixc.finalize()
+        r = hybrid_record(c, ixc, rows_c, sp, "clustered", steps=max(args.steps, 20), warmup=args.warmup, name="hybrid_1M_clustered")
+        if args.hnsw_rows > 0 and not args.no_cpu_baseline:
+            from oracle import c_oracle as CO
+            r["cpu_baseline"]["hnsw"] = hnsw_baseline(CO, rows_c, make_queries(1024, 29, "clustered"), args.hnsw_rows, n_total,
+                                                      CO.num_threads(), "clustered rows (256 centres)")
+        extra.append(r)
+        ixc.close()
+        del ixc, rows_c
+        log(f"hybrid_1M_clustered done, {time.perf_counter() - t_start:.0f}s")
+    sp = None
+    torch.cuda.empty_cache()
 
-    # ---- device-resident timing -------------------------------------------
-    for s in range(args.warmup):
-        step_device(s)
-    barrier()
-    launches0 = lib.cqs_b200_kernel_launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clk = ClockSampler(local)
-    clk.__enter__()
-    barrier()
-    e0.record(stream)
-    for s in range(args.steps):
-        step_device(args.warmup + s)           # the library joins its second lane back into `stream`
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = lib.cqs_b200_kernel_launches() - launches0
-    per_rank_ms = [ms]
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        allms = torch.empty((world,), device=dev)
-        dist.all_gather_into_tensor(allms, t)
-        per_rank_ms = [float(x) for x in allms.cpu().tolist()]
-        ms = max(per_rank_ms)
-    nq_timed = Q * args.steps
-    value = nq_timed / (ms / 1e3)
-
-    # ---- end to end through the C ABI with host buffers -----------------------
-    out_rows = np.empty(K, np.uint64)
-    out_sc = np.empty(K, np.float32)
-    out_n = C.c_uint32(0)
-    lat = []
-    h_pin = torch.empty((Q, K), dtype=torch.float32).pin_memory() if world > 1 else None
-    h_pin_r = torch.empty((Q, K), dtype=torch.int64).pin_memory() if world > 1 else None
-    h_q = torch.from_numpy(queries).pin_memory()
-
-    q_base = queries.ctypes.data
-    p_rows, p_sc, p_n = out_rows.ctypes.data_as(C.c_void_p), out_sc.ctypes.data_as(C.c_void_p), C.byref(out_n)
-    search = lib.cqs_b200_search
-
-    search_sh = lib.cqs_b200_search_sharded
-    b_rows = np.empty((Q, K), np.uint64)
-    b_sc = np.empty((Q, K), np.float32)
-    b_n = np.zeros(Q, np.uint32)
-    pb_rows, pb_sc, pb_n = (b_rows.ctypes.data_as(C.c_void_p), b_sc.ctypes.data_as(C.c_void_p),
-                            b_n.ctypes.data_as(C.c_void_p))
-
-    batch_call = args.storage == "f32"
-
-    def step_e2e(s: int):
-        """One public batch call per step: Q host queries in, Q host top-k lists out (H2D of the
-        queries, Q scan launches, D2H of the results, all inside the call)."""
-        base = s * Q
-        qp = C.c_void_p(q_base + base * DIM * 4)
-        if world > 1 and pg is None:
-            # transport 'nccl': host queries -> H2D (pinned) -> scans -> all-gather -> merge -> D2H
-            d_queries[base:base + Q].copy_(h_q[base:base + Q], non_blocking=True)
-            step_device(s)
-            h_pin.copy_(m_sc, non_blocking=True)
-            h_pin_r.copy_(m_rw, non_blocking=True)
-            torch.cuda.synchronize()
-        elif not batch_call:
-            # bf16 storage: a batch call would switch to the tensor-core algorithm, which is a different
-            # workload (configs[2]); stay with one blocking single-query call per query
-            for i in range(Q):
-                qi = C.c_void_p(q_base + (base + i) * DIM * 4)
-                if pg is not None:
-                    check(search_sh(ix._h, pg._h, qi, K, None, p_rows, p_sc, p_n))
-                else:
-                    check(search(ix._h, qi, K, None, p_rows, p_sc, p_n))
-        elif pg is not None:
-            check(lib.cqs_b200_search_batch_sharded(ix._h, pg._h, qp, Q, K, None, pb_rows, pb_sc, pb_n))
-        else:
-            check(lib.cqs_b200_search_batch(ix._h, qp, Q, K, None, pb_rows, pb_sc, pb_n))
-
-    def latency_pass(nq: int):
-        """Per-query latency of the blocking single-query call (VectorIndex::search shape):
-        host query in, host top-k out, one launch, result polled from host-mapped memory."""
-        for i in range(nq):
-            qp = C.c_void_p(q_base + i * DIM * 4)
-            t0 = time.perf_counter()
-            if pg is not None:
-                rc = search_sh(ix._h, pg._h, qp, K, None, p_rows, p_sc, p_n)
-            else:
-                rc = search(ix._h, qp, K, None, p_rows, p_sc, p_n)
-            lat.append(time.perf_counter() - t0)
-            if rc:
-                check(rc)
-
-    for s in range(args.warmup):
-        step_e2e(s)
-    lat.clear()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_e2e(args.warmup + s)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clk.__exit__()
-    if world == 1 or pg is not None:
-        latency_pass(16)
-        lat.clear()
-        latency_pass(min(nq_total, 128))
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = nq_timed / e2e_s
+    big_uniform = [n for n in want if n in ("batch_10M", "sharded_single", "sharded_batch")]
+    if big_uniform:
+        extra.extend(big_records(c, args, pg, "uniform", big_uniform, P, t_start))
+        log(f"big uniform records done, {time.perf_counter() - t_start:.0f}s")
+    if "batch_10M_clustered" in want and world == 1:
+        extra.extend(big_records(c, args, pg, "clustered", ["batch_10M_clustered"], P, t_start))
+        log(f"big clustered records done, {time.perf_counter() - t_start:.0f}s")
 
     if rank == 0:
-        peak, peak_src = peaks()
-        elem = 4 if args.storage == "f32" else 2
-        ld = DIM
-        alg_bytes = n_local * ld * elem                    # per launch (one query over this rank's shard)
-        scan_launches = nq_timed
-        # average duration of the scan launch over the timed region (CUDA events on the
-        # launching stream; includes the 3 KB query staging copy that precedes each launch)
-        avg_launch_s = (ms / 1e3) / scan_launches
-        achieved = alg_bytes / avg_launch_s / 1e9
-        line = {
-            "metric": METRIC if (n_total == N_ROWS and args.storage == "f32") else
-                      f"queries_per_s_exact_top20_{n_total}x{DIM}_{args.storage}",
-            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": args.storage, "data": "synthetic",
-            "config": {"workload": f"exact top-{K}, single query at a time, {n_total}x{DIM} {args.storage} "
-                                   f"(BASELINE configs[1]), row-sharded over {world} GPU(s)",
-                       "queries_per_step": Q, "rows_per_gpu": n_local,
-                       "launch_lanes": P, "per_rank_ms_timed_region": per_rank_ms,
-                       **({"transport_note": transport_note} if transport_note else {}),
-                       **({"DIAGNOSTIC": "transport none: per-shard lists are never merged; not a search result"}
-                          if diag_no_exchange else {}),
-                       "l2": f"per-GPU shard {alg_bytes / 1e6:.0f} MB > 126 MB L2: no flush needed",
-                       "collective": "none" if world == 1 else (
-                           "none: every scan kernel stores its top-k into the peers' mailboxes over NVLink, "
-                           "waits for theirs and merges in its own tail (csrc/peer.cuh)" if pg is not None else
-                           "2 x all_gather_into_tensor per step (scores, rows) + merge kernel")},
-            "clocks": clk.summary(),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Q * DIM * 4,
-                    "d2h_bytes_per_step": Q * K * 12 + (Q * 4 if (world == 1 or pg is not None) else 0)},
-            "gpu_launches": int(launches),
-            "e2e_call": (("cqs_b200_search_batch" if world == 1 else "cqs_b200_search_batch_sharded" if pg is not None
-                          else "search_device + all_gather + merge") + f", one call per step of {Q} queries")
-                        if (batch_call or (world > 1 and pg is None)) else
-                        (("cqs_b200_search" if world == 1 else "cqs_b200_search_sharded") + ", one blocking call per query"),
-            "p50_ms_single_query_call": float(np.median(lat) * 1e3) if lat else None,
-            "p95_ms_single_query_call": float(np.percentile(lat, 95) * 1e3) if lat else None,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": ncu_traffic(f"scan_topk_kernel:{n_local}x{DIM}:{args.storage}"),
-                         "peak_source": peak_src,
-                         "kernel": "scan_topk_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                         "avg_launch_us": avg_launch_s * 1e6,
-                         "avg_launch_is": "timed region / launches = launch interval (CUDA events on the launching "
-                                          "stream); with 4 launch lanes the tail of a launch overlaps the next ones",
-                         "frac_of_nominal_8TBs": achieved / 8000.0},
-        }
-        if world == 1 and not args.no_cpu_baseline and keep_host:
-            from oracle import c_oracle as CO
-            rows_h = np.concatenate(keep_host)
-            nb = 8
-            CO.brute_force_batch(rows_h, queries[:1], K, use_f64=False, threads=1)
-            t0 = time.perf_counter()
-            o_r, o_s, o_n = CO.brute_force_batch(rows_h, queries[:nb], K, use_f64=False, threads=1)
-            dt1 = time.perf_counter() - t0
-            thr = CO.num_threads()
-            nbt = max(2 * thr, 8)
-            t0 = time.perf_counter()
-            CO.brute_force_batch(rows_h, queries[:nbt], K, use_f64=False, threads=thr)
-            dtn = time.perf_counter() - t0
-            line["cpu_baseline"] = {
-                "value": nb / dt1, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"{nb} queries over the full {n_total}x{DIM} f32 corpus held in RAM (no SQLite), "
-                          f"1 thread as in src/search/query.rs:469; f32 SIMD dot",
-                "all_cores": {"value": nbt / dtn, "cores": thr, "queries": nbt}}
-            # the timed GPU path agrees with the CPU port on the sample
-            chk_r = np.empty(K, np.uint64); chk_s = np.empty(K, np.float32); chk_n = C.c_uint32(0)
-            agree = 0
-            for i in range(nb):
-                check(lib.cqs_b200_search(ix._h, queries[i].ctypes.data_as(C.c_void_p), K, None,
-                                          chk_r.ctypes.data_as(C.c_void_p), chk_s.ctypes.data_as(C.c_void_p),
-                                          C.byref(chk_n)))
-                agree += int(np.array_equal(chk_r, o_r[i]))
-            line["cpu_baseline"]["ids_identical_queries"] = f"{agree}/{nb}"
-            if args.hnsw_rows > 0:
-                # the reference's default CPU index (HNSW, tier parameters of src/hnsw/mod.rs:104-112),
-                # restated in oracle/hnsw_baseline.c; approximate => speed baseline only, recall reported
-                hn = min(args.hnsw_rows, n_total)
-                t0 = time.perf_counter()
-                hn_index = CO.Hnsw(rows_h[:hn], threads=thr)
-                build_s = time.perf_counter() - t0
-                nqh = 200
-                ids1, _, n1, lat1 = hn_index.search(queries[:nqh], K, threads=1)
-                t0 = time.perf_counter()
-                hn_index.search(queries[:nqh * 4], K, threads=thr)
-                dt_all = time.perf_counter() - t0
-                exact_r, _, _ = CO.brute_force_batch(rows_h[:hn], queries[:nqh], K, use_f64=False, threads=thr)
-                hits = sum(len(set(exact_r[i].tolist()) & set(ids1[i, :n1[i]].tolist())) for i in range(nqh))
-                line["cpu_baseline"]["hnsw"] = {
-                    "rows": hn, "M": hn_index.M, "ef_construction": hn_index.efC, "ef_search": hn_index.efS,
-                    "build_s": build_s, "p50_ms": float(np.median(lat1) * 1e3),
-                    "p95_ms": float(np.percentile(lat1, 95) * 1e3),
-                    "value": float(nqh / lat1.sum()), "unit": UNIT, "cores": 1,
-                    "all_cores": {"value": nqh * 4 / dt_all, "cores": thr},
-                    "recall_at_20_vs_exact": hits / (nqh * K),
-                    "sample": f"graph over the first {hn} rows of the corpus (bounded build time), {nqh} queries, "
-                              "approximate: speed baseline only"}
-                hn_index.close()
+        line["extra"] = extra
+        line["bench_wall_s"] = time.perf_counter() - t_start
         emit(line)
     if pg is not None:
-        if pg.status() != 0:
-            raise RuntimeError("peer exchange timed out during the run")
-        dist.barrier()
+        c.dist.barrier()
         pg.close()
     if world > 1:
-        dist.destroy_process_group()
-    ix.close()
+        c.dist.destroy_process_group()
+
+
+# ======== configs[2] / configs[3]: the big bf16 corpora ========
+def big_records(c, args, pg, mode, names, P, t_start):
+    """One 12.5M-rows-per-GPU corpus; at N = 1 its first 10M rows are configs[2] (the index is
+    finalized at 10M rows, measured, re-opened and extended — the TieredIndex::extend path)."""
+    import cqs_b200
+    from cqs_b200.capi import lib, check
+    from cqs_b200.sharded import shard_range
+    torch, world, rank = c.torch, c.world, c.rank
+    storage = args.big_storage
+    n_big = args.shard_rows * world
+    row0b, nlb = shard_range(n_big, world, rank)
+    steps_b, warm_b = 4, 3
+    bq = make_queries(BATCH_Q * (steps_b + warm_b), 101, mode)
+    pq = bq[:P]                                         # parity queries = head of batch 0
+    o_stored = BlockOracle(pq, K, c.cpu_threads)
+    o_exact = BlockOracle(pq, K, c.cpu_threads) if storage == "bf16" else None
+    oracles = [(o_stored, "stored")] + ([(o_exact, "exact")] if o_exact else [])
+    data = f"synthetic ({mode})"
+    want_sharded = mode == "uniform" and any(n.startswith("sharded") for n in names)
+    want10 = world == 1 and any(n.startswith("batch_10M") for n in names) and (args.batch_rows < nlb or not want_sharded)
+    ixb = cqs_b200.B200Index(DIM, storage=storage, devices=[c.local], row_base=row0b)
+    ixb.reserve(nlb)
+    recs = []
+    finalized = False
+
+    def measure_batch(name, n_tot, n_loc, pgb, cfg):
+        tb = time_batch(c, ixb, pgb, bq, K, BATCH_Q, steps_b, warm_b)
+        r = batch_record(c, tb, name=name, n_total=n_tot, n_local=n_loc, storage=storage, k=K, nq=BATCH_Q, steps=steps_b,
+                         warmup=warm_b, workload=cfg, scaling="weak", data=data,
+                         traffic_key=f"scan_batch_kernel:{n_loc}x{DIM}:{storage}:{BATCH_Q}q")
+        return r, tb
+
+    for done in fill_index(c, ixb, storage, row0b, nlb, mode, oracles):
+        if want10 and done == min(args.batch_rows, nlb):
+            s_rows, s_sc, s_cpu, s_fed = o_stored.snapshot()
+            e_rows = o_exact.snapshot()[0] if o_exact else None
+            ixb.finalize()
+            finalized = True
+            torch.cuda.empty_cache()
+            log(f"{mode}: {done} rows built, measuring configs[2], {time.perf_counter() - t_start:.0f}s")
+            r, tb = measure_batch("batch_10M" if mode == "uniform" else "batch_10M_clustered", done, done, None,
+                                  f"exact top-{K}, {BATCH_Q}-query batches, {done}x{DIM} {storage} (BASELINE configs[2])")
+            r["parity"] = batch_parity(c, tb, bq, BATCH_Q, K, s_rows, s_sc, e_rows)
+            r["cpu_baseline"] = {"value": P / s_cpu, "unit": UNIT, "cores": c.cpu_threads, "kind": "port",
+                                 "sample": f"{P} queries over the full {s_fed}x{DIM} corpus, f64-accumulated dot, fed block by block"}
+            recs.append(r)
+            if not want_sharded:
+                break
+            if done < nlb:
+                check(lib.cqs_b200_reopen(ixb._h))        # extend in place: reopen, append, finalize
+                finalized = False
+    if not finalized:
+        ixb.finalize()
+    torch.cuda.empty_cache()
+    if want_sharded:
+        log(f"{mode}: {nlb} rows/GPU built, measuring configs[3], {time.perf_counter() - t_start:.0f}s")
+        par, (g_rows, g_sc) = sharded_parity(c, ixb, pg, pq, K, o_stored, o_exact)
+        all_cpu = gather_objects(c, (o_stored.cpu_s, o_stored.rows_fed))
+        cpu_b = {"value": P / max(a[0] for a in all_cpu), "unit": UNIT, "cores": c.cpu_threads * world, "kind": "port",
+                 "sample": f"{P} queries over the full {n_big}x{DIM} corpus ({world} shard(s) scored concurrently on "
+                           f"{c.cpu_threads} threads each), f64-accumulated dot, fed block by block"}
+        if "sharded_single" in names:
+            Qs, steps_s = 16, 12
+            sq_ = make_queries(Qs * (steps_s + 3), 103, mode)
+            ts = time_single(c, ixb, pg, sq_, K, Qs, steps_s, 3)
+            r = single_record(c, ts, metric=f"queries_per_s_exact_top{K}_{n_big}x{DIM}_{storage}", n_total=n_big, n_local=nlb,
+                              storage=storage, k=K, Q=Qs, steps=steps_s, warmup=3,
+                              workload=f"exact top-{K}, single query at a time, {n_big}x{DIM} {storage} row-sharded over "
+                                       f"{world} GPU(s), {nlb} rows per GPU (BASELINE configs[3]; 100M rows at N = 8)",
+                              scaling="weak", data=data, traffic_key=f"scan_topk_kernel:{nlb}x{DIM}:{storage}")
+            r["record"] = "sharded_single"
+            r["parity"] = par
+            r["cpu_baseline"] = cpu_b
+            r["roofline"]["target"] = ">= 0.80 of aggregate nominal HBM (north star)"
+            recs.append(r)
+        if "sharded_batch" in names:
+            r, tb = measure_batch("sharded_batch", n_big, nlb, pg,
+                                  f"exact top-{K}, {BATCH_Q}-query batches, {n_big}x{DIM} {storage} row-sharded over {world} "
+                                  f"GPU(s), {nlb} rows per GPU (BASELINE configs[3])")
+            r["parity"] = batch_parity(c, tb, bq, BATCH_Q, K, g_rows, g_sc, None)
+            if f"recall_at_{K}_vs_f32_exact" in par:
+                r["parity"][f"recall_at_{K}_vs_f32_exact"] = par[f"recall_at_{K}_vs_f32_exact"]
+            r["cpu_baseline"] = cpu_b
+            r["roofline"]["target"] = ">= 0.60 tensor-pipe utilisation (north star)"
+            recs.append(r)
+        if pg is not None and pg.status():
+            raise RuntimeError("peer exchange timed out during the run")
+    ixb.close()
+    torch.cuda.empty_cache()
+    return recs
+
+
+def hnsw_baseline(CO, rows_h, queries, hnsw_rows, n_total, thr, what):
+    """The reference's default CPU index (HNSW, tier parameters of src/hnsw/mod.rs:104-112), restated in
+    oracle/hnsw_baseline.c; approximate => speed baseline only, recall reported."""
+    hn = min(hnsw_rows, n_total)
+    t0 = time.perf_counter()
+    hn_index = CO.Hnsw(rows_h[:hn], threads=thr)
+    build_s = time.perf_counter() - t0
+    nqh = 200
+    ids1, _, n1, lat1 = hn_index.search(queries[:nqh], K, threads=1)
+    t0 = time.perf_counter()
+    hn_index.search(queries[:nqh * 4], K, threads=thr)
+    dt_all = time.perf_counter() - t0
+    exact_r, _, _ = CO.brute_force_batch(rows_h[:hn], queries[:nqh], K, use_f64=False, threads=thr)
+    hits = sum(len(set(exact_r[i].tolist()) & set(ids1[i, :n1[i]].tolist())) for i in range(nqh))
+    out = {"rows": hn, "M": hn_index.M, "ef_construction": hn_index.efC, "ef_search": hn_index.efS,
+           "build_s": build_s, "p50_ms": float(np.median(lat1) * 1e3), "p95_ms": float(np.percentile(lat1, 95) * 1e3),
+           "value": float(nqh / lat1.sum()), "unit": UNIT, "cores": 1,
+           "all_cores": {"value": nqh * 4 / dt_all, "cores": thr},
+           "recall_at_20_vs_exact": hits / (nqh * K),
+           "sample": f"graph over the first {hn} rows of the corpus ({what}; bounded build time), {nqh} queries, "
+                     "approximate: speed baseline only"}
+    hn_index.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -1707,6 +1707,7 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   // dense leg: a malformed query yields an EMPTY dense pool (src/cagra.rs:458-470);
   // the sparse leg still runs (search_hybrid_inner calls both unconditionally).
   const bool dense_ok = query_is_finite(query, ix->dim);
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev_b0, s.stream));
   CK(ix, cudaMemsetAsync(s.d_out_n, 0, 4, s.stream));
   CK(ix, cudaMemsetAsync(s.d_sp_n, 0, 4, s.stream));
   if (peer) CK(ix, cudaMemsetAsync(s.d_spm_n, 0, 4, s.stream));
@@ -1744,9 +1745,12 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   f.d_out_rows = s.d_f_rows; f.d_out_fused = s.d_f_fused; f.d_out_dense = s.d_f_dense;
   f.d_out_sparse_raw = s.d_f_sraw; f.d_out_present = s.d_f_present; f.d_out_n = s.d_f_n;
   CK(ix, launch_fuse_pools(f, s.stream));
+  if (ix->timing) CK(ix, cudaEventRecord(s.ev_b1, s.stream));
   rc = copy_fused_out(ix, s, pool_k, out_rows, out_fused, out_dense, out_sparse_raw, out_present,
                       out_n, s.stream);
   if (rc) return rc;
+  // device time of the whole hybrid pipeline (both legs + fusion), read like the batch timer
+  if (ix->timing) CK(ix, cudaEventElapsedTime(&ix->last_batch_ms, s.ev_b0, s.ev_b1));
   if (peer) {
     uint32_t st = 0;
     CK(ix, cudaMemcpy(&st, peer->d_status, sizeof st, cudaMemcpyDeviceToHost));
