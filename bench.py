@@ -940,7 +940,7 @@ def main():
     # ======== headline: configs[1] ========
     n_total = args.rows
     Q = args.queries_per_step or 64 * world
-    queries = make_queries(Q * (args.steps + args.warmup), 7)          # identical on every rank (same seed)
+    queries = make_queries(Q * (max(args.steps, 4) + args.warmup), 7)  # identical on every rank (same seed)
     head_oracle = None if args.no_cpu_baseline else BlockOracle(queries[:P], K, c.cpu_threads)
     need_host = rank == 0 and world == 1 and not args.no_cpu_baseline
     ix, row0, n_local, rows_host = build_index(c, args.storage, n_total, "uniform",

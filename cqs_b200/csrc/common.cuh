@@ -208,12 +208,18 @@ struct TopK {
   // valid lower bound of the k-th best — with one histogram pass instead of a sort.
   // Keys live in registers (ITEMS per thread, ITEMS * nthr >= cap) while the buffer is
   // rewritten.  Buckets are linear in key space between the current min and max.
+  //
+  // m / vm_out (optional): also reports a lower bound of the m-th best key held BEFORE the
+  // shrink (m <= k): at least m keys of the buffer are >= *vm_out (0 when fewer than m keys).
+  // The scan kernel publishes it so that the CTAs can share a global threshold.
   template <int ITEMS>
-  __device__ __forceinline__ void select(uint32_t k) {
+  __device__ __forceinline__ void select(uint32_t k, uint32_t m = 0, ckey_t* vm_out = nullptr) {
     g.sync();
     const uint32_t n = min(*cnt, cap);
     if (n <= kRankSortMax || n <= k || hist == nullptr) {
       compact(k);
+      if (vm_out && g.tid == 0) *vm_out = (m > 0 && m <= min(n, k)) ? buf[m - 1] : 0;
+      g.sync();
       return;
     }
     const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
@@ -279,10 +285,20 @@ struct TopK {
         acc += h;
       }
     }
+    if (vm_out && m > 0 && before < m && m <= before + local) {  // likewise for the m-th best (m <= k <= n)
+      uint32_t acc = before;
+      for (uint32_t j = 0; j < per; ++j) {
+        acc += hist[b_hi - j];
+        if (acc >= m) {
+          *vm_out = lo + ((ckey_t)(b_hi - j) << sh);   // lower edge of its bucket: >= m keys are >= this
+          break;
+        }
+      }
+    }
     g.sync();
     const uint32_t bstar = aux32[0], n_keep = aux32[1];
     if (n_keep > (cap >> 1)) {  // pathological ties: fall back to the exact sort (buffer untouched so far)
-      compact(k);
+      compact(k);               // (*vm_out, if any, stays: it was derived from the untouched buffer)
       return;
     }
     uint32_t mine = 0;
@@ -305,6 +321,43 @@ struct TopK {
     if (g.tid == 0) {
       *cnt = n_keep;
       *thr = lo + ((ckey_t)bstar << sh) - 1;  // every kept key is > thr; thr >= the previous threshold
+    }
+    g.sync();
+  }
+  // Collective: drop every key that is not > t (a valid lower bound of the final k-th best key
+  // obtained elsewhere, e.g. the global threshold shared by the scan CTAs); raises thr to t.
+  template <int ITEMS>
+  __device__ __forceinline__ void prune(ckey_t t) {
+    g.sync();
+    const uint32_t n = min(*cnt, cap);
+    const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
+    uint32_t* aux32 = hist + kSelBuckets + 64;
+    ckey_t r[ITEMS];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const uint32_t i = j * g.nthr + g.tid;
+      r[j] = (i < n) ? buf[i] : 0;
+      if (r[j] > t) ++mine;
+    }
+    uint32_t inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) aux32[2 + warp] = inc;
+    g.sync();
+    uint32_t off = inc - mine, total = 0;
+    for (uint32_t w = 0; w < nwarps; ++w) {
+      if (w < warp) off += aux32[2 + w];
+      total += aux32[2 + w];
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (r[j] > t) buf[off++] = r[j];
+    if (g.tid == 0) {
+      *cnt = total;
+      if (t > *thr) *thr = t;
     }
     g.sync();
   }
@@ -355,12 +408,14 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
                                                         const uint32_t* partial_cnt, uint32_t G,
                                                         uint64_t row_base, float* out_scores,
                                                         uint64_t* out_rows, uint32_t* out_n,
-                                                        unsigned long long* trace = nullptr) {
+                                                        unsigned long long* trace = nullptr,
+                                                        ckey_t thr0 = 0) {
+  // thr0: a lower bound of the global k-th best key the caller already knows (0 = none)
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
   for (uint32_t l = tid; l < G; l += T) s_pos[l] = __ldcg(partial_cnt + l);
   if (tid == 0) {
     *tk.cnt = 0;
-    *tk.thr = 0;
+    *tk.thr = thr0;
   }
   tk.g.sync();
   // ---- 1. column bounds (two columns: the first m with ceil(k/m) <= G, and 2m) ----
@@ -443,6 +498,7 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
   }
   topk_finish<ITEMS>(tk, k);
   if (trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
+  if (out_scores == nullptr) return;   // caller post-processes the sorted keys in tk.buf[0..*tk.cnt)
   uint32_t n = *tk.cnt;
   for (uint32_t i = tid; i < k; i += T) {
     if (i < n) {

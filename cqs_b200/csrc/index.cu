@@ -74,6 +74,7 @@ struct Shard {
     ckey_t* d_partial = nullptr;
     uint32_t* d_partial_cnt = nullptr;
     uint32_t* d_done = nullptr;
+    ckey_t* d_col = nullptr;       // [kMaxGrid], zero between launches
     float* d_query = nullptr;      // [ld], zero padded beyond dim
     cudaEvent_t ev = nullptr;      // recorded after the last launch that used this set
     cudaStream_t stream = nullptr;
@@ -128,6 +129,7 @@ struct Shard {
   uint32_t* d_bm_n = nullptr;
   float* d_maxnorm = nullptr;     // [1]
   float max_row_norm = 0.f;
+  float max_row_delta = 0.f;      // STORAGE_BF16_F32: max |f32 row - bf16 shadow row|_2
   // structured filter / per-row signals (cqs_b200_set_row_meta / _signals)
   uint8_t* d_ctype = nullptr;
   uint8_t* d_lang = nullptr;
@@ -154,6 +156,7 @@ struct cqs_b200_index {
   float last_kernel_ms = 0.f;
   bool timing = false;   // record CUDA events around the dominant kernel (cqs_b200_set_timing)
   float max_note_boost = 1.f, max_importance = 1.f;
+  uint64_t shadow_reruns = 0;       // single-query shadow scans re-run on the f32 master (cumulative)
   uint32_t batch_reruns_total = 0;  // queries the batched path sent to the exact kernel (cumulative)
   uint32_t last_batch_reruns = 0;   // ... by the most recent batch call
   // Device time of the most recent tensor-core batch call, CUDA events on the shard's stream from
@@ -195,7 +198,7 @@ static void free_shard(Shard& s) {
   if (s.stream) cudaStreamSynchronize(s.stream);
   cudaFree(s.d_rows); cudaFree(s.d_rows16); cudaFree(s.d_stage); cudaFree(s.d_bitset);
   for (auto& c : s.scr) {
-    cudaFree(c.d_partial); cudaFree(c.d_partial_cnt); cudaFree(c.d_done); cudaFree(c.d_query);
+    cudaFree(c.d_partial); cudaFree(c.d_partial_cnt); cudaFree(c.d_done); cudaFree(c.d_query); cudaFree(c.d_col);
     if (c.ev) cudaEventDestroy(c.ev);
   }
   cudaFree(s.d_out_scores); cudaFree(s.d_out_rows); cudaFree(s.d_out_n);
@@ -239,6 +242,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
     CK(ix, cudaMalloc((void**)&c.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
     CK(ix, cudaMalloc((void**)&c.d_done, 4 * sizeof(uint32_t)));
     CK(ix, cudaMemset(c.d_done, 0, 4 * sizeof(uint32_t)));
+    CK(ix, cudaMalloc((void**)&c.d_col, sizeof(ckey_t) * kMaxGrid));
+    CK(ix, cudaMemset(c.d_col, 0, sizeof(ckey_t) * kMaxGrid));
     CK(ix, cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
   }
   CK(ix, cudaMalloc((void**)&s.d_out_scores, sizeof(float) * kMaxK));
@@ -266,6 +271,23 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaEventCreate(&s.ev1));
   CK(ix, cudaEventCreate(&s.ev_b0));
   CK(ix, cudaEventCreate(&s.ev_b1));
+  if (ix->shards.size() == 1) {
+    // Query / result buffers of the batch entry points (27 MB), allocated up front: a cudaMalloc
+    // issued later, while a peer rank's exchange kernel is already spinning for this rank on the
+    // SAME device (ranks emulated on one GPU), waits for that kernel — i.e. for its timeout.
+    // Only the 250 MB scratch of the tensor-core path stays lazy (first bf16 batch).
+    const uint32_t ld = ix->layout.ld;
+    CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
+    CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bout_n, sizeof(uint32_t) * kBatchMaxQ));
+    CK(ix, cudaMalloc((void**)&s.d_bm_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bm_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_bm_n, sizeof(uint32_t) * kBatchMaxQ));
+    CK(ix, cudaMalloc((void**)&s.d_spm_scores, sizeof(float) * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_spm_rows, sizeof(uint64_t) * kMaxK));
+    CK(ix, cudaMalloc((void**)&s.d_spm_n, sizeof(uint32_t)));
+  }
   if (getenv("CQS_B200_TRACE")) {
     CK(ix, cudaMalloc((void**)&s.d_trace, sizeof(unsigned long long) * kMaxGrid * 8));
     CK(ix, cudaMemset(s.d_trace, 0, sizeof(unsigned long long) * kMaxGrid * 8));
@@ -478,6 +500,13 @@ int cqs_b200_finalize(cqs_b200_index* ix) try {
       CK(ix, launch_max_row_norm(s.d_rows, s.n_rows, ix->layout, s.d_maxnorm, s.stream));
       CK(ix, cudaMemcpyAsync(&s.max_row_norm, s.d_maxnorm, sizeof(float), cudaMemcpyDeviceToHost,
                              s.stream));
+      s.max_row_delta = 0.f;
+      if (ix->storage == CQS_B200_STORAGE_BF16_F32) {
+        CK(ix, cudaStreamSynchronize(s.stream));
+        CK(ix, launch_max_row_delta(s.d_rows, s.d_rows16, s.n_rows, ix->layout.ld, s.d_maxnorm, s.stream));
+        CK(ix, cudaMemcpyAsync(&s.max_row_delta, s.d_maxnorm, sizeof(float), cudaMemcpyDeviceToHost,
+                               s.stream));
+      }
     }
     CK(ix, cudaStreamSynchronize(s.stream));
   }
@@ -557,11 +586,34 @@ static int release_scratch(cqs_b200_index* ix, Shard::ScanScratch* c, cudaStream
 constexpr size_t kOffScores = 0, kOffRows = sizeof(float) * kMaxK,
                  kOffN = (sizeof(float) + sizeof(uint64_t)) * kMaxK, kOffFlag = kOffN + 4;
 
+// Which rows a single-query scan streams.  STORAGE_BF16_F32 and a plain search (no score fold):
+// the bf16 shadow (2 B/elem) with an over-fetch of k' candidates that the kernel tail re-scores on
+// the f32 master rows — f32-exact answers at bf16 bandwidth; a pool that cannot be proven complete
+// comes back with kUnprovenBit and is re-run on the master (force_master).  Everything else: the
+// master rows.
+static void fill_scan_rows(const cqs_b200_index* ix, const Shard& s, ScanArgs& a, uint32_t k, bool signals,
+                           bool force_master) {
+  a.d_rows = s.d_rows;
+  a.layout = ix->layout;
+  a.k = k;
+  const uint32_t kp = shadow_kprime(k);
+  if (ix->storage == CQS_B200_STORAGE_BF16_F32 && !signals && !force_master && kp != 0 && s.d_rows16) {
+    a.d_rows = s.d_rows16;
+    a.layout = ix->layout16;
+    a.k = kp;
+    a.k_out = k;
+    a.d_exact_rows = s.d_rows;
+    a.exact_nv = ix->layout.nv;
+    a.max_row_delta = s.max_row_delta;
+    a.max_row_norm = s.max_row_norm + s.max_row_delta;
+  }
+}
+
 // to_host: the kernel writes the result into the host-mapped buffer and publishes a
 // completion word (the latency path of cqs_b200_search); otherwise into the device pool.
 static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32_t k,
                         const uint32_t* bitset, const ScanSignals* sig = nullptr,
-                        bool to_host = false, const PeerCtx* peer = nullptr) {
+                        bool to_host = false, const PeerCtx* peer = nullptr, bool force_master = false) {
   CK(ix, cudaSetDevice(s.device));
   Shard::ScanScratch* scr = nullptr;
   if (int rc = acquire_scratch(ix, s, s.stream, &scr)) return rc;
@@ -577,9 +629,10 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
     d_bits = s.d_bitset;
   }
   ScanArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = scr->d_query;
-  a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
+  fill_scan_rows(ix, s, a, k, sig != nullptr, force_master);
+  a.n_rows = s.n_rows; a.d_query = scr->d_query;
+  a.d_bitset = d_bits; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done; a.d_col = scr->d_col;
   a.d_out_scores = s.d_out_scores; a.d_out_rows = s.d_out_rows; a.d_out_n = s.d_out_n;
   if (to_host) {
     a.d_out_scores = (float*)(s.d_hout + kOffScores);
@@ -664,6 +717,13 @@ static int search_impl(cqs_b200_index* ix, const float* query, uint32_t k, const
   float kms = 0.f;
   for (Shard* s : live) {
     if (int rcw = wait_host_flag(ix, *s)) return rcw;
+    if (*(uint32_t*)(s->h_out + kOffN) & kUnprovenBit) {
+      // bf16 shadow scan whose candidate pool could not be proven complete: the f32 master decides
+      ++ix->shadow_reruns;
+      rc = launch_dense(ix, *s, query, k, bitset, nullptr, /*to_host=*/true, nullptr, /*force_master=*/true);
+      if (rc) return rc;
+      if (int rcw = wait_host_flag(ix, *s)) return rcw;
+    }
     if (ix->timing) {
       CK(ix, cudaSetDevice(s->device));
       CK(ix, cudaEventSynchronize(s->ev1));
@@ -816,9 +876,10 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
     qp = scr->d_query;
   }
   ScanArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
-  a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
+  fill_scan_rows(ix, s, a, k, false, false);
+  a.n_rows = s.n_rows; a.d_query = qp;
+  a.d_bitset = d_bitset; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done; a.d_col = scr->d_col;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   CK(ix, launch_scan_single(a, s.num_sms, st));
   return release_scratch(ix, scr, st);
@@ -889,9 +950,10 @@ int cqs_b200_search_sharded_device(cqs_b200_index* ix, cqs_b200_peer* peer, cons
   PeerCtx pc;
   CK(ix, peer_begin(peer, st, &pc, /*exclusive=*/false));
   ScanArgs a;
-  a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
-  a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
-  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
+  fill_scan_rows(ix, s, a, k, false, false);
+  a.n_rows = s.n_rows; a.d_query = qp;
+  a.d_bitset = d_bitset; a.row_base = ix->row_base + s.first_row;
+  a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done; a.d_col = scr->d_col;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
   a.peer = &pc;
   CK(ix, launch_scan_single(a, s.num_sms, st));
@@ -923,7 +985,7 @@ static int ensure_batch_buffers(cqs_b200_index* ix, Shard& s, bool tensor_path) 
 static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, const float* d_queries,
                              uint32_t q_stride, uint32_t nq, uint32_t k, const uint32_t* d_bitset,
                              float* d_out_scores, uint64_t* d_out_rows, uint32_t* d_out_n,
-                             const uint8_t* skip, cudaStream_t st) {
+                             const uint8_t* skip, cudaStream_t st, bool force_master = false) {
   const bool staged = q_stride < ix->layout.ld;  // query must be zero padded to the row stride
   cudaStream_t lanes[kLanes];
   lanes[0] = st;
@@ -953,9 +1015,10 @@ static int launch_scan_lanes(cqs_b200_index* ix, Shard& s, cqs_b200_peer* peer, 
     PeerCtx pc;
     if (peer) CK(ix, peer_begin(peer, ln, &pc, /*exclusive=*/false));
     ScanArgs a;
-    a.d_rows = s.d_rows; a.n_rows = s.n_rows; a.layout = ix->layout; a.d_query = qp;
-    a.d_bitset = d_bitset; a.k = k; a.row_base = ix->row_base + s.first_row;
-    a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done;
+    fill_scan_rows(ix, s, a, k, false, force_master);
+    a.n_rows = s.n_rows; a.d_query = qp;
+    a.d_bitset = d_bitset; a.row_base = ix->row_base + s.first_row;
+    a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done; a.d_col = scr->d_col;
     a.d_out_scores = d_out_scores + (size_t)i * k;
     a.d_out_rows = d_out_rows + (size_t)i * k;
     a.d_out_n = d_out_n + i;
@@ -1038,7 +1101,31 @@ static int search_batch_exact(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
     peer_failed(ix, peer);
     return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
   }
-  for (uint32_t i = 0; i < nq; ++i) out_n[i] = bad[i] ? 0 : std::min(ns[i], k);
+  // STORAGE_BF16_F32: shadow scans whose pool could not be proven complete are re-run on the f32
+  // master rows (the flag travels with the exchange, so every rank re-runs the same queries)
+  std::vector<uint8_t> skip2(nq, 1);
+  uint32_t n_unproven = 0;
+  for (uint32_t i = 0; i < nq; ++i)
+    if (!bad[i] && (ns[i] & kUnprovenBit)) {
+      skip2[i] = 0;
+      ++n_unproven;
+    }
+  if (n_unproven) {
+    ix->shadow_reruns += n_unproven;
+    if (int rc = launch_scan_lanes(ix, s, peer, s.d_bq, ld, nq, k, d_bits, s.d_bout_scores, s.d_bout_rows,
+                                   s.d_bout_n, skip2.data(), s.stream, /*force_master=*/true))
+      return rc;
+    CK(ix, cudaMemcpyAsync(out_scores, s.d_bout_scores, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaMemcpyAsync(out_rows, s.d_bout_rows, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaMemcpyAsync(ns.data(), s.d_bout_n, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, s.stream));
+    if (peer) CK(ix, cudaMemcpyAsync(&status, peer->d_status, sizeof status, cudaMemcpyDeviceToHost, s.stream));
+    CK(ix, cudaStreamSynchronize(s.stream));
+    if (status) {
+      peer_failed(ix, peer);
+      return fail(CQS_B200_ERR_CUDA, "peer exchange timed out (a rank did not take part in this batch)");
+    }
+  }
+  for (uint32_t i = 0; i < nq; ++i) out_n[i] = bad[i] ? 0 : std::min(ns[i] & ~kUnprovenBit, k);
   return CQS_B200_OK;
 }
 
@@ -1063,6 +1150,15 @@ int cqs_b200_search_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const float
   if ((rc = launch_dense(ix, s, query, k, bitset, nullptr, /*to_host=*/true, &pc))) return rc;
   CK(ix, peer_mark(peer, s.stream, /*exclusive=*/false));
   if ((rc = wait_host_flag(ix, s))) return rc;
+  if (*(uint32_t*)(s.h_out + kOffN) & kUnprovenBit) {
+    // some shard's bf16 shadow scan could not prove its list; the flag reached every rank with the
+    // exchange, so every rank repeats this search on its f32 master rows (one more exchange each)
+    ++ix->shadow_reruns;
+    CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/false));
+    if ((rc = launch_dense(ix, s, query, k, bitset, nullptr, /*to_host=*/true, &pc, /*force_master=*/true))) return rc;
+    CK(ix, peer_mark(peer, s.stream, /*exclusive=*/false));
+    if ((rc = wait_host_flag(ix, s))) return rc;
+  }
   uint32_t n = std::min(*(uint32_t*)(s.h_out + kOffN), k);
   if (n == 0) {
     // empty can also mean "a peer never answered": the kernel raised the sticky status word
@@ -1109,11 +1205,12 @@ static int search_batch_tc(cqs_b200_index* ix, const float* queries, uint32_t nq
   a.layout = shadow ? ix->layout16 : ix->layout;
   a.d_exact_rows = s.d_rows;
   a.exact_layout = ix->layout;
-  // bf16 rounding of the query (2^-9) [+ of the rows (2^-9) and the cross term] + fp32 accumulation
-  a.err_factor = shadow ? 0.0041656494140625f : 0.0020751953125f;
+  // exactness bound inputs: the measured row rounding distance (0 when the bf16 rows are the
+  // corpus) and a bound on the norm of the scanned bf16 rows (final_select_kernel)
+  a.max_row_delta = shadow ? s.max_row_delta : 0.f;
   a.n_rows = s.n_rows; a.d_queries = s.d_bq; a.nq = nq;
   a.k = k; a.d_bitset = d_bits; a.row_base = ix->row_base + s.first_row;
-  a.max_row_norm = s.max_row_norm; a.d_scratch = s.d_bscratch;
+  a.max_row_norm = s.max_row_norm + a.max_row_delta; a.d_scratch = s.d_bscratch;
   a.d_out_scores = s.d_bout_scores; a.d_out_rows = s.d_bout_rows; a.d_out_n = s.d_bout_n;
   a.d_flags = s.d_bflags;
   if (int rc2 = order_after_last(ix, s, s.stream)) return rc2;
@@ -1252,11 +1349,6 @@ int cqs_b200_search_batch_sharded(cqs_b200_index* ix, cqs_b200_peer* peer, const
     std::lock_guard<std::mutex> gp(peer->mu);
     Shard& s = ix->shards[0];
     CK(ix, cudaSetDevice(s.device));
-    if (!s.d_bm_scores) {
-      CK(ix, cudaMalloc((void**)&s.d_bm_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
-      CK(ix, cudaMalloc((void**)&s.d_bm_rows, sizeof(uint64_t) * (size_t)kBatchMaxQ * kMaxK));
-      CK(ix, cudaMalloc((void**)&s.d_bm_n, sizeof(uint32_t) * kBatchMaxQ));
-    }
     for (uint32_t i : rerun) {
       CK(ix, cudaMemcpyAsync(s.d_bout_scores + (size_t)i * k, osc + (size_t)i * k, sizeof(float) * out_n[q0 + i],
                              cudaMemcpyHostToDevice, s.stream));
@@ -1699,11 +1791,6 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   Shard& s = ix->shards[0];
   if (!s.sparse.d_tptr) return fail(CQS_B200_ERR_INVALID, "no sparse index attached");
   CK(ix, cudaSetDevice(s.device));
-  if (peer && !s.d_spm_scores) {
-    CK(ix, cudaMalloc((void**)&s.d_spm_scores, sizeof(float) * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_spm_rows, sizeof(uint64_t) * kMaxK));
-    CK(ix, cudaMalloc((void**)&s.d_spm_n, sizeof(uint32_t)));
-  }
   // dense leg: a malformed query yields an EMPTY dense pool (src/cagra.rs:458-470);
   // the sparse leg still runs (search_hybrid_inner calls both unconditionally).
   const bool dense_ok = query_is_finite(query, ix->dim);
@@ -1715,7 +1802,8 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   if (dense_ok) {
     PeerCtx pc;
     if (peer) CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/false));
-    rc = launch_dense(ix, s, query, pool_k, bitset, nullptr, false, peer ? &pc : nullptr);
+    // (the fusion kernel reads the pool's length on the device: always the f32 master here)
+    rc = launch_dense(ix, s, query, pool_k, bitset, nullptr, false, peer ? &pc : nullptr, /*force_master=*/true);
     if (rc) return rc;
     if (peer) CK(ix, peer_mark(peer, s.stream, /*exclusive=*/false));
     if (bitset) d_bits = s.d_bitset;
@@ -2090,6 +2178,7 @@ int cqs_b200_set_timing(cqs_b200_index* ix, int enable) try {
 // development aids, not declared in the public header
 uint32_t cqs_b200_debug_batch_reruns(cqs_b200_index* ix) { return ix ? ix->batch_reruns_total : 0; }
 uint32_t cqs_b200_debug_last_batch_reruns(cqs_b200_index* ix) { return ix ? ix->last_batch_reruns : 0; }
+uint64_t cqs_b200_debug_shadow_reruns(cqs_b200_index* ix) { return ix ? ix->shadow_reruns : 0; }
 int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) try {
   if (!ix || ix->shards.empty() || !ix->shards[0].d_bflags) return CQS_B200_ERR_INVALID;
   cudaSetDevice(ix->shards[0].device);

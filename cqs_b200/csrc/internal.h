@@ -17,6 +17,11 @@ constexpr uint32_t kMaxGrid = 1024;     // upper bound on scan CTAs (partial-lis
 // so the tail of launch i (list merge, cross-shard exchange — slow while the next scans keep
 // HBM saturated) is hidden behind launches i+1 .. i+kLanes-1.  Launch i only waits for i-kLanes.
 constexpr uint32_t kLanes = 4;
+// Bit 31 of an out_n word: the answer came from the bf16 shadow scan of a STORAGE_BF16_F32 index
+// and its re-scored candidate pool could NOT be proven complete — the host entry points re-run such
+// a query on the f32 master rows before returning; device-resident entry points hand the bit to the
+// caller (CQS_B200_UNPROVEN in include/cqs_b200.h).
+constexpr uint32_t kUnprovenBit = 0x80000000u;
 
 extern std::atomic<uint64_t> g_kernel_launches;
 
@@ -58,6 +63,7 @@ struct ScanArgs {
   ckey_t* d_partial;         // [kMaxGrid][kMaxK] scratch
   uint32_t* d_partial_cnt;  // [kMaxGrid]
   uint32_t* d_done;         // [2]: CTA ticket + tile counter, zero between launches
+  ckey_t* d_col;            // [kMaxGrid] shared-threshold scratch of the large-k path, zero between launches
   float* d_out_scores;      // [k]
   uint64_t* d_out_rows;     // [k]
   uint32_t* d_out_n;        // [1]
@@ -66,7 +72,17 @@ struct ScanArgs {
   uint32_t* d_host_flag = nullptr;  // device alias of a host-mapped completion word (nullable)
   uint32_t seq = 0;                 // value written to it
   const PeerCtx* peer = nullptr;    // row-sharded corpus: exchange + merge in the kernel tail; out_* = GLOBAL top-k
+  // STORAGE_BF16_F32 fast path: d_rows is the bf16 shadow, k the over-fetched candidate count k';
+  // the kernel tail re-scores the k' candidates on the f32 master rows (the f32 scan's arithmetic:
+  // bit-identical scores), keeps the best k_out and proves the pool complete or raises kUnprovenBit.
+  const void* d_exact_rows = nullptr;
+  int exact_nv = 0;                 // lane vectors per row of the f32 master layout
+  uint32_t k_out = 0;
+  float max_row_delta = 0.f;        // measured max |f32 row - bf16 row|_2
+  float max_row_norm = 0.f;         // bound on |bf16 row|_2
 };
+// Over-fetch of the shadow scan for a final k (0 = k too large: scan the f32 master instead).
+uint32_t shadow_kprime(uint32_t k);
 // Kernel 1+3: single-query streaming scan with the top-k select fused in.
 cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t stream);
 
@@ -94,13 +110,13 @@ struct BatchArgs {
   RowLayout layout;          // mode 1 or 2 (bf16)
   const void* d_exact_rows;  // rows the candidates are re-scored on (== d_rows, or the f32 master)
   RowLayout exact_layout;    // same ld as `layout`
-  float err_factor;          // |tensor score - exact score| <= err_factor * |q| * max|row|
+  float max_row_delta;       // max over rows of |exact row - scanned bf16 row|_2 (0 when the bf16 rows ARE the corpus)
   const float* d_queries;    // f32 [nq][ld], zero padded beyond dim
   uint32_t nq;               // <= kBatchMaxQ
   uint32_t k;
   const uint32_t* d_bitset;  // nullable
   uint64_t row_base;
-  float max_row_norm;        // max L2 norm over the corpus rows (exactness bound)
+  float max_row_norm;        // upper bound of the L2 norm of every scanned (bf16) row (exactness bound)
   void* d_scratch;           // batch_scratch_bytes(round_up(nq,128), ld)
   float* d_out_scores;       // [nq][k]
   uint64_t* d_out_rows;      // [nq][k]
@@ -112,6 +128,10 @@ uint32_t batch_kprime(uint32_t k);
 cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_max_row_norm(const void* d_rows, uint64_t n_rows, RowLayout layout, float* d_out,
                                 cudaStream_t stream);
+// max over rows of |f32 master row - bf16 shadow row|_2 (same ld): the measured rounding distance
+// that makes the batch path's exactness bound rigorous AND tight.
+cudaError_t launch_max_row_delta(const void* d_rows_f32, const void* d_rows_bf16, uint64_t n_rows, uint32_t ld,
+                                 float* d_out, cudaStream_t stream);
 
 // ---- sparse (SPLADE) ----
 struct SparseDev {

@@ -118,7 +118,7 @@ __device__ __forceinline__ void peer_merge_query(const PeerCtx& c, const Group& 
   uint32_t nl[kPeerMaxWorld];
   const float* sl[kPeerMaxWorld];
   const uint64_t* rl[kPeerMaxWorld];
-  uint32_t total = 0;
+  uint32_t total = 0, unproven = 0;   // bit 31 of a list length: that shard could not prove its list (kUnprovenBit)
 #pragma unroll
   for (uint32_t l = 0; l < kPeerMaxWorld; ++l) {
     nl[l] = 0;
@@ -126,7 +126,9 @@ __device__ __forceinline__ void peer_merge_query(const PeerCtx& c, const Group& 
     rl[l] = nullptr;
     if (l < c.world) {
       const PeerBlock b = peer_block(c, c.rank, l);
-      nl[l] = min(__ldcg(b.n + qi), k);
+      const uint32_t raw = __ldcg(b.n + qi);
+      unproven |= raw & 0x80000000u;
+      nl[l] = min(raw & 0x7FFFFFFFu, k);
       sl[l] = b.scores + (size_t)qi * k;
       rl[l] = b.rows + (size_t)qi * k;
       total += nl[l];
@@ -172,7 +174,7 @@ __device__ __forceinline__ void peer_merge_query(const PeerCtx& c, const Group& 
     out_scores[i] = __uint_as_float(0xFF800000u);  // -inf
     out_rows[i] = ~0ull;
   }
-  if (g.tid == 0) *out_n = n;
+  if (g.tid == 0) *out_n = n | unproven;
 }
 
 // Collective over g: empty result (exchange failed).

@@ -332,23 +332,36 @@ scan_batch_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // ---- query preparation: f32 -> bf16 (RNE), zero padding rows, norms, state reset -------
 __global__ void prep_queries_kernel(const float* __restrict__ q32, uint32_t nq, uint32_t nq_pad,
                                     uint32_t ld, __nv_bfloat16* __restrict__ q16,
-                                    float* __restrict__ qnorm, ckey_t* thr, uint32_t* cnt,
-                                    uint32_t* overflow, uint32_t dense_count) {
+                                    float* __restrict__ qnorm, float* __restrict__ dqnorm, ckey_t* thr,
+                                    uint32_t* cnt, uint32_t* overflow, uint32_t dense_count) {
   const uint32_t q = blockIdx.x;
-  float acc = 0.f;
+  float acc = 0.f, dacc = 0.f;
   for (uint32_t i = threadIdx.x; i < ld; i += blockDim.x) {
     float v = q < nq ? q32[(size_t)q * ld + i] : 0.f;
-    q16[(size_t)q * ld + i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    q16[(size_t)q * ld + i] = b;
+    const float d = v - __bfloat162float(b);   // exact (Sterbenz): the rounding error of this element
     acc += v * v;
+    dacc += d * d;
   }
-  __shared__ float red[32];
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __shared__ float red[32], dred[32];
+  for (int off = 16; off > 0; off >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    dacc += __shfl_xor_sync(0xffffffffu, dacc, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = acc;
+    dred[threadIdx.x >> 5] = dacc;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    float t = 0.f, dt = 0.f;
+    for (uint32_t w = 0; w < (blockDim.x + 31) / 32; ++w) {
+      t += red[w];
+      dt += dred[w];
+    }
     qnorm[q] = sqrtf(t);
+    dqnorm[q] = sqrtf(dt);      // |q - bf16(q)|_2, measured: what the tensor-core scan did not see of the query
     thr[q] = 0;
     cnt[q] = q < nq ? dense_count : 0;
     overflow[q] = 0;
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const uint8_t* __restrict_
 // ---- final selection + exactness check ---------------------------------------------------
 __global__ void __launch_bounds__(kUpdThreads) final_select_kernel(
     const ckey_t* cand, const uint32_t* cnt, const ckey_t* thr, const uint32_t* overflow,
-    const float* qnorm, float max_row_norm, float err_factor, uint32_t cap, uint32_t kprime, uint32_t k,
+    const float* qnorm, const float* dqnorm, float max_row_norm, float max_row_delta, uint32_t cap, uint32_t kprime, uint32_t k,
     uint64_t row_base, float* out_scores, uint64_t* out_rows, uint32_t* out_n, uint32_t* flags) {
   __shared__ ckey_t s_buf[kUpdCap];
   __shared__ uint32_t s_cnt;
@@ -505,16 +518,21 @@ __global__ void __launch_bounds__(kUpdThreads) final_select_kernel(
   }
   if (tid == 0) {
     out_n[q] = m;
-    // Rows outside the pool have approx score <= the pool's cut-off; |approx - exact| <= E
-    // with E = err_factor * |q| * max|row| (bf16 rounding of the query — and of the rows
-    // when they shadow an f32 master — plus fp32 accumulation).  If the k-th exact score
-    // clears cut-off + E nothing was missed.
+    // Rows outside the pool have approx score <= the pool's cut-off.  With q16 = bf16(q),
+    // r16 = the scanned bf16 row, r = the exact row:  q.r - q16.r16 = q.(r - r16) + (q - q16).r16,
+    // so |exact - approx| <= |q| * D + |q - q16| * R + fp32 accumulation, where D = max_row_delta
+    // (MEASURED max |r - r16|_2 over the corpus; 0 when the bf16 rows are the corpus),
+    // |q - q16| is measured per query, R bounds |r16|, and 2^-13 |q| R covers 768-term fp32
+    // accumulation with truncation (768 * 2^-23 < 2^-13).  Cauchy-Schwarz on measured norms:
+    // rigorous, and ~2.5x tighter than the worst-case unit roundoff 2^-8.  If the k-th exact
+    // score clears cut-off + E nothing was missed.
     // flag codes: 1 = pool overflowed, 2 = too few exact survivors, 3 = margin not proven
     uint32_t flag = overflow[q] ? 1u : 0u;
     const ckey_t t = thr[q];
     if (t != 0 && !flag) {
       const float cut = key_score(t);
-      const float E = err_factor * qnorm[q] * max_row_norm;
+      const float E = 1.001f * (qnorm[q] * max_row_delta + dqnorm[q] * max_row_norm +
+                                0.0001220703125f * qnorm[q] * max_row_norm);
       if (m < k) flag = 2;  // the pool was full yet fewer than k exact survivors: be safe
       else if (!(key_score(s_buf[k - 1]) > cut + E)) flag = 3;
     }
@@ -534,6 +552,25 @@ __global__ void max_row_norm_kernel(const uint8_t* __restrict__ rows, uint64_t n
       float v = is_bf16 ? __bfloat162float(((const __nv_bfloat16*)rows)[r * ld + i])
                         : ((const float*)rows)[r * ld + i];
       acc += v * v;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (acc == acc && acc < 3.0e38f) best = fmaxf(best, acc);
+  }
+  if (lane == 0 && best > 0.f) atomicMax((int*)out, __float_as_int(sqrtf(best)));
+}
+
+// max over rows of |f32 master row - bf16 shadow row|_2; one warp per row
+__global__ void max_row_delta_kernel(const float* __restrict__ r32, const __nv_bfloat16* __restrict__ r16,
+                                     uint64_t n_rows, uint32_t ld, float* out) {
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  float best = 0.f;
+  for (uint64_t r = warp; r < n_rows; r += nwarps) {
+    float acc = 0.f;
+    for (uint32_t i = lane; i < ld; i += 32) {
+      const float d = r32[r * ld + i] - __bfloat162float(r16[r * ld + i]);
+      acc += d * d;
     }
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (acc == acc && acc < 3.0e38f) best = fmaxf(best, acc);
@@ -583,6 +620,16 @@ cudaError_t launch_max_row_norm(const void* d_rows, uint64_t n_rows, RowLayout l
   return cudaGetLastError();
 }
 
+cudaError_t launch_max_row_delta(const void* d_rows_f32, const void* d_rows_bf16, uint64_t n_rows, uint32_t ld,
+                                 float* d_out, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(float), st);
+  if (e != cudaSuccess || n_rows == 0) return e;
+  max_row_delta_kernel<<<148 * 4, 256, 0, st>>>((const float*)d_rows_f32, (const __nv_bfloat16*)d_rows_bf16, n_rows,
+                                               ld, d_out);
+  g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
 uint32_t batch_kprime(uint32_t k) {
   uint32_t extra = k / 4 < 44 ? 44 : k / 4;
   uint32_t kp = (k + extra + 31) / 32 * 32;
@@ -620,6 +667,8 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   base += (size_t)nq_pad * 4;
   float* qnorm = (float*)base;
   base += (size_t)nq_pad * 4;
+  float* dqnorm = (float*)base;
+  base += (size_t)nq_pad * 4;
   base = (uint8_t*)(((uintptr_t)base + 255) & ~(uintptr_t)255);
   ckey_t* sub = (ckey_t*)base;
   base += (size_t)nq_pad * kMaxGridB * kSub * 8;
@@ -631,7 +680,7 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
     return cudaErrorNotSupported;
 
   const uint64_t r0 = a.n_rows < kBatchDenseRows ? a.n_rows : kBatchDenseRows;
-  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(a.d_queries, a.nq, nq_pad, ld, q16, qnorm, thr, cnt,
+  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(a.d_queries, a.nq, nq_pad, ld, q16, qnorm, dqnorm, thr, cnt,
                                               overflow, (uint32_t)r0);
   cudaError_t e = cudaFuncSetAttribute(scan_batch_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kBatchSmem);
@@ -669,8 +718,8 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   }
   rescore_kernel<<<a.nq, 256, 0, st>>>((const uint8_t*)a.d_exact_rows, ld, a.exact_layout.mode,
                                        a.exact_layout.nv, a.d_queries, cand, cnt, kBatchCap, kprime);
-  final_select_kernel<<<a.nq, kUpdThreads, 0, st>>>(cand, cnt, thr, overflow, qnorm,
-                                                    a.max_row_norm, a.err_factor, kBatchCap, kprime, a.k,
+  final_select_kernel<<<a.nq, kUpdThreads, 0, st>>>(cand, cnt, thr, overflow, qnorm, dqnorm,
+                                                    a.max_row_norm, a.max_row_delta, kBatchCap, kprime, a.k,
                                                     a.row_base, a.d_out_scores, a.d_out_rows,
                                                     a.d_out_n, a.d_flags);
   launches += 2;

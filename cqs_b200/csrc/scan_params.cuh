@@ -19,6 +19,7 @@ struct ScanParams {
   ckey_t* partial;
   uint32_t* partial_cnt;
   uint32_t* done;        // [0] finished-CTA ticket, [1] dynamic tile counter; zero between launches
+  ckey_t* col;           // [kMaxGrid] large k: per-CTA published m-th-key bounds; zero between launches
   float* out_scores;
   uint64_t* out_rows;
   uint32_t* out_n;
@@ -30,6 +31,11 @@ struct ScanParams {
   uint64_t n_big = 0;         // number of big work units; the remaining tiles are handed out one by one
   uint32_t chunk_override = 0;  // development aid: CQS_B200_CHUNK
   PeerCtx peer;               // peer.world != 0: exchange the local list with the other shards and emit the GLOBAL top-k
+  const uint8_t* exact_rows = nullptr;  // f32 master rows: re-score the k candidates, keep k_out (ScanArgs)
+  uint32_t exact_nv = 0;
+  uint32_t k_out = 0;
+  float max_row_delta = 0.f;
+  float max_row_norm = 0.f;
 };
 
 }  // namespace cqs

@@ -70,6 +70,13 @@ bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
   return true;
 }
 
+uint32_t shadow_kprime(uint32_t k) {
+  if (k <= 24) return 32;                      // per-warp register lists (SMALLK) still apply
+  const uint32_t extra = k / 4 < 44 ? 44 : k / 4;
+  const uint32_t kp = (k + extra + 31) / 32 * 32;
+  return kp > kMaxK ? 0 : kp;
+}
+
 // one translation unit per (row mode, top-k variant): scan_v_*.cu
 #define CQS_DECL_VARIANT(name) cudaError_t name(const ScanParams& p, int nv, int num_sms, cudaStream_t st)
 CQS_DECL_VARIANT(launch_scan_m0_small); CQS_DECL_VARIANT(launch_scan_m0_large);
@@ -90,6 +97,7 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.partial = a.d_partial;
   p.partial_cnt = a.d_partial_cnt;
   p.done = a.d_done;
+  p.col = a.d_col;
   p.out_scores = a.d_out_scores;
   p.out_rows = a.d_out_rows;
   p.out_n = a.d_out_n;
@@ -98,6 +106,14 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.host_flag = a.d_host_flag;
   p.seq = a.seq;
   if (a.peer) p.peer = *a.peer;
+  if (a.d_exact_rows) {
+    if (a.k_out == 0 || a.k_out > a.k || a.layout.mode == 0 || a.exact_nv <= 0 || a.signals) return cudaErrorInvalidValue;
+    p.exact_rows = (const uint8_t*)a.d_exact_rows;
+    p.exact_nv = (uint32_t)a.exact_nv;
+    p.k_out = a.k_out;
+    p.max_row_delta = a.max_row_delta;
+    p.max_row_norm = a.max_row_norm;
+  }
   static const uint32_t chunk_env = getenv("CQS_B200_CHUNK") ? (uint32_t)atoi(getenv("CQS_B200_CHUNK")) : 0;
   p.chunk_override = chunk_env;
   const bool small = a.k <= 32;  // per-warp register lists; larger k: shared-memory accumulator

@@ -128,6 +128,101 @@ struct ScanCfg {
   static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + kCap * sizeof(ckey_t);
 };
 
+// Collective over tk.g: raise the CTA's threshold to the j-th largest of the values the CTAs have
+// published in col[0..G) (0 = nothing published yet), minus one ("key > thr" keeps keys >= it).
+// A published value is usable iff at least j published values are >= it (those j CTAs hold >= m
+// keys >= it each); the largest usable one is the j-th largest.  colv: shared scratch for G keys.
+// Not inlined: one copy per translation unit instead of one per instantiation.
+static __device__ __noinline__ void refresh_global_thr(TopK tk, ckey_t* colv, const ckey_t* col,
+                                                       uint32_t G, uint32_t j) {
+  const uint32_t tid = tk.g.tid, T = tk.g.nthr;
+  for (uint32_t l = tid; l < G; l += T) colv[l] = __ldcg(col + l);
+  tk.g.sync();
+  for (uint32_t t = tid; t < G; t += T) {
+    const ckey_t mine = colv[t];
+    if (mine == 0) continue;
+    uint32_t ge = 0;
+    for (uint32_t i = 0; i < G; ++i) ge += (colv[i] >= mine) ? 1u : 0u;
+    if (ge >= j) atomicMax(tk.thr, mine - 1);
+  }
+  tk.g.sync();
+}
+
+// STORAGE_BF16_F32 fast path, run by the last CTA on the merged candidate list (sorted keys of the
+// bf16 shadow scan in tk.buf[0..n), n <= k' = kp): every candidate is re-scored on its f32 master
+// row with the f32 scan's own arithmetic (LaneVec<0>: lane l owns elements (v*32+l)*4.., four
+// accumulators, the same butterfly) — the scores are bit-identical to a STORAGE_F32 scan — the best
+// k_out are kept and emitted, and the pool is proven complete:
+//   a row outside the pool has shadow score <= cut (the pool's k'-th shadow score), and
+//   |q.r - q.r16| = |q.(r - r16)| <= |q| * D, D = max_row_delta (measured at finalize), plus the fp32
+//   accumulation error of both dots (<= 2^-18 |q| R for ld <= 2048), so its exact score is <= cut + E.
+//   If the k_out-th exact score is > cut + E nothing outside the pool can belong to the answer.
+// Otherwise bit 31 of *out_n is raised and the host re-runs the query on the f32 master rows.
+static __device__ __noinline__ void rescore_and_emit(TopK tk, const ScanParams& p, uint32_t kp, float* out_scores,
+                                                     uint64_t* out_rows, uint32_t* out_n, float* s_red) {
+  const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const uint32_t n = *tk.cnt;
+  const ckey_t cut_key = (n >= kp) ? tk.buf[kp - 1] : 0;   // pool not full: it holds every eligible row
+  const uint32_t ld = p.exact_nv * 128;
+  float qq = 0.f;
+  for (uint32_t i = tid; i < ld; i += T) {
+    const float v = __ldg(p.query + i);
+    qq = fmaf(v, v, qq);
+  }
+  for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  if (lane == 0) s_red[warp] = qq;
+  tk.g.sync();   // also: every thread has read cut_key before the keys are overwritten
+  for (uint32_t j = warp; j < n; j += nwarps) {
+    const ckey_t key = tk.buf[j];
+    const uint32_t r = key_row(key);
+    const uint8_t* row = p.exact_rows + (size_t)r * ld * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t v = 0; v < p.exact_nv; ++v) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(row) + v * 32 + lane);
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p.query) + v * 32 + lane);
+      acc[0] = fmaf(x.x, q.x, acc[0]);
+      acc[1] = fmaf(x.y, q.y, acc[1]);
+      acc[2] = fmaf(x.z, q.z, acc[2]);
+      acc[3] = fmaf(x.w, q.w, acc[3]);
+    }
+    float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __syncwarp();
+    // a non-finite exact score drops the row (candidate.rs:275): its key becomes (0, ~row) — below every
+    // valid key (whose high word is >= 0x00800000) yet unique, as the rank sort requires
+    if (lane == 0) tk.buf[j] = finite_bits(__float_as_uint(s)) ? make_key(s, r) : (ckey_t)(~r);
+  }
+  tk.g.sync();
+  tk.compact(p.k_out);                       // exact sort; dropped candidates sink to the end
+  const uint32_t m = *tk.cnt;
+  uint32_t valid = 0;
+  for (uint32_t i = 0; i < m; ++i) valid += (tk.buf[i] >> 32) != 0 ? 1u : 0u;   // m <= k_out <= 1024, broadcast reads
+  float qn = 0.f;
+  for (uint32_t w = 0; w < nwarps; ++w) qn += s_red[w];
+  qn = sqrtf(qn);
+  uint32_t flag = 0;
+  if (cut_key != 0) {
+    const float E = 1.001f * qn * (p.max_row_delta + 3.814697265625e-6f * p.max_row_norm);
+    if (valid < p.k_out || !(key_score(tk.buf[p.k_out - 1]) > key_score(cut_key) + E)) flag = kUnprovenBit;
+  }
+  for (uint32_t i = tid; i < p.k_out; i += T) {
+    if (i < valid) {
+      const ckey_t key = tk.buf[i];
+      out_scores[i] = key_score(key);
+      out_rows[i] = p.row_base + key_row(key);
+    } else {
+      out_scores[i] = __uint_as_float(0xFF800000u);
+      out_rows[i] = ~0ull;
+    }
+  }
+  if (tid == 0) {
+    *tk.cnt = valid;
+    *out_n = valid | flag;
+  }
+  tk.g.sync();
+}
+
 // SMALLK (k <= 32): every consumer warp keeps its own sorted top-32 in registers
 // (lane i holds the i-th best key); a row that beats the warp's k-th key is
 // inserted with one ballot and one shuffle.  No shared-memory traffic, no
@@ -152,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   __shared__ uint32_t s_last;
-  __shared__ uint32_t s_pos[kMaxGrid];
+  __shared__ __align__(8) uint32_t s_pos[kMaxGrid];
   __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
 
   const uint32_t lane = threadIdx.x & 31;
@@ -225,6 +320,22 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   const uint32_t k = p.k;
   ckey_t thr = 0;
   ckey_t slot = 0, wthr = 0;  // SMALLK: this lane's entry of the warp's sorted list / its k-th key
+  // Large k: a CTA sees only n/G rows, so its own k-th best is a weak filter (k = 500 of 6,757 rows
+  // lets 7 % of the rows through) and every CTA would carry ~k candidates into its final sort and
+  // into the merge.  The CTAs therefore share a GLOBAL threshold: whenever a CTA re-selects its
+  // buffer it also publishes v = a lower bound of its m-th best key (p.col[blockIdx.x], monotone);
+  // the j-th largest published value, j = ceil(k/m), is a lower bound of the global k-th best
+  // (those j CTAs hold >= m keys >= it each, j*m >= k keys in all, and keys of different CTAs are
+  // different rows) — the column bound of the merge, applied while streaming.  m = ceil(2k/G) makes
+  // j ~ G/2: the bound sits near the median of the CTAs' m-th keys.  Always valid, never too tight:
+  // no fallback pass.  Refreshed at every check interval (one 1.2 KB L2 read per CTA).
+  uint32_t m_pub = 0, j_need = 0;
+  if (!SMALLK && gridDim.x >= 8) {
+    m_pub = (2 * k + gridDim.x - 1) / gridDim.x;
+    j_need = (k + m_pub - 1) / m_pub;
+    if (j_need > gridDim.x) m_pub = 0;
+  }
+  ckey_t* s_vm = reinterpret_cast<ckey_t*>(s_pos);   // [0]: select()'s m-th-key bound (s_pos is free until the merge)
   uint32_t it = 0, s = 0, ph = 0;
   for (;; ++it) {
     mbar_wait(&s_full[s], ph);
@@ -314,12 +425,16 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
         need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
       }
       if (tk.g.any(need)) {
-        tk.template select<kCap / kConsumers>(k);
-        thr = s_thr;
+        if (ctid == 0) s_vm[0] = 0;
+        tk.template select<kCap / kConsumers>(k, m_pub, s_vm);
+        if (m_pub && ctid == 0 && s_vm[0]) atomicMax(p.col + blockIdx.x, s_vm[0]);
       }
+      if (m_pub) refresh_global_thr(tk, reinterpret_cast<ckey_t*>(s_hist), p.col, gridDim.x, j_need);
+      thr = s_thr;
     }
   }
   TRACE(1);
+  ckey_t gthr = 0;
   if (SMALLK) {
     // combine the 8 warp lists: rank sort of 256 keys straight into the partial list
     s_buf[ctid] = (lane < k) ? slot : 0;
@@ -337,6 +452,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
     TRACE(2);
     if (ctid == 0) p.partial_cnt[blockIdx.x] = s_cnt;
   } else {
+    if (m_pub) {
+      // whatever the other CTAs have published by now bounds the global k-th best: drop the
+      // keys below it before the exact sort (this CTA then sorts and emits tens of keys, not k)
+      refresh_global_thr(tk, reinterpret_cast<ckey_t*>(s_hist), p.col, gridDim.x, j_need);
+      gthr = s_thr;   // max(local k-th bound, shared bound): a lower bound of the global k-th best
+      tk.template prune<kCap / kConsumers>(gthr);
+    }
     topk_finish<kCap / kConsumers>(tk, k);
     TRACE(2);
     const uint32_t mycnt = s_cnt;
@@ -354,10 +476,16 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   TRACE(3);
   if (!s_last) return;
   __threadfence();
+  const ckey_t thr0 = gthr;   // the shared threshold is a valid start for the merge
+  if (m_pub)
+    for (uint32_t l = ctid; l < gridDim.x; l += kConsumers) p.col[l] = 0;  // every CTA is past its last read
+  const bool rescore = p.exact_rows != nullptr;
+  const uint32_t k_emit = rescore ? p.k_out : k;   // what leaves this kernel / goes to the peers
   if (p.peer.world == 0) {
     merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, p.out_scores, p.out_rows, p.out_n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+                                               p.row_base, rescore ? nullptr : p.out_scores, p.out_rows, p.out_n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr0);
+    if (rescore) rescore_and_emit(tk, p, k, p.out_scores, p.out_rows, p.out_n, reinterpret_cast<float*>(s_hist));
   } else {
     // Row-sharded corpus: the shard's list goes into this rank's own mailbox
     // block and, by plain stores over NVLink, into every peer's; one release flag per peer
@@ -365,21 +493,23 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
     // ride in the tail of the scan, no collective call and no extra launch.
     const PeerBlock own = peer_block(p.peer, p.peer.rank, p.peer.rank);
     merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, own.scores, own.rows, own.n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr);
+                                               p.row_base, rescore ? nullptr : own.scores, own.rows, own.n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr0);
+    if (rescore) rescore_and_emit(tk, p, k, own.scores, own.rows, own.n, reinterpret_cast<float*>(s_hist));
     const uint32_t n = *tk.cnt;  // sorted keys are still in tk.buf[0..n)
-    for (uint32_t e = ctid; e < p.peer.world * k; e += kConsumers) {
-      const uint32_t g = e / k, i = e - g * k;
+    const uint32_t n_word = rescore ? *own.n : n;   // carries kUnprovenBit to every rank
+    for (uint32_t e = ctid; e < p.peer.world * k_emit; e += kConsumers) {
+      const uint32_t g = e / k_emit, i = e - g * k_emit;
       if (g == p.peer.rank || i >= n) continue;
       const PeerBlock pb = peer_block(p.peer, g, p.peer.rank);
       const ckey_t key = s_buf[i];
       pb.scores[i] = key_score(key);
       pb.rows[i] = p.row_base + key_row(key);
     }
-    if (ctid < p.peer.world && ctid != p.peer.rank) peer_block(p.peer, ctid, p.peer.rank).n[0] = n;
+    if (ctid < p.peer.world && ctid != p.peer.rank) peer_block(p.peer, ctid, p.peer.rank).n[0] = n_word;
     peer_signal(p.peer, tk.g);
-    if (peer_wait(p.peer, tk.g)) peer_merge_query(p.peer, tk.g, 0, k, p.out_scores, p.out_rows, p.out_n);
-    else peer_emit_empty(tk.g, k, p.out_scores, p.out_rows, p.out_n);
+    if (peer_wait(p.peer, tk.g)) peer_merge_query(p.peer, tk.g, 0, k_emit, p.out_scores, p.out_rows, p.out_n);
+    else peer_emit_empty(tk.g, k_emit, p.out_scores, p.out_rows, p.out_n);
   }
   TRACE(4);
   if (p.host_flag) {

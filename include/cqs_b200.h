@@ -49,8 +49,16 @@ extern "C" {
 #define CQS_B200_STORAGE_F32 0      /* rows kept as f32 (BLOB layout, src/store/helpers/embeddings.rs:14-41) */
 #define CQS_B200_STORAGE_BF16 1     /* rows rounded (RNE) to bf16; the rounded matrix IS the corpus */
 #define CQS_B200_STORAGE_BF16_F32 2 /* f32 master rows (every result is exact f32, as STORAGE_F32) plus a
-                                       bf16 shadow copy that only feeds the tensor-core candidate scan of
-                                       cqs_b200_search_batch; candidates are re-scored on the f32 rows */
+                                       bf16 shadow copy that feeds the candidate scans: single queries
+                                       stream the shadow (2 B/elem) and over-fetch k' candidates, batches
+                                       run the tensor-core scan over it; the candidates are re-scored on
+                                       the f32 rows and the pool is PROVEN complete from measured rounding
+                                       distances — or the query is re-run on the f32 rows.  6 B/elem. */
+/* Bit 31 of an out_n word written by the DEVICE-RESIDENT entry points (cqs_b200_search_device,
+ * _search_sharded_device, _search_many_device) on a STORAGE_BF16_F32 index: the candidate pool of
+ * that query could not be proven complete; the caller must repeat it through a host entry point
+ * (which does this re-run itself and never returns the bit).  n = out_n & 0x7FFFFFFF. */
+#define CQS_B200_UNPROVEN 0x80000000u
 
 #define CQS_B200_MAX_K 1024u        /* VectorIndex::max_k()  src/index.rs:217  */
 

@@ -348,6 +348,53 @@ def test_extend_after_reopen(cqs):
     ix.close()
 
 
+def test_bf16_shadow_scan_with_f32_rescoring_equals_f32_storage(cqs, config1):
+    """STORAGE_BF16_F32: single queries stream the bf16 shadow (2 B/elem), over-fetch k' candidates,
+    re-score them on the f32 master rows inside the kernel tail and PROVE the pool complete (measured
+    rounding distance) — or are re-run on the f32 rows.  Either way the answer must be bit-identical
+    to STORAGE_F32 (same rows, same scores), for every k, with a filter, on self-matches, exact
+    duplicates (ties by row) and on near-duplicate clusters that defeat the proof."""
+    import ctypes as C
+    from cqs_b200.capi import lib
+    lib.cqs_b200_debug_shadow_reruns.restype = C.c_uint64
+    lib.cqs_b200_debug_shadow_reruns.argtypes = [C.c_void_p]
+    rows, queries = config1
+    rows = rows.copy()
+    rng = np.random.default_rng(9)
+    base = rows[9000].copy()
+    for j in range(200):                                   # 200 rows within ~2e-5 of each other: no pool of
+        v = base + rng.standard_normal(768).astype(f32) * f32(2e-5)   # k' candidates can be proven complete
+        rows[9001 + 7 * j] = v / np.linalg.norm(v)
+    a = cqs.B200Index(768, storage="f32")
+    a.append(None, rows); a.finalize()
+    b = cqs.B200Index(768, storage="bf16+f32")
+    b.append(None, rows); b.finalize()
+    mask = rng.random(rows.shape[0]) < 0.4
+    bs = O.mask_to_bitset(mask)
+    qs = [queries[i] for i in (0, 5, 32, 40, 100, 217)] + [base, rows[9001]]
+    for qi, q in enumerate(qs):
+        for k in (1, 20, 24, 25, 100, 500, 700, 1024):
+            ra, sa = a.search_rows(q, k)
+            rb, sb = b.search_rows(q, k)
+            assert np.array_equal(ra, rb), (qi, k)
+            assert np.array_equal(bits(sa), bits(sb)), (qi, k)
+        ra, sa = a.search_rows(q, 20, bs)
+        rb, sb = b.search_rows(q, 20, bs)
+        assert np.array_equal(ra, rb) and np.array_equal(bits(sa), bits(sb))
+    reruns = lib.cqs_b200_debug_shadow_reruns(b._h)
+    assert reruns >= 2, reruns                              # the near-duplicate queries fell back to the f32 rows
+    assert reruns < 50, reruns                              # ... and most of the 72 searches were proven on the shadow
+    # batch entry (exact lanes for < 8 queries, tensor cores otherwise): same answers
+    q8 = np.stack(qs[:8])
+    for nq in (3, 8):
+        r, sc, nn = b.search_batch_rows(q8[:nq], 20)
+        for i in range(nq):
+            ra, sa = a.search_rows(q8[i], 20)
+            assert int(nn[i]) == 20 and np.array_equal(r[i], ra) and np.array_equal(bits(sc[i]), bits(sa)), (nq, i)
+    assert b.index_scores_are_cosine()
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("storage", ["f32", "bf16"])
 def test_extend_after_build_and_after_load(cqs, tmp_path, storage):
     """INTEGRATION.md §6 (watch loop): an index that was built (reserve + append) or loaded from

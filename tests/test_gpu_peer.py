@@ -159,6 +159,18 @@ def test_peer_failure_reaches_is_poisoned():
     ix.close()
 
 
+def _warm(ix, dim, batch=False, sparse_nnz=0):
+    """Emulated ranks share ONE device: a cudaMalloc issued by rank A's host thread while rank B's
+    exchange kernel is already spinning for A waits for that kernel (device-wide implicit
+    synchronisation) — a deadlock until the exchange times out.  The library's lazily allocated
+    scratch (tensor-core batch scratch, sparse bounds) is therefore touched once per shard, locally,
+    before the rank threads start.  Real multi-GPU ranks (one device each) are not affected."""
+    if batch:
+        ix.search_batch_rows(O.fast_unit_rows(8, dim, seed=999), 20)
+    if sparse_nnz:
+        ix.search_sparse_rows(np.arange(sparse_nnz, dtype=np.uint32), np.ones(sparse_nnz, f32), 500)
+
+
 def _rank_devices(max_ranks=4):
     """Device of every rank: one GPU each when the box has several, else 2 ranks emulated on cuda:0."""
     import torch
@@ -186,6 +198,7 @@ def test_ranks_in_process_fused_scan_exchange_merge(storage):
         row0, nl = shard_range(n, G, g)
         ix = cqs_b200.B200Index(dim, storage=storage, devices=[devs[g]], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        _warm(ix, dim, batch=True)
         shards.append(ix)
         groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
@@ -251,6 +264,64 @@ def test_ranks_in_process_fused_scan_exchange_merge(storage):
     whole.close()
 
 
+def test_ranks_shadow_scan_flag_travels_with_the_exchange():
+    """STORAGE_BF16_F32 shards: the shadow scan + f32 rescoring runs per shard inside the fused
+    kernel; a shard that cannot prove its list raises bit 31 of its list length, the bit reaches every
+    rank with the exchange, and every rank repeats the search on its f32 rows.  Result == unsharded f32."""
+    import cqs_b200
+    from cqs_b200.sharded import PeerGroup, shard_range, search_sharded, search_batch_sharded
+    devs = _rank_devices(2)
+    G = len(devs)
+    rng = np.random.default_rng(19)
+    n, dim = 60_000, 768
+    rows = O.fast_unit_rows(n, dim, seed=61)
+    base = rows[11].copy()
+    for j in range(150):                                    # near-duplicates, all inside shard 0
+        v = base + rng.standard_normal(dim).astype(f32) * f32(2e-5)
+        rows[50 + 13 * j] = v / np.linalg.norm(v)
+    qs = O.fast_unit_rows(6, dim, seed=62)
+    qs[0] = base
+    whole = cqs_b200.B200Index(dim, storage="f32", devices=[0])
+    whole.append(None, rows); whole.finalize()
+    shards, groups = [], []
+    for g in range(G):
+        row0, nl = shard_range(n, G, g)
+        ix = cqs_b200.B200Index(dim, storage="bf16+f32", devices=[devs[g]], row_base=row0)
+        ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        shards.append(ix); groups.append(PeerGroup(devs[g], G, g))
+    PeerGroup.connect_local(groups)
+    res = [None] * G
+
+    def run(g):
+        out = [search_sharded(shards[g], groups[g], qs[i], kk) for i in range(6) for kk in (20, 100)]
+        out.append(search_batch_sharded(shards[g], groups[g], qs[:4], 20))     # < 8 queries: exact lanes
+        res[g] = out
+
+    th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    i = 0
+    for qi in range(6):
+        for kk in (20, 100):
+            a, b = whole.search_rows(qs[qi], kk)
+            for g in range(G):
+                c, d = res[g][i]
+                assert np.array_equal(a, c) and np.array_equal(b.view(np.uint32), d.view(np.uint32)), (qi, kk, g)
+            i += 1
+    for g in range(G):
+        r, s, nn = res[g][i]
+        for qi in range(4):
+            a, b = whole.search_rows(qs[qi], 20)
+            assert int(nn[qi]) == 20 and np.array_equal(r[qi], a) and np.array_equal(s[qi].view(np.uint32), b.view(np.uint32))
+    for g in range(G):
+        assert groups[g].status() == 0
+        groups[g].close(); shards[g].close()
+    whole.close()
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
@@ -278,6 +349,8 @@ def _ipc_worker(rank, world, port, out):
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
         whole = cqs_b200.B200Index(dim, storage=storage, devices=[dev])
         whole.append(None, rows); whole.finalize()
+        ix.search_batch_rows(queries[:8], k)                # both processes may share cuda:0: allocate the
+        dist.barrier()                                       # batch scratch before any exchange kernel spins
         pg = PeerGroup.from_dist(dist, dev)                  # CUDA IPC handles over all_gather_object
         for qi in range(Q):
             a, b = whole.search_rows(queries[qi], k)
@@ -333,6 +406,7 @@ def test_ranks_sharded_hybrid_equals_unsharded():
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
         lo, hi = int(indptr[row0]), int(indptr[row0 + nl])
         ix.sparse_attach(indptr[row0:row0 + nl + 1] - indptr[row0], tok[lo:hi], w[lo:hi], vocab)
+        _warm(ix, dim, sparse_nnz=48)
         shards.append(ix); groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
     cases = []
@@ -397,6 +471,7 @@ def test_ranks_sharded_batch_with_exact_fallback():
         row0, nl = shard_range(n, G, g)
         ix = cqs_b200.B200Index(dim, storage="bf16", devices=[devs[g]], row_base=row0)
         ix.append(None, rows[row0:row0 + nl]); ix.finalize()
+        _warm(ix, dim, batch=True)
         shards.append(ix); groups.append(PeerGroup(devs[g], G, g))
     PeerGroup.connect_local(groups)
     res = [None] * G

@@ -17,7 +17,7 @@ ix.finalize()
 ix.set_timing(True)
 q = np.random.default_rng(0).standard_normal(768).astype(np.float32); q /= np.linalg.norm(q)
 lib.cqs_b200_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
-for k in (1, 20, 500):
+for k in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1, 20, 500)):
     for i in range(4):
         ix.search_rows(q, k)
     tr = np.zeros(148 * 8, np.uint64)
