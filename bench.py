@@ -456,6 +456,9 @@ def time_single(c, ix, pg, queries, k, Q, steps, warmup, transport="peer", pipel
     barrier(c)
     ms_local = e0.elapsed_time(e1)
     launches = lib.cqs_b200_kernel_launches() - launches0
+    # STORAGE_BF16_F32: bit 31 of out_n = that query's shadow-scan pool was not proven complete (the host
+    # entry points re-run such queries on the f32 rows; the device-resident path reports them)
+    unproven = int((d_n.cpu().numpy().view(np.uint32) >> 31).sum())
     per_rank_ms = [ms_local]
     if world > 1:
         allms = torch.empty((world,), device=dev)
@@ -530,7 +533,7 @@ def time_single(c, ix, pg, queries, k, Q, steps, warmup, transport="peer", pipel
                 (("cqs_b200_search" if pg is None else "cqs_b200_search_sharded") + ", one blocking call per query"))
     return {"ms": ms, "per_rank_ms": per_rank_ms, "launches": int(launches), "clocks": clk.summary(),
             "value": nq_timed / (ms / 1e3), "e2e_value": nq_timed / e2e_s, "nq_timed": nq_timed, "lanes": P,
-            "e2e_call": e2e_call, "batch_call": batch_call,
+            "e2e_call": e2e_call, "batch_call": batch_call, "unproven_last_step": unproven,
             "p50_ms": float(np.median(lat) * 1e3) if lat else None,
             "p95_ms": float(np.percentile(lat, 95) * 1e3) if lat else None}
 
@@ -903,8 +906,12 @@ def build_parser():
     ap.add_argument("--queries-per-step", type=int, default=0, help="headline: queries per step (0 = 64 x N)")
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"], help="headline corpus storage")
     ap.add_argument("--rows", type=int, default=N_ROWS, help="headline corpus rows")
-    ap.add_argument("--big-storage", default="bf16", choices=["bf16", "bf16+f32"],
-                    help="storage of the configs[2]/[3] corpora (10M / 12.5M-per-GPU rows)")
+    ap.add_argument("--big-storage", default="bf16+f32", choices=["bf16", "bf16+f32"],
+                    help="storage of the configs[2]/[3] corpora (10M / 12.5M-per-GPU rows): bf16+f32 = bf16 rows for the "
+                         "scans + f32 master rows for the rescoring (answers identical to the f32 brute force); bf16 = "
+                         "the rounded rows are the corpus")
+    ap.add_argument("--no-bf16-only", action="store_true",
+                    help="N = 1: skip the *_bf16only twins of the big records (2 B/elem storage, rounded corpus)")
     ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS, help="rows per GPU of the configs[3] records")
     ap.add_argument("--batch-rows", type=int, default=BATCH_ROWS, help="rows of the configs[2] record (N = 1)")
     ap.add_argument("--records", default="all", help="comma list out of: " + ",".join(ALL_RECORDS) + " | all | none")
@@ -1053,6 +1060,9 @@ def main():
     if "batch_10M_clustered" in want and world == 1:
         extra.extend(big_records(c, args, pg, "clustered", ["batch_10M_clustered"], P, t_start))
         log(f"big clustered records done, {time.perf_counter() - t_start:.0f}s")
+    if big_uniform and world == 1 and not args.no_bf16_only and args.big_storage != "bf16":
+        extra.extend(big_records(c, args, pg, "uniform", big_uniform, P, t_start, storage="bf16", suffix="_bf16only"))
+        log(f"bf16-only twins done, {time.perf_counter() - t_start:.0f}s")
 
     if rank == 0:
         line["extra"] = extra
@@ -1066,14 +1076,14 @@ def main():
 
 
 # ======== configs[2] / configs[3]: the big bf16 corpora ========
-def big_records(c, args, pg, mode, names, P, t_start):
+def big_records(c, args, pg, mode, names, P, t_start, storage=None, suffix=""):
     """One 12.5M-rows-per-GPU corpus; at N = 1 its first 10M rows are configs[2] (the index is
     finalized at 10M rows, measured, re-opened and extended — the TieredIndex::extend path)."""
     import cqs_b200
     from cqs_b200.capi import lib, check
     from cqs_b200.sharded import shard_range
     torch, world, rank = c.torch, c.world, c.rank
-    storage = args.big_storage
+    storage = storage or args.big_storage
     n_big = args.shard_rows * world
     row0b, nlb = shard_range(n_big, world, rank)
     steps_b, warm_b = 4, 3
@@ -1082,6 +1092,7 @@ def big_records(c, args, pg, mode, names, P, t_start):
     o_stored = BlockOracle(pq, K, c.cpu_threads)
     o_exact = BlockOracle(pq, K, c.cpu_threads) if storage == "bf16" else None
     oracles = [(o_stored, "stored")] + ([(o_exact, "exact")] if o_exact else [])
+    exact_for_recall = o_exact if o_exact is not None else o_stored   # bf16+f32: the f32 rows ARE the corpus
     data = f"synthetic ({mode})"
     want_sharded = mode == "uniform" and any(n.startswith("sharded") for n in names)
     want10 = world == 1 and any(n.startswith("batch_10M") for n in names) and (args.batch_rows < nlb or not want_sharded)
@@ -1100,12 +1111,12 @@ def big_records(c, args, pg, mode, names, P, t_start):
     for done in fill_index(c, ixb, storage, row0b, nlb, mode, oracles):
         if want10 and done == min(args.batch_rows, nlb):
             s_rows, s_sc, s_cpu, s_fed = o_stored.snapshot()
-            e_rows = o_exact.snapshot()[0] if o_exact else None
+            e_rows = exact_for_recall.snapshot()[0]
             ixb.finalize()
             finalized = True
             torch.cuda.empty_cache()
             log(f"{mode}: {done} rows built, measuring configs[2], {time.perf_counter() - t_start:.0f}s")
-            r, tb = measure_batch("batch_10M" if mode == "uniform" else "batch_10M_clustered", done, done, None,
+            r, tb = measure_batch(("batch_10M" if mode == "uniform" else "batch_10M_clustered") + suffix, done, done, None,
                                   f"exact top-{K}, {BATCH_Q}-query batches, {done}x{DIM} {storage} (BASELINE configs[2])")
             r["parity"] = batch_parity(c, tb, bq, BATCH_Q, K, s_rows, s_sc, e_rows)
             r["cpu_baseline"] = {"value": P / s_cpu, "unit": UNIT, "cores": c.cpu_threads, "kind": "port",
@@ -1121,7 +1132,7 @@ def big_records(c, args, pg, mode, names, P, t_start):
     torch.cuda.empty_cache()
     if want_sharded:
         log(f"{mode}: {nlb} rows/GPU built, measuring configs[3], {time.perf_counter() - t_start:.0f}s")
-        par, (g_rows, g_sc) = sharded_parity(c, ixb, pg, pq, K, o_stored, o_exact)
+        par, (g_rows, g_sc) = sharded_parity(c, ixb, pg, pq, K, o_stored, exact_for_recall)
         all_cpu = gather_objects(c, (o_stored.cpu_s, o_stored.rows_fed))
         cpu_b = {"value": P / max(a[0] for a in all_cpu), "unit": UNIT, "cores": c.cpu_threads * world, "kind": "port",
                  "sample": f"{P} queries over the full {n_big}x{DIM} corpus ({world} shard(s) scored concurrently on "
@@ -1135,13 +1146,20 @@ def big_records(c, args, pg, mode, names, P, t_start):
                               workload=f"exact top-{K}, single query at a time, {n_big}x{DIM} {storage} row-sharded over "
                                        f"{world} GPU(s), {nlb} rows per GPU (BASELINE configs[3]; 100M rows at N = 8)",
                               scaling="weak", data=data, traffic_key=f"scan_topk_kernel:{nlb}x{DIM}:{storage}")
-            r["record"] = "sharded_single"
+            r["record"] = "sharded_single" + suffix
+            r["config"]["storage"] = storage
+            r["config"]["hbm_footprint_bytes_per_gpu"] = nlb * DIM * {"bf16": 2, "bf16+f32": 6}.get(storage, 4)
+            if storage == "bf16+f32":
+                r["config"]["scan"] = ("bf16 shadow rows streamed (2 B/elem, what roofline.achieved counts), k' = 32 candidates "
+                                       "re-scored on the f32 master rows in the kernel tail, pool proven complete or the query "
+                                       "re-run on the f32 rows")
+                r["unproven_queries_last_timed_step"] = ts["unproven_last_step"]
             r["parity"] = par
             r["cpu_baseline"] = cpu_b
             r["roofline"]["target"] = ">= 0.80 of aggregate nominal HBM (north star)"
             recs.append(r)
         if "sharded_batch" in names:
-            r, tb = measure_batch("sharded_batch", n_big, nlb, pg,
+            r, tb = measure_batch("sharded_batch" + suffix, n_big, nlb, pg,
                                   f"exact top-{K}, {BATCH_Q}-query batches, {n_big}x{DIM} {storage} row-sharded over {world} "
                                   f"GPU(s), {nlb} rows per GPU (BASELINE configs[3])")
             r["parity"] = batch_parity(c, tb, bq, BATCH_Q, K, g_rows, g_sc, None)
