@@ -370,16 +370,24 @@ struct TopK {
 // paid by every CTA at the end of its scan and again by the last CTA's merge).
 // Not inlined (TopK by value: a handful of shared-memory pointers): the scan file instantiates
 // 48 kernels and this tail code would otherwise be compiled into each of them.
+#define CQS_STAMP(tr, i)                                                        \
+  do {                                                                          \
+    if ((tr) && tk.g.tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"((tr)[i])); \
+  } while (0)
 template <int ITEMS>
-__device__ __noinline__ void topk_finish(TopK tk, uint32_t k) {
+__device__ __noinline__ void topk_finish(TopK tk, uint32_t k, unsigned long long* stamps = nullptr) {
   tk.g.sync();
+  if (stamps && tk.g.tid == 0) stamps[7] = *tk.cnt;
   if (min(*tk.cnt, tk.cap) > kRankSortMax) {
     const ckey_t before = *tk.thr;
     tk.template select<ITEMS>(k);
     if (tk.g.tid == 0 && before > *tk.thr) *tk.thr = before;
     tk.g.sync();
+    CQS_STAMP(stamps, 4);
     if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k) tk.template select<ITEMS>(k);
+    CQS_STAMP(stamps, 5);
   }
+  if (stamps && tk.g.tid == 0) stamps[6] = *tk.cnt;
   tk.compact(k);
 }
 
@@ -412,6 +420,9 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
                                                         ckey_t thr0 = 0) {
   // thr0: a lower bound of the global k-th best key the caller already knows (0 = none)
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
+  // development aid: extra stamps of the merge go to the last row of the trace buffer
+  unsigned long long* mstamps = trace ? trace - (size_t)blockIdx.x * 8 + (size_t)(kPartialStride - 1) * 8 : nullptr;
+  CQS_STAMP(mstamps, 0);
   for (uint32_t l = tid; l < G; l += T) s_pos[l] = __ldcg(partial_cnt + l);
   if (tid == 0) {
     *tk.cnt = 0;
@@ -444,6 +455,7 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
     }
     tk.g.sync();
   }
+  CQS_STAMP(mstamps, 1);
   // ---- 2. rounds ----
   uint32_t b = (tk.cap / 2) / G;  // at most cap/2 pushes per round
   if (b == 0) b = 1;
@@ -496,7 +508,9 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
     }
     tk.g.sync();
   }
-  topk_finish<ITEMS>(tk, k);
+  CQS_STAMP(mstamps, 2);
+  if (mstamps && tid == 0) mstamps[3] = *tk.thr;
+  topk_finish<ITEMS>(tk, k, mstamps);
   if (trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace[6]));
   if (out_scores == nullptr) return;   // caller post-processes the sorted keys in tk.buf[0..*tk.cnt)
   uint32_t n = *tk.cnt;

@@ -272,10 +272,10 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaEventCreate(&s.ev_b0));
   CK(ix, cudaEventCreate(&s.ev_b1));
   if (ix->shards.size() == 1) {
-    // Query / result buffers of the batch entry points (27 MB), allocated up front: a cudaMalloc
-    // issued later, while a peer rank's exchange kernel is already spinning for this rank on the
-    // SAME device (ranks emulated on one GPU), waits for that kernel — i.e. for its timeout.
-    // Only the 250 MB scratch of the tensor-core path stays lazy (first bf16 batch).
+    // Query / result buffers of the batch entry points (27 MB), allocated up front so that no
+    // search call allocates between its kernels (a device allocation can serialise against
+    // kernels that are already waiting for this rank's part of an exchange).  Only the 250 MB
+    // scratch of the tensor-core path stays lazy (first bf16 batch).
     const uint32_t ld = ix->layout.ld;
     CK(ix, cudaMalloc((void**)&s.d_bq, sizeof(float) * (size_t)kBatchMaxQ * ld));
     CK(ix, cudaMalloc((void**)&s.d_bout_scores, sizeof(float) * (size_t)kBatchMaxQ * kMaxK));
@@ -2185,6 +2185,7 @@ int cqs_b200_debug_batch_flags(cqs_b200_index* ix, uint32_t* out, uint32_t n) tr
   return cudaMemcpy(out, ix->shards[0].d_bflags, 4 * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : CQS_B200_ERR_CUDA;
 } API_CATCH
 float cqs_b200_debug_last_batch_ms(cqs_b200_index* ix) { return ix ? ix->last_batch_ms : 0.f; }
+float cqs_b200_debug_max_row_delta(cqs_b200_index* ix) { return ix && !ix->shards.empty() ? ix->shards[0].max_row_delta : -1.f; }
 float cqs_b200_debug_max_row_norm(cqs_b200_index* ix) { return ix && !ix->shards.empty() ? ix->shards[0].max_row_norm : -1.f; }
 // copies the trace stamps of shard 0
 int cqs_b200_debug_trace(cqs_b200_index* ix, unsigned long long* out, uint32_t n_words) try {
