@@ -1,0 +1,80 @@
+// debug_topk.cu — development aid (not part of the public header): times the CTA-level top-k
+// building blocks of common.cuh (select / compact / topk_finish / prune) in isolation, one CTA
+// of 256 threads, globaltimer around each repetition, so that the tail of the scan kernels can be
+// tuned from measurements instead of guesses.  tools/bench_topk.py drives it.
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace cqs {
+namespace {
+constexpr uint32_t kDbgCap = 4096;
+constexpr int kDbgThreads = 256;
+
+__device__ __forceinline__ uint64_t splitmix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// op: 0 = select(k), 1 = compact(k), 2 = topk_finish(k), 3 = prune(median key)
+__global__ void __launch_bounds__(kDbgThreads) debug_topk_kernel(int op, uint32_t n, uint32_t k, uint32_t reps,
+                                                                 unsigned long long* out_ns, uint32_t* out_cnt) {
+  __shared__ ckey_t s_buf[kDbgCap];
+  __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
+  __shared__ uint32_t s_cnt;
+  __shared__ ckey_t s_thr;
+  const uint32_t tid = threadIdx.x;
+  TopK tk{s_buf, &s_cnt, &s_thr, kDbgCap, Group{tid, kDbgThreads, 0}, s_hist};
+  unsigned long long total = 0;
+  for (uint32_t r = 0; r < reps; ++r) {
+    // keys shaped like scan candidates: scores ~ tail of a normal (0.1 .. 0.2), unique rows
+    for (uint32_t i = tid; i < n; i += kDbgThreads) {
+      const uint64_t h = splitmix((uint64_t)r * 1000003ull + i);
+      const float u = (float)(h >> 40) * (1.0f / 16777216.0f);
+      const float score = 0.1f - 0.02f * __logf(1.0f - u + 1e-7f) * 0.2f;
+      s_buf[i] = make_key(score, (uint32_t)(h & 0xFFFFFF) * 64u + (i & 63u));
+    }
+    if (tid == 0) {
+      s_cnt = n;
+      s_thr = 0;
+    }
+    __syncthreads();
+    unsigned long long t0 = 0, t1 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (op == 0) tk.template select<kDbgCap / kDbgThreads>(k);
+    else if (op == 1) tk.compact(k);
+    else if (op == 2) topk_finish<kDbgCap / kDbgThreads>(tk, k);
+    else tk.template prune<kDbgCap / kDbgThreads>(make_key(0.105f, 0));
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (r > 0) total += t1 - t0;   // first repetition warms the instruction cache
+    }
+  }
+  if (tid == 0) {
+    *out_ns = total / (reps > 1 ? reps - 1 : 1);
+    *out_cnt = s_cnt;
+  }
+}
+}  // namespace
+}  // namespace cqs
+
+extern "C" int cqs_b200_debug_topk_ns(int device, int op, uint32_t n, uint32_t k, uint32_t reps,
+                                      unsigned long long* out_ns, uint32_t* out_cnt) {
+  using namespace cqs;
+  if (n > kDbgCap || reps < 2) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -2;
+  unsigned long long* d_ns = nullptr;
+  uint32_t* d_cnt = nullptr;
+  if (cudaMalloc((void**)&d_ns, 8) != cudaSuccess || cudaMalloc((void**)&d_cnt, 4) != cudaSuccess) return -2;
+  debug_topk_kernel<<<1, kDbgThreads>>>(op, n, k, reps, d_ns, d_cnt);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_ns, d_ns, 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_ns);
+  cudaFree(d_cnt);
+  return e == cudaSuccess ? 0 : -2;
+}

@@ -71,6 +71,8 @@ bool choose_layout(uint32_t dim, int storage, RowLayout* out) {
 }
 
 uint32_t shadow_kprime(uint32_t k) {
+  static const uint32_t kp_env = getenv("CQS_B200_SHADOW_KP") ? (uint32_t)atoi(getenv("CQS_B200_SHADOW_KP")) : 0;
+  if (kp_env >= k && kp_env <= kMaxK) return kp_env;   // development aid
   if (k <= 24) return 32;                      // per-warp register lists (SMALLK) still apply
   const uint32_t extra = k / 4 < 44 ? 44 : k / 4;
   const uint32_t kp = (k + extra + 31) / 32 * 32;

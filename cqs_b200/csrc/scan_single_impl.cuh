@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
     j_need = (k + m_pub - 1) / m_pub;
     if (j_need > gridDim.x) m_pub = 0;
   }
+  float thr_s = __uint_as_float(0xFF800000u);   // score of the current threshold key (-inf: none yet)
   ckey_t* s_vm = reinterpret_cast<ckey_t*>(s_pos);   // [0]: select()'s m-th-key bound (s_pos is free until the merge)
   uint32_t it = 0, s = 0, ph = 0;
   for (;; ++it) {
@@ -371,8 +372,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
 #pragma unroll
     for (int u = 1; u < U; ++u)
       if (lane == u) mine = sc[u];
+    // Warp-uniform fast reject: in steady state none of a tile's rows beats the current
+    // threshold, and the key / filter / push code below (a third of the loop's instructions)
+    // is skipped.  thr_s is the threshold's SCORE (-inf while there is none): a key can only
+    // beat the threshold key if its score is >= that (ties go on to the exact key compare);
+    // NaN never qualifies and is dropped anyway.  Not applied with the score fold (rare).
+    const bool maybe = p.sig.pipeline || __any_sync(0xffffffffu, lane < U && mine >= thr_s);
     ckey_t mykey = 0;
-    if (lane < U && row0 + lane < n) {
+    if (maybe && lane < U && row0 + lane < n) {
       const uint64_t r = row0 + lane;
       const uint32_t bits = __float_as_uint(mine);
       bool ok = finite_bits(bits);
@@ -403,14 +410,17 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
       if (ok) mykey = make_key(sc, (uint32_t)r);
     }
     if (SMALLK) {
+      if (maybe) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const ckey_t key = __shfl_sync(0xffffffffu, mykey, u);
-        if (key > wthr) {  // warp-uniform
-          const uint32_t pos = __popc(__ballot_sync(0xffffffffu, slot > key));
-          const ckey_t up = __shfl_up_sync(0xffffffffu, slot, 1);
-          slot = lane < pos ? slot : (lane == pos ? key : up);
-          wthr = __shfl_sync(0xffffffffu, slot, k - 1);
+        for (int u = 0; u < U; ++u) {
+          const ckey_t key = __shfl_sync(0xffffffffu, mykey, u);
+          if (key > wthr) {  // warp-uniform
+            const uint32_t pos = __popc(__ballot_sync(0xffffffffu, slot > key));
+            const ckey_t up = __shfl_up_sync(0xffffffffu, slot, 1);
+            slot = lane < pos ? slot : (lane == pos ? key : up);
+            wthr = __shfl_sync(0xffffffffu, slot, k - 1);
+            if (wthr) thr_s = key_score(wthr);
+          }
         }
       }
       continue;
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
       }
       if (m_pub) refresh_global_thr(tk, reinterpret_cast<ckey_t*>(s_hist), p.col, gridDim.x, j_need);
       thr = s_thr;
+      if (thr) thr_s = key_score(thr);
     }
   }
   TRACE(1);
