@@ -124,7 +124,7 @@ struct BatchArgs {
   uint32_t* d_flags;         // [nq]: 1 = not provably exact, caller re-runs the exact scan
 };
 size_t batch_scratch_bytes(uint32_t nq_pad, uint32_t ld);
-uint32_t batch_kprime(uint32_t k);
+uint32_t batch_kprime(uint32_t k, bool shadow);
 cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_max_row_norm(const void* d_rows, uint64_t n_rows, RowLayout layout, float* d_out,
                                 cudaStream_t stream);

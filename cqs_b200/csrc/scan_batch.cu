@@ -630,8 +630,13 @@ cudaError_t launch_max_row_delta(const void* d_rows_f32, const void* d_rows_bf16
   return cudaGetLastError();
 }
 
-uint32_t batch_kprime(uint32_t k) {
-  uint32_t extra = k / 4 < 44 ? 44 : k / 4;
+// Candidates kept per query.  The pool must reach down to (k-th exact score - E) for the proof to
+// succeed; with an f32 master behind bf16 rows E carries the row rounding distance as well as the
+// query's (~2x), so the pool is deeper there (measured on clustered rows, 2M..10M: the exact-score gap
+// rank 20 -> rank 64 is 0.0036..0.0043 against E = 0.0037, rank 20 -> rank 128 is 0.0072).
+uint32_t batch_kprime(uint32_t k, bool shadow) {
+  const uint32_t floor_extra = shadow ? 108 : 44, frac = shadow ? k / 2 : k / 4;
+  uint32_t extra = frac < floor_extra ? floor_extra : frac;
   uint32_t kp = (k + extra + 31) / 32 * 32;
   return kp > 1536 ? 1536 : kp;
 }
@@ -652,7 +657,7 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
     return cudaErrorInvalidValue;
   const uint32_t nq_pad = (a.nq + kBM - 1) / kBM * kBM;
   const uint32_t ld = a.layout.ld;
-  const uint32_t kprime = batch_kprime(a.k);
+  const uint32_t kprime = batch_kprime(a.k, a.max_row_delta > 0.f);
   // carve the scratch
   uint8_t* base = (uint8_t*)a.d_scratch;
   __nv_bfloat16* q16 = (__nv_bfloat16*)base;
