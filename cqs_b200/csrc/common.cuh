@@ -172,10 +172,10 @@ struct TopK {
     if (slot < cap) buf[slot] = key;  // cannot fail when the caller honours the bound
   }
   // Collective.  Afterwards buf[0..min(n,k)) holds the best keys, descending.
-  __device__ __forceinline__ void compact(uint32_t k) {
+  __device__ __forceinline__ void compact(uint32_t k, uint32_t rank_sort_max = kRankSortMax) {
     g.sync();
     uint32_t n = min(*cnt, cap);
-    if (n <= kRankSortMax) {
+    if (n <= rank_sort_max) {
       // small n: rank sort.  Every thread counts how many keys beat its own (all
       // threads read the same address each step -> shared-memory broadcast) and
       // scatters the key to that rank in the scratch half of the buffer.  Keys are

@@ -19,7 +19,7 @@ __device__ __forceinline__ uint64_t splitmix(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-// op: 0 = select(k), 1 = compact(k), 2 = topk_finish(k), 3 = prune(median key)
+// op: 0 = select(k), 1 = compact(k), 2 = topk_finish(k), 3 = prune(median key), 4 = compact(k) forced bitonic
 __global__ void __launch_bounds__(kDbgThreads) debug_topk_kernel(int op, uint32_t n, uint32_t k, uint32_t reps,
                                                                  unsigned long long* out_ns, uint32_t* out_cnt) {
   __shared__ ckey_t s_buf[kDbgCap];
@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(kDbgThreads) debug_topk_kernel(int op, uint32_
     if (op == 0) tk.template select<kDbgCap / kDbgThreads>(k);
     else if (op == 1) tk.compact(k);
     else if (op == 2) topk_finish<kDbgCap / kDbgThreads>(tk, k);
+    else if (op == 4) tk.compact(k, 0);   // always the register/shuffle bitonic network
     else tk.template prune<kDbgCap / kDbgThreads>(make_key(0.105f, 0));
     __syncthreads();
     if (tid == 0) {

@@ -242,8 +242,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
     CK(ix, cudaMalloc((void**)&c.d_partial_cnt, sizeof(uint32_t) * kMaxGrid));
     CK(ix, cudaMalloc((void**)&c.d_done, 4 * sizeof(uint32_t)));
     CK(ix, cudaMemset(c.d_done, 0, 4 * sizeof(uint32_t)));
-    CK(ix, cudaMalloc((void**)&c.d_col, sizeof(ckey_t) * kMaxGrid));
-    CK(ix, cudaMemset(c.d_col, 0, sizeof(ckey_t) * kMaxGrid));
+    CK(ix, cudaMalloc((void**)&c.d_col, sizeof(ckey_t) * 2 * kMaxGrid));
+    CK(ix, cudaMemset(c.d_col, 0, sizeof(ckey_t) * 2 * kMaxGrid));
     CK(ix, cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
   }
   CK(ix, cudaMalloc((void**)&s.d_out_scores, sizeof(float) * kMaxK));
@@ -1676,12 +1676,13 @@ int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t*
 } API_CATCH
 
 static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
-                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits) {
-  CK(ix, cudaMemcpyAsync(s.d_q_tok, q_tok, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, s.stream));
-  CK(ix, cudaMemcpyAsync(s.d_q_w, q_w, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, s.stream));
+                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st = nullptr) {
+  if (!st) st = s.stream;
+  CK(ix, cudaMemcpyAsync(s.d_q_tok, q_tok, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, st));
+  CK(ix, cudaMemcpyAsync(s.d_q_w, q_w, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, st));
   const size_t need = sparse_bounds_bytes(s.n_rows, q_nnz);
   if (need > s.bounds_bytes) {
-    CK(ix, cudaStreamSynchronize(s.stream));
+    CK(ix, cudaStreamSynchronize(st));
     cudaFree(s.d_bounds);
     s.d_bounds = nullptr;
     s.bounds_bytes = 0;
@@ -1695,7 +1696,7 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;
   a.d_out_scores = s.d_sp_scores; a.d_out_rows = s.d_sp_rows; a.d_out_n = s.d_sp_n;
-  CK(ix, launch_sparse_search(a, s.stream));
+  CK(ix, launch_sparse_search(a, st));
   return 0;
 }
 
@@ -1798,6 +1799,7 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   CK(ix, cudaMemsetAsync(s.d_out_n, 0, 4, s.stream));
   CK(ix, cudaMemsetAsync(s.d_sp_n, 0, 4, s.stream));
   if (peer) CK(ix, cudaMemsetAsync(s.d_spm_n, 0, 4, s.stream));
+  CK(ix, cudaEventRecord(s.ev_fork, s.stream));   // fork point of the sparse leg's stream (see below)
   const uint32_t* d_bits = nullptr;
   if (dense_ok) {
     PeerCtx pc;
@@ -1813,8 +1815,22 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   }
   if (q_nnz) {
     if (!q_tok || !q_w) return fail(CQS_B200_ERR_INVALID, "NULL sparse query");
-    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits);
+    // The legs are independent until the fusion.  The sparse leg goes to a second stream: its CTAs
+    // cannot share an SM with the scan's (shared memory), so they start as the scan's CTAs retire and
+    // run while the scan's LAST CTA merges the per-CTA lists (tens of microseconds on one SM at
+    // k = 500) — the dense leg's tail is hidden behind the sparse leg instead of preceding it.
+    // (Not with a filter bitset, which both legs read from one staging buffer, nor with a peer
+    // group, whose exchanges are ordered on one stream.)
+    cudaStream_t sp_st = (!peer && !bitset && dense_ok) ? s.lane_stream[0] : s.stream;
+    // (ev_fork was recorded BEFORE the dense launch: the sparse stream only waits for the resets
+    // above; the scan was submitted first and takes the SMs first)
+    if (sp_st != s.stream) CK(ix, cudaStreamWaitEvent(sp_st, s.ev_fork, 0));
+    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits, sp_st);
     if (rc) return rc;
+    if (sp_st != s.stream) {
+      CK(ix, cudaEventRecord(s.ev_join[0], sp_st));
+      CK(ix, cudaStreamWaitEvent(s.stream, s.ev_join[0], 0));
+    }
     if (peer) {
       PeerCtx pc;
       CK(ix, peer_begin(peer, s.stream, &pc, /*exclusive=*/true));

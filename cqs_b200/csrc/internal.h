@@ -63,7 +63,8 @@ struct ScanArgs {
   ckey_t* d_partial;         // [kMaxGrid][kMaxK] scratch
   uint32_t* d_partial_cnt;  // [kMaxGrid]
   uint32_t* d_done;         // [2]: CTA ticket + tile counter, zero between launches
-  ckey_t* d_col;            // [kMaxGrid] shared-threshold scratch of the large-k path, zero between launches
+  ckey_t* d_col;            // [2 * kMaxGrid]: shared-threshold scratch of the large-k path (zero between launches)
+                            // + per-CTA exclusion bounds of the shadow scan
   float* d_out_scores;      // [k]
   uint64_t* d_out_rows;     // [k]
   uint32_t* d_out_n;        // [1]

@@ -20,6 +20,7 @@ struct ScanParams {
   uint32_t* partial_cnt;
   uint32_t* done;        // [0] finished-CTA ticket, [1] dynamic tile counter; zero between launches
   ckey_t* col;           // [kMaxGrid] large k: per-CTA published m-th-key bounds; zero between launches
+  ckey_t* excl;          // [kMaxGrid] shadow scan: per-CTA bound of the shadow keys it did not re-score
   float* out_scores;
   uint64_t* out_rows;
   uint32_t* out_n;

@@ -100,6 +100,7 @@ cudaError_t launch_scan_single(const ScanArgs& a, int num_sms, cudaStream_t st) 
   p.partial_cnt = a.d_partial_cnt;
   p.done = a.d_done;
   p.col = a.d_col;
+  p.excl = a.d_col + kMaxGrid;   // second half of the same scratch (written by every CTA before its ticket)
   p.out_scores = a.d_out_scores;
   p.out_rows = a.d_out_rows;
   p.out_n = a.d_out_n;

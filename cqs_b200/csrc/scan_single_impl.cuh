@@ -148,21 +148,88 @@ static __device__ __noinline__ void refresh_global_thr(TopK tk, ckey_t* colv, co
   tk.g.sync();
 }
 
-// STORAGE_BF16_F32 fast path, run by the last CTA on the merged candidate list (sorted keys of the
-// bf16 shadow scan in tk.buf[0..n), n <= k' = kp): every candidate is re-scored on its f32 master
-// row with the f32 scan's own arithmetic (LaneVec<0>: lane l owns elements (v*32+l)*4.., four
-// accumulators, the same butterfly) — the scores are bit-identical to a STORAGE_F32 scan — the best
-// k_out are kept and emitted, and the pool is proven complete:
-//   a row outside the pool has shadow score <= cut (the pool's k'-th shadow score), and
-//   |q.r - q.r16| = |q.(r - r16)| <= |q| * D, D = max_row_delta (measured at finalize), plus the fp32
-//   accumulation error of both dots (<= 2^-18 |q| R for ld <= 2048), so its exact score is <= cut + E.
-//   If the k_out-th exact score is > cut + E nothing outside the pool can belong to the answer.
-// Otherwise bit 31 of *out_n is raised and the host re-runs the query on the f32 master rows.
-static __device__ __noinline__ void rescore_and_emit(TopK tk, const ScanParams& p, uint32_t kp, float* out_scores,
-                                                     uint64_t* out_rows, uint32_t* out_n, float* s_red) {
+// STORAGE_BF16_F32 fast path (the scan streams the bf16 shadow rows, p.k = k' candidates per CTA).
+// EVERY CTA re-scores its own candidates (tk.buf[0..n), keys of the shadow scan) on their f32 master
+// rows before it emits its list — in parallel on all SMs, ~k' random 3 KB rows each — with the f32
+// scan's own arithmetic (LaneVec<0>: lane l owns elements (v*32+l)*4.., four accumulators, the same
+// butterfly), so the scores are bit-identical to a STORAGE_F32 scan.  The list is then sorted by
+// EXACT score and cut to k_out: the last CTA merges G short exact lists, exactly as for a k_out scan.
+// Four rows are in flight per warp.  Collective over tk.g; on return buf[0..*cnt) holds the valid
+// exact keys, descending.
+static __device__ __noinline__ void rescore_local(TopK tk, const ScanParams& p) {
   const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-  const uint32_t n = *tk.cnt;
-  const ckey_t cut_key = (n >= kp) ? tk.buf[kp - 1] : 0;   // pool not full: it holds every eligible row
+  tk.g.sync();
+  const uint32_t n = min(*tk.cnt, tk.cap);
+  const uint32_t ld4 = p.exact_nv * 32;   // float4 per row
+  const float4* q4 = reinterpret_cast<const float4*>(p.query);
+  for (uint32_t j0 = warp * 4; j0 < n; j0 += nwarps * 4) {
+    const float4* row[4];
+    uint32_t r[4];
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t j = min(j0 + u, n - 1);
+      r[u] = key_row(tk.buf[j]);
+      row[u] = reinterpret_cast<const float4*>(p.exact_rows) + (size_t)r[u] * ld4 + lane;
+      acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+    }
+    for (uint32_t v = 0; v < p.exact_nv; ++v) {
+      const float4 q = __ldg(q4 + v * 32 + lane);
+      float4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = __ldg(row[u] + v * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u][0] = fmaf(x[u].x, q.x, acc[u][0]);
+        acc[u][1] = fmaf(x[u].y, q.y, acc[u][1]);
+        acc[u][2] = fmaf(x[u].z, q.z, acc[u][2]);
+        acc[u][3] = fmaf(x[u].w, q.w, acc[u][3]);
+      }
+    }
+    float sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sc[u] = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
+    __syncwarp();
+    // a non-finite exact score drops the row (candidate.rs:275): its key becomes (0, ~row) — below every
+    // valid key (whose high word is >= 0x00800000) yet unique, as the rank sort requires
+    if (lane < 4 && j0 + lane < n) {
+      float mine = sc[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (lane == u) mine = sc[u];
+      uint32_t rr = r[0];
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (lane == u) rr = r[u];
+      tk.buf[j0 + lane] = finite_bits(__float_as_uint(mine)) ? make_key(mine, rr) : (ckey_t)(~rr);
+    }
+  }
+  tk.g.sync();
+  tk.compact(p.k_out);                       // exact sort; dropped candidates sink to the end
+  const uint32_t m = *tk.cnt;
+  uint32_t valid = 0;
+  for (uint32_t i = 0; i < m; ++i) valid += (tk.buf[i] >> 32) != 0 ? 1u : 0u;   // m <= k_out, broadcast reads
+  tk.g.sync();
+  if (tid == 0) *tk.cnt = valid;
+  tk.g.sync();
+}
+
+// Completeness proof of the shadow scan, by the last CTA (collective over tk.g).  excl[c] is an upper
+// bound of the SHADOW key of every row CTA c scanned but did not re-score (its streaming threshold /
+// the cut of its candidate list; 0 = it re-scored every eligible row).  With cut = max_c excl[c]:
+//   a row that was not re-scored has shadow score <= cut, and |q.r - q.r16| = |q.(r - r16)| <= |q| * D
+//   (D = max_row_delta, measured at finalize) plus the fp32 accumulation error of both dots
+//   (<= 2^-18 |q| R for ld <= 2048), so its exact score is <= cut + E.  If the k_out-th exact score of
+//   the merged answer is > cut + E, no such row can belong to the answer.
+// Returns kUnprovenBit when the proof fails (the host then re-runs the query on the f32 master rows).
+static __device__ __noinline__ uint32_t prove_shadow(TopK tk, const ScanParams& p, const ckey_t* excl, uint32_t G,
+                                                     float* s_red, ckey_t* s_cut) {
+  const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  if (tid == 0) *s_cut = 0;
   const uint32_t ld = p.exact_nv * 128;
   float qq = 0.f;
   for (uint32_t i = tid; i < ld; i += T) {
@@ -171,56 +238,23 @@ static __device__ __noinline__ void rescore_and_emit(TopK tk, const ScanParams& 
   }
   for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
   if (lane == 0) s_red[warp] = qq;
-  tk.g.sync();   // also: every thread has read cut_key before the keys are overwritten
-  for (uint32_t j = warp; j < n; j += nwarps) {
-    const ckey_t key = tk.buf[j];
-    const uint32_t r = key_row(key);
-    const uint8_t* row = p.exact_rows + (size_t)r * ld * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (uint32_t v = 0; v < p.exact_nv; ++v) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(row) + v * 32 + lane);
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p.query) + v * 32 + lane);
-      acc[0] = fmaf(x.x, q.x, acc[0]);
-      acc[1] = fmaf(x.y, q.y, acc[1]);
-      acc[2] = fmaf(x.z, q.z, acc[2]);
-      acc[3] = fmaf(x.w, q.w, acc[3]);
-    }
-    float s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    __syncwarp();
-    // a non-finite exact score drops the row (candidate.rs:275): its key becomes (0, ~row) — below every
-    // valid key (whose high word is >= 0x00800000) yet unique, as the rank sort requires
-    if (lane == 0) tk.buf[j] = finite_bits(__float_as_uint(s)) ? make_key(s, r) : (ckey_t)(~r);
-  }
   tk.g.sync();
-  tk.compact(p.k_out);                       // exact sort; dropped candidates sink to the end
-  const uint32_t m = *tk.cnt;
-  uint32_t valid = 0;
-  for (uint32_t i = 0; i < m; ++i) valid += (tk.buf[i] >> 32) != 0 ? 1u : 0u;   // m <= k_out <= 1024, broadcast reads
+  ckey_t mx = 0;
+  for (uint32_t l = tid; l < G; l += T) {
+    const ckey_t e = __ldcg(excl + l);
+    mx = e > mx ? e : mx;
+  }
+  if (mx) atomicMax(s_cut, mx);
+  tk.g.sync();
+  const ckey_t cut_key = *s_cut;
+  if (cut_key == 0) return 0;                 // every eligible row of the corpus was re-scored
   float qn = 0.f;
   for (uint32_t w = 0; w < nwarps; ++w) qn += s_red[w];
   qn = sqrtf(qn);
-  uint32_t flag = 0;
-  if (cut_key != 0) {
-    const float E = 1.001f * qn * (p.max_row_delta + 3.814697265625e-6f * p.max_row_norm);
-    if (valid < p.k_out || !(key_score(tk.buf[p.k_out - 1]) > key_score(cut_key) + E)) flag = kUnprovenBit;
-  }
-  for (uint32_t i = tid; i < p.k_out; i += T) {
-    if (i < valid) {
-      const ckey_t key = tk.buf[i];
-      out_scores[i] = key_score(key);
-      out_rows[i] = p.row_base + key_row(key);
-    } else {
-      out_scores[i] = __uint_as_float(0xFF800000u);
-      out_rows[i] = ~0ull;
-    }
-  }
-  if (tid == 0) {
-    *tk.cnt = valid;
-    *out_n = valid | flag;
-  }
-  tk.g.sync();
+  const float E = 1.001f * qn * (p.max_row_delta + 3.814697265625e-6f * p.max_row_norm);
+  const uint32_t n = *tk.cnt;                 // merged exact keys, descending, in tk.buf
+  if (n < p.k_out) return kUnprovenBit;
+  return key_score(tk.buf[p.k_out - 1]) > key_score(cut_key) + E ? 0u : kUnprovenBit;
 }
 
 // SMALLK (k <= 32): every consumer warp keeps its own sorted top-32 in registers
@@ -446,22 +480,43 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   }
   TRACE(1);
   ckey_t gthr = 0;
+  const bool rescore = p.exact_rows != nullptr;
   if (SMALLK) {
-    // combine the 8 warp lists: rank sort of 256 keys straight into the partial list
+    // combine the 8 warp lists: rank sort of 256 keys straight into the partial list (or, when the
+    // candidates are re-scored first, into a second shared-memory list)
     s_buf[ctid] = (lane < k) ? slot : 0;
     tk.g.sync();
     const ckey_t mine = s_buf[ctid];
+    uint32_t rank = 0;
     if (mine != 0) {
-      uint32_t rank = 0;
       for (uint32_t j = 0; j < kConsumers; ++j) rank += (s_buf[j] > mine) ? 1u : 0u;
       if (rank < k) {
-        p.partial[(size_t)blockIdx.x * kMaxK + rank] = mine;
+        if (rescore) s_buf[kConsumers + rank] = mine;
+        else p.partial[(size_t)blockIdx.x * kMaxK + rank] = mine;
         atomicAdd(&s_cnt, 1u);
       }
     }
-    tk.g.sync();
+    if (rescore) {
+      // anything this CTA dropped — a warp's full list rejecting a row, the cut of the 256-key union —
+      // is <= the union's k-th key (it contains every warp's k best)
+      const bool dropped = tk.g.any(wthr != 0 || (mine != 0 && rank >= k));
+      const uint32_t n_c = s_cnt;
+      const ckey_t excl = (dropped && n_c >= k) ? s_buf[kConsumers + k - 1] : 0;
+      tk.g.sync();
+      if (ctid < n_c) s_buf[ctid] = s_buf[kConsumers + ctid];   // k <= 32 < kConsumers
+      tk.g.sync();
+      rescore_local(tk, p);
+      const uint32_t mycnt = s_cnt;
+      if (ctid < mycnt) p.partial[(size_t)blockIdx.x * kMaxK + ctid] = s_buf[ctid];
+      if (ctid == 0) {
+        p.partial_cnt[blockIdx.x] = mycnt;
+        p.excl[blockIdx.x] = excl;
+      }
+    } else {
+      tk.g.sync();
+      if (ctid == 0) p.partial_cnt[blockIdx.x] = s_cnt;
+    }
     TRACE(2);
-    if (ctid == 0) p.partial_cnt[blockIdx.x] = s_cnt;
   } else {
     if (m_pub) {
       // whatever the other CTAs have published by now bounds the global k-th best: drop the
@@ -471,6 +526,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
       tk.template prune<kCap / kConsumers>(gthr);
     }
     topk_finish<kCap / kConsumers>(tk, k);
+    if (rescore) {
+      // rows this CTA scanned but does not re-score were filtered by its (monotone) streaming
+      // threshold or cut from its list: their shadow keys are <= max(shared bound, list cut)
+      const ckey_t cut = s_thr;
+      rescore_local(tk, p);
+      if (ctid == 0) p.excl[blockIdx.x] = gthr > cut ? gthr : cut;
+    }
     TRACE(2);
     const uint32_t mycnt = s_cnt;
     for (uint32_t i = ctid; i < mycnt; i += kConsumers)
@@ -490,25 +552,33 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
   const ckey_t thr0 = gthr;   // the shared threshold is a valid start for the merge
   if (m_pub)
     for (uint32_t l = ctid; l < gridDim.x; l += kConsumers) p.col[l] = 0;  // every CTA is past its last read
-  const bool rescore = p.exact_rows != nullptr;
+  // with re-scoring the partial lists hold EXACT keys cut to k_out: a plain k_out merge (the shared
+  // threshold of the shadow scan does not apply to exact keys)
   const uint32_t k_emit = rescore ? p.k_out : k;   // what leaves this kernel / goes to the peers
+  const ckey_t thr_m = rescore ? 0 : thr0;
   if (p.peer.world == 0) {
-    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, rescore ? nullptr : p.out_scores, p.out_rows, p.out_n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr0);
-    if (rescore) rescore_and_emit(tk, p, k, p.out_scores, p.out_rows, p.out_n, reinterpret_cast<float*>(s_hist));
+    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k_emit, p.partial, p.partial_cnt, gridDim.x,
+                                               p.row_base, p.out_scores, p.out_rows, p.out_n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr_m);
+    if (rescore) {
+      const uint32_t flag = prove_shadow(tk, p, p.excl, gridDim.x, reinterpret_cast<float*>(s_hist), &s_thr);
+      if (ctid == 0 && flag) *p.out_n |= flag;
+    }
   } else {
     // Row-sharded corpus: the shard's list goes into this rank's own mailbox
     // block and, by plain stores over NVLink, into every peer's; one release flag per peer
     // publishes it; then wait for the peers' lists and merge — the all-gather and the merge
     // ride in the tail of the scan, no collective call and no extra launch.
     const PeerBlock own = peer_block(p.peer, p.peer.rank, p.peer.rank);
-    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k, p.partial, p.partial_cnt, gridDim.x,
-                                               p.row_base, rescore ? nullptr : own.scores, own.rows, own.n,
-                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr0);
-    if (rescore) rescore_and_emit(tk, p, k, own.scores, own.rows, own.n, reinterpret_cast<float*>(s_hist));
+    merge_partials_and_emit<kCap / kConsumers>(tk, s_pos, k_emit, p.partial, p.partial_cnt, gridDim.x,
+                                               p.row_base, own.scores, own.rows, own.n,
+                                               p.trace ? p.trace + blockIdx.x * 8 : nullptr, thr_m);
     const uint32_t n = *tk.cnt;  // sorted keys are still in tk.buf[0..n)
-    const uint32_t n_word = rescore ? *own.n : n;   // carries kUnprovenBit to every rank
+    uint32_t n_word = n;         // carries kUnprovenBit to every rank
+    if (rescore) {
+      n_word |= prove_shadow(tk, p, p.excl, gridDim.x, reinterpret_cast<float*>(s_hist), &s_thr);
+      if (ctid == 0) *own.n = n_word;
+    }
     for (uint32_t e = ctid; e < p.peer.world * k_emit; e += kConsumers) {
       const uint32_t g = e / k_emit, i = e - g * k_emit;
       if (g == p.peer.rank || i >= n) continue;

@@ -5,10 +5,11 @@ import ctypes as C
 from cqs_b200.capi import lib
 f = lib.cqs_b200_debug_topk_ns
 f.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
-names = {0: "select", 1: "compact", 2: "topk_finish", 3: "prune"}
+names = {0: "select", 1: "compact", 2: "topk_finish", 3: "prune", 4: "compact/bitonic"}
 for op, cases in ((1, [(64, 64), (128, 128), (173, 100), (256, 256), (500, 500), (512, 500), (900, 500), (1024, 1024), (2048, 1024), (4096, 1024)]),
                   (0, [(600, 500), (900, 500), (1024, 100), (1024, 500), (2048, 500), (2048, 1024), (4096, 500), (4096, 1024)]),
                   (2, [(173, 100), (600, 500), (900, 500), (1100, 500), (1600, 1024), (2500, 500), (4096, 1024)]),
+                  (4, [(64, 64), (128, 128), (173, 100), (256, 256), (300, 300), (500, 500), (512, 500), (900, 500)]),
                   (3, [(1024, 0), (4096, 0)])):
     for n, k in cases:
         ns, cnt = C.c_uint64(0), C.c_uint32(0)
