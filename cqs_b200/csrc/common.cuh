@@ -146,7 +146,10 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
   }
 }
 
-constexpr uint32_t kRankSortMax = 512;  // compact() uses a rank sort up to this many keys
+// compact() uses a rank sort up to this many keys, the register/shuffle bitonic network above.
+// Measured (tools/bench_topk.py, one 256-thread CTA, warm): rank sort 128 / 256 / 500 keys = 1.3 /
+// 2.5 / 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us: they cross near 380.
+constexpr uint32_t kRankSortMax = 384;
 constexpr uint32_t kSelBuckets = 2048;  // histogram resolution of select()
 
 // Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
@@ -378,13 +381,14 @@ template <int ITEMS>
 __device__ __noinline__ void topk_finish(TopK tk, uint32_t k, unsigned long long* stamps = nullptr) {
   tk.g.sync();
   if (stamps && tk.g.tid == 0) stamps[7] = *tk.cnt;
-  if (min(*tk.cnt, tk.cap) > kRankSortMax) {
+  // a selection (2.6 us) pays off when it moves the sort to a smaller network / into rank-sort range
+  if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k + 64) {
     const ckey_t before = *tk.thr;
     tk.template select<ITEMS>(k);
     if (tk.g.tid == 0 && before > *tk.thr) *tk.thr = before;
     tk.g.sync();
     CQS_STAMP(stamps, 4);
-    if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k) tk.template select<ITEMS>(k);
+    if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k + 64) tk.template select<ITEMS>(k);
     CQS_STAMP(stamps, 5);
   }
   if (stamps && tk.g.tid == 0) stamps[6] = *tk.cnt;
