@@ -362,9 +362,9 @@ def test_bf16_shadow_scan_with_f32_rescoring_equals_f32_storage(cqs, config1):
     rows = rows.copy()
     rng = np.random.default_rng(9)
     base = rows[9000].copy()
-    for j in range(300):                                   # 300 CONSECUTIVE rows within ~2e-5 of each other: they
-        v = base + rng.standard_normal(768).astype(f32) * f32(2e-5)   # land in one CTA's tile run, whose candidate
-        rows[9001 + j] = v / np.linalg.norm(v)             # list (k' of them) cannot be proven complete
+    for j in range(6000):                                  # 6000 rows within ~2e-5 of each other: more than the
+        v = base + rng.standard_normal(768).astype(f32) * f32(2e-5)   # 148 CTAs x 32 candidates a k <= 24 scan re-scores,
+        rows[9001 + j] = v / np.linalg.norm(v)             # so rows it did NOT re-score tie with the answer: no proof
     a = cqs.B200Index(768, storage="f32")
     a.append(None, rows); a.finalize()
     b = cqs.B200Index(768, storage="bf16+f32")
