@@ -140,6 +140,7 @@ struct Shard {
 
 constexpr uint32_t kSpMaxQ = 1024;
 constexpr size_t kHostOutBytes = kMaxK * (8 + 4 + 4 + 4 + 1) + 64;
+constexpr size_t kOffHybridFlag = kMaxK * (8 + 4 + 4 + 4 + 1) + 8;   // completion word of the fused-pool layout
 
 }  // namespace
 
@@ -584,7 +585,8 @@ static int release_scratch(cqs_b200_index* ix, Shard::ScanScratch* c, cudaStream
 }
 
 constexpr size_t kOffScores = 0, kOffRows = sizeof(float) * kMaxK,
-                 kOffN = (sizeof(float) + sizeof(uint64_t)) * kMaxK, kOffFlag = kOffN + 4;
+                 kOffN = (sizeof(float) + sizeof(uint64_t)) * kMaxK,
+                 kOffFlag = kMaxK * (8 + 4 + 4 + 4 + 1) + 16;   // completion words live past both result layouts
 
 // Which rows a single-query scan streams.  STORAGE_BF16_F32 and a plain search (no score fold):
 // the bf16 shadow (2 B/elem) with an over-fetch of k' candidates that the kernel tail re-scores on
@@ -653,10 +655,10 @@ static int launch_dense(cqs_b200_index* ix, Shard& s, const float* query, uint32
 
 // Poll the completion word the kernel writes into mapped host memory; fall back to the
 // stream status every so often so a faulted kernel cannot hang the caller.
-static int wait_host_flag(cqs_b200_index* ix, Shard& s) {
+static int wait_host_flag(cqs_b200_index* ix, Shard& s, size_t flag_off = kOffFlag) {
   // acquire load: the result words in h_out that the caller reads next must not be
   // speculated ahead of the flag (matters on weakly ordered hosts, e.g. Grace)
-  const uint32_t* flag = (const uint32_t*)(s.h_out + kOffFlag);
+  const uint32_t* flag = (const uint32_t*)(s.h_out + flag_off);
   for (uint64_t spin = 0; __atomic_load_n(flag, __ATOMIC_ACQUIRE) != s.seq; ++spin) {
     if ((spin & 0xFFF) == 0xFFF) {
       CK(ix, cudaSetDevice(s.device));
@@ -1740,33 +1742,6 @@ int cqs_b200_search_sparse(cqs_b200_index* ix, const uint32_t* q_tok, const floa
   return CQS_B200_OK;
 } API_CATCH
 
-static int copy_fused_out(cqs_b200_index* ix, Shard& s, uint32_t cap, uint64_t* out_rows,
-                          float* out_fused, float* out_dense, float* out_sparse_raw,
-                          uint8_t* out_present, uint32_t* out_n, cudaStream_t st) {
-  uint8_t* h = s.h_out;
-  uint64_t* hr = (uint64_t*)h;
-  float* hf = (float*)(h + 8 * kMaxK);
-  float* hd = hf + kMaxK;
-  float* hs = hd + kMaxK;
-  uint8_t* hp = (uint8_t*)(hs + kMaxK);
-  uint32_t* hn = (uint32_t*)(hp + kMaxK);
-  CK(ix, cudaMemcpyAsync(hr, s.d_f_rows, 8 * cap, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaMemcpyAsync(hf, s.d_f_fused, 4 * cap, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaMemcpyAsync(hd, s.d_f_dense, 4 * cap, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaMemcpyAsync(hs, s.d_f_sraw, 4 * cap, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaMemcpyAsync(hp, s.d_f_present, cap, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaMemcpyAsync(hn, s.d_f_n, 4, cudaMemcpyDeviceToHost, st));
-  CK(ix, cudaStreamSynchronize(st));
-  uint32_t n = std::min(*hn, cap);
-  memcpy(out_rows, hr, 8 * n);
-  memcpy(out_fused, hf, 4 * n);
-  if (out_dense) memcpy(out_dense, hd, 4 * n);
-  if (out_sparse_raw) memcpy(out_sparse_raw, hs, 4 * n);
-  if (out_present) memcpy(out_present, hp, n);
-  *out_n = n;
-  return 0;
-}
-
 // peer == nullptr: this index alone.  Otherwise the corpus is row-sharded: the dense leg's scan
 // exchanges + merges in its tail (GLOBAL dense pool on every rank), the sparse leg's per-shard pool
 // goes through one gather+merge kernel (GLOBAL sparse pool), and every rank fuses the same two
@@ -1846,13 +1821,34 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   f.d_sparse_scores = peer ? s.d_spm_scores : s.d_sp_scores;
   f.d_n_sparse = peer ? s.d_spm_n : s.d_sp_n;
   f.alpha = alpha; f.pool_k = pool_k;
-  f.d_out_rows = s.d_f_rows; f.d_out_fused = s.d_f_fused; f.d_out_dense = s.d_f_dense;
-  f.d_out_sparse_raw = s.d_f_sraw; f.d_out_present = s.d_f_present; f.d_out_n = s.d_f_n;
+  // the fused pool is written straight into the host-mapped result buffer (layout of copy_fused_out)
+  // and a completion word is polled, as on the dense latency path
+  {
+    uint8_t* d = s.d_hout;
+    f.d_out_rows = (uint64_t*)d;
+    f.d_out_fused = (float*)(d + 8 * kMaxK);
+    f.d_out_dense = f.d_out_fused + kMaxK;
+    f.d_out_sparse_raw = f.d_out_dense + kMaxK;
+    f.d_out_present = (uint8_t*)(f.d_out_sparse_raw + kMaxK);
+    f.d_out_n = (uint32_t*)(f.d_out_present + kMaxK);
+    f.d_host_flag = (uint32_t*)(d + kOffHybridFlag);
+    f.seq = ++s.seq;
+    if (f.seq == 0) f.seq = s.seq = 1;
+  }
   CK(ix, launch_fuse_pools(f, s.stream));
   if (ix->timing) CK(ix, cudaEventRecord(s.ev_b1, s.stream));
-  rc = copy_fused_out(ix, s, pool_k, out_rows, out_fused, out_dense, out_sparse_raw, out_present,
-                      out_n, s.stream);
-  if (rc) return rc;
+  if ((rc = wait_host_flag(ix, s, kOffHybridFlag))) return rc;
+  {
+    const uint8_t* h = s.h_out;
+    const uint32_t n = std::min(*(const uint32_t*)(h + (8 + 4 + 4 + 4 + 1) * kMaxK), pool_k);
+    memcpy(out_rows, h, 8 * (size_t)n);
+    memcpy(out_fused, h + 8 * kMaxK, 4 * (size_t)n);
+    if (out_dense) memcpy(out_dense, h + 12 * kMaxK, 4 * (size_t)n);
+    if (out_sparse_raw) memcpy(out_sparse_raw, h + 16 * kMaxK, 4 * (size_t)n);
+    if (out_present) memcpy(out_present, h + 20 * kMaxK, n);
+    *out_n = n;
+  }
+  if (ix->timing) CK(ix, cudaEventSynchronize(s.ev_b1));
   // device time of the whole hybrid pipeline (both legs + fusion), read like the batch timer
   if (ix->timing) CK(ix, cudaEventElapsedTime(&ix->last_batch_ms, s.ev_b0, s.ev_b1));
   if (peer) {

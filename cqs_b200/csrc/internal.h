@@ -199,6 +199,8 @@ struct FuseArgs {
   float alpha; uint32_t pool_k;
   uint64_t* d_out_rows; float* d_out_fused; float* d_out_dense; float* d_out_sparse_raw;
   uint8_t* d_out_present; uint32_t* d_out_n;
+  uint32_t* d_host_flag = nullptr;  // optional: the outputs are host-mapped; publish `seq` here when they are written
+  uint32_t seq = 0;
 };
 cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t stream);
 

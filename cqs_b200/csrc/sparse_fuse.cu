@@ -230,16 +230,23 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
           lo = __ldg(row);
           hi = __ldg(row + 1);
         }
-        const uint32_t n_tok = min(32u, p.q_nnz - i0);
-        for (uint32_t j0 = 0; j0 < n_tok; j0 += kSpBatch) {
+        // Only the tokens that HAVE postings in this block are visited (most of a 64-token query's
+        // light tokens do not): the set bits of `present`, lowest first = query order, eight per
+        // batch so that all of a batch's posting loads are in flight together.  (Before: every token
+        // paid its shuffles and predicated loads — the kernel was issue-bound at 66 % of the slots.)
+        uint32_t present = __ballot_sync(0xffffffffu, hi > lo);
+        while (present) {
           uint2 pp[kSpBatch][2];
-          uint32_t ln[kSpBatch];
+          uint32_t ln[kSpBatch], tix[kSpBatch];
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
-            const uint32_t tl = __shfl_sync(0xffffffffu, lo, (j0 + u) & 31);
-            const uint32_t th = __shfl_sync(0xffffffffu, hi, (j0 + u) & 31);
-            ln[u] = (j0 + u < n_tok) ? th - tl : 0;   // <= 64
-            const uint64_t e = s.base[min(i0 + j0 + u, p.q_nnz - 1)] + tl + lane;
+            const bool have = present != 0;
+            tix[u] = have ? (uint32_t)(__ffs(present) - 1) : 0u;
+            present &= present - 1;     // clears the lowest set bit; 0 stays 0
+            const uint32_t tl = __shfl_sync(0xffffffffu, lo, tix[u]);
+            const uint32_t th = __shfl_sync(0xffffffffu, hi, tix[u]);
+            ln[u] = have ? th - tl : 0;   // <= 64
+            const uint64_t e = s.base[i0 + tix[u]] + tl + lane;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               pp[u][h] = make_uint2(0u, 0u);
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
             if (ln[u] == 0) continue;  // warp-uniform
-            const float qw = s.qw[i0 + j0 + u];
+            const float qw = s.qw[i0 + tix[u]];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               if (lane + 32 * h < ln[u]) {
@@ -484,6 +491,13 @@ __global__ void __launch_bounds__(kFuseThreads, 1) fuse_pools_kernel(const FuseA
     a.d_out_present[i] = (uint8_t)((pd ? 1 : 0) | (ps ? 2 : 0));
   }
   if (tid == 0) *a.d_out_n = n_out;
+  if (a.d_host_flag) {
+    // the pool went straight into host-mapped memory: make it visible system-wide, then publish the
+    // completion word the host polls (saves six D2H copies and the stream-sync wake-up per query)
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile uint32_t*>(a.d_host_flag) = a.seq;
+  }
 }
 
 cudaError_t launch_fuse_pools(const FuseArgs& a, cudaStream_t st) {
