@@ -247,24 +247,28 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
             const uint32_t th = __shfl_sync(0xffffffffu, hi, tix[u]);
             ln[u] = have ? th - tl : 0;   // <= 64
             const uint64_t e = s.base[i0 + tix[u]] + tl + lane;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              pp[u][h] = make_uint2(0u, 0u);
-              if (lane + 32 * h < ln[u]) pp[u][h] = __ldg(p.post + e + 32 * h);
-            }
+            pp[u][0] = make_uint2(0u, 0u);
+            pp[u][1] = make_uint2(0u, 0u);
+            if (lane < ln[u]) pp[u][0] = __ldg(p.post + e);
+            if (ln[u] > 32 && lane + 32 < ln[u]) pp[u][1] = __ldg(p.post + e + 32);   // warp-uniform outer test: rare
           }
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
             if (ln[u] == 0) continue;  // warp-uniform
             const float qw = s.qw[i0 + tix[u]];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              if (lane + 32 * h < ln[u]) {
-                const uint32_t d = pp[u][h].x - d0;
-                // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
-                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][h].y)));
+            if (lane < ln[u]) {
+              const uint32_t d = pp[u][0].x - d0;
+              // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
+              acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][0].y)));
+              touched[d] = 1;
+            }
+            if (ln[u] > 32) {   // warp-uniform; a slice longer than 32 postings (of <= 64 docs) is the exception
+              if (lane + 32 < ln[u]) {
+                const uint32_t d = pp[u][1].x - d0;
+                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][1].y)));
                 touched[d] = 1;
               }
+            }
             __syncwarp();
           }
         }
