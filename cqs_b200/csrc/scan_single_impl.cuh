@@ -589,8 +589,16 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
     }
     if (ctid < p.peer.world && ctid != p.peer.rank) peer_block(p.peer, ctid, p.peer.rank).n[0] = n_word;
     peer_signal(p.peer, tk.g);
-    if (peer_wait(p.peer, tk.g)) peer_merge_query(p.peer, tk.g, 0, k_emit, p.out_scores, p.out_rows, p.out_n);
-    else peer_emit_empty(tk.g, k_emit, p.out_scores, p.out_rows, p.out_n);
+    if (peer_wait(p.peer, tk.g)) {
+      // the tile ring is idle by now (the producer has retired, every bulk copy has landed): stage the
+      // world lists there so that the merge's binary searches probe shared memory, not the mailbox
+      if ((size_t)p.peer.world * k_emit * 12 + 64 <= (size_t)Cfg::STAGES * Cfg::STAGE_BYTES)
+        peer_merge_query_staged(p.peer, tk.g, 0, k_emit, smem, p.out_scores, p.out_rows, p.out_n);
+      else
+        peer_merge_query(p.peer, tk.g, 0, k_emit, p.out_scores, p.out_rows, p.out_n);
+    } else {
+      peer_emit_empty(tk.g, k_emit, p.out_scores, p.out_rows, p.out_n);
+    }
   }
   TRACE(4);
   if (p.host_flag) {
