@@ -468,12 +468,18 @@ __global__ void __launch_bounds__(kThreads, 1) scan_topk_kernel(const ScanParams
         uint32_t c = s_cnt;
         need = (c + 2 * kBurst > kCap) || (s_thr == 0 && c >= k);
       }
-      if (tk.g.any(need)) {
+      const bool selected = tk.g.any(need);
+      if (selected) {
         if (ctid == 0) s_vm[0] = 0;
         tk.template select<kCap / kConsumers>(k, m_pub, s_vm);
         if (m_pub && ctid == 0 && s_vm[0]) atomicMax(p.col + blockIdx.x, s_vm[0]);
       }
-      if (m_pub) refresh_global_thr(tk, reinterpret_cast<ckey_t*>(s_hist), p.col, gridDim.x, j_need);
+      // the shared bound is re-read after a re-selection (this CTA just published), at the first two
+      // checks (the other CTAs publish their first values around then) and every 8th check after
+      // that: on a 12.5M-row shard a CTA passes ~80 checks, and a refresh per check cost 3-6 %
+      const uint32_t chk = it / kCheckEvery;
+      if (m_pub && (selected || chk < 2 || (chk & 7) == 7))
+        refresh_global_thr(tk, reinterpret_cast<ckey_t*>(s_hist), p.col, gridDim.x, j_need);
       thr = s_thr;
       if (thr) thr_s = key_score(thr);
     }
