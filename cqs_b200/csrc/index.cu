@@ -64,6 +64,7 @@ struct Shard {
   float* d_stage = nullptr;  // staging for row ingest
   uint64_t stage_rows = 0;
   float* h_query = nullptr;   // pinned
+  uint32_t* h_sq = nullptr;   // pinned staging of a sparse query: [kSpMaxQ] tokens | [kSpMaxQ] weights
   uint32_t* d_bitset = nullptr;
   uint64_t bitset_words = 0;
   // Scratch of one dense scan launch: per-CTA partial lists, CTA ticket + tile counter, the
@@ -215,6 +216,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_ctype); cudaFree(s.d_lang); cudaFree(s.d_note_boost); cudaFree(s.d_importance);
   free_sparse(s.sparse);
   if (s.h_query) cudaFreeHost(s.h_query);
+  if (s.h_sq) cudaFreeHost(s.h_sq);
   if (s.h_out) cudaFreeHost(s.h_out);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
@@ -237,6 +239,7 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   for (auto& e : s.ev_join) CK(ix, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(ix, cudaHostAlloc((void**)&s.h_query, sizeof(float) * ix->layout.ld,
                        cudaHostAllocDefault));
+  CK(ix, cudaHostAlloc((void**)&s.h_sq, sizeof(uint32_t) * 2 * 1024, cudaHostAllocDefault));
   for (auto& c : s.scr) {
     CK(ix, cudaMalloc((void**)&c.d_query, sizeof(float) * ix->layout.ld));
     CK(ix, cudaMalloc((void**)&c.d_partial, sizeof(ckey_t) * kMaxGrid * kMaxK));
@@ -1680,8 +1683,11 @@ int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t*
 static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
                          uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st = nullptr) {
   if (!st) st = s.stream;
-  CK(ix, cudaMemcpyAsync(s.d_q_tok, q_tok, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, st));
-  CK(ix, cudaMemcpyAsync(s.d_q_w, q_w, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, st));
+  // through pinned staging: a pageable source would make these copies synchronous with the host
+  memcpy(s.h_sq, q_tok, sizeof(uint32_t) * q_nnz);
+  memcpy(s.h_sq + kSpMaxQ, q_w, sizeof(float) * q_nnz);
+  CK(ix, cudaMemcpyAsync(s.d_q_tok, s.h_sq, sizeof(uint32_t) * q_nnz, cudaMemcpyHostToDevice, st));
+  CK(ix, cudaMemcpyAsync(s.d_q_w, s.h_sq + kSpMaxQ, sizeof(float) * q_nnz, cudaMemcpyHostToDevice, st));
   const size_t need = sparse_bounds_bytes(s.n_rows, q_nnz);
   if (need > s.bounds_bytes) {
     CK(ix, cudaStreamSynchronize(st));

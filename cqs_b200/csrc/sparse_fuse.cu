@@ -39,7 +39,9 @@ constexpr uint32_t kSpBlock = kSparseDocsPerBlock;  // docs owned by one warp at
 // bounds[i][j] = number of postings of query token i with doc < j*64 (j = 0..n_blocks).
 // Found by streaming the doc ids of the touched lists once (no dependent binary-search
 // chains): the thread that sees the first posting of a block writes the offsets of that
-// block and of the empty blocks before it.  bounds is zero-filled beforehand (empty lists).
+// block and of the empty blocks before it.  Rows of empty lists (a token with no postings, or out
+// of the vocabulary) are written as zeros by the same kernel — there is no per-query memset; rows
+// of tokens served by the static block index are never read and are left alone.
 struct BoundsParams {
   const uint64_t* tptr;
   const uint32_t* doc;
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
     uint64_t b0 = 0, b1 = 0;
-    if (t < p.vocab && !(p.slot_of && __ldg(p.slot_of + t) >= 0)) {
+    const bool covered = t < p.vocab && p.slot_of && __ldg(p.slot_of + t) >= 0;   // static index row exists
+    if (t < p.vocab && !covered) {
       b0 = __ldg(p.tptr + t);
       b1 = __ldg(p.tptr + t + 1);
     }
@@ -70,8 +73,9 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
     s_len[i] = (uint32_t)len;
     // long lists are streamed (a thread that sees the first posting of a block writes the
     // offsets of that block and of the empty blocks before it); short lists would leave
-    // long serial fills to a few threads, so every block boundary is binary-searched.
-    s_prefix[i + 1] = len == 0 ? 0 : (len <= kBoundsShort ? search_units
+    // long serial fills to a few threads, so every block boundary is binary-searched — which
+    // for an empty list writes the all-zero row the search kernel expects.
+    s_prefix[i + 1] = covered ? 0 : (len <= kBoundsShort ? search_units
                                                          : (len + kBoundsChunk - 1) / kBoundsChunk);
   }
   __syncthreads();
@@ -328,8 +332,7 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaMemsetAsync(a.d_bounds, 0, sparse_bounds_bytes(a.n_docs, a.q_nnz), st);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
   // the static block index only applies while the corpus still has the block count it was built for
   const bool use_index = a.sp.d_slot_of && a.sp.d_block_index && a.sp.index_stride == n_blocks + 1;
   BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds,
