@@ -1699,7 +1699,7 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
   }
   SparseArgs a;
   a.d_bounds = s.d_bounds;
-  a.d_trace = s.d_trace;
+  a.d_trace = s.d_trace ? s.d_trace + 512 * 8 : nullptr;   // rows 512.. of the trace buffer (the scan uses rows 0..147 and 1023)
   a.sp = s.sparse; a.n_docs = s.n_rows; a.d_q_tok = s.d_q_tok; a.d_q_w = s.d_q_w; a.q_nnz = q_nnz;
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;

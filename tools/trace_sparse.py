@@ -33,9 +33,9 @@ for k in (20, 500):
         t = np.unique(np.searchsorted(cdf_h, rng.random(q_nnz * 2)).clip(0, vocab - 1))[:q_nnz].astype(np.uint32)
         qw = np.log1p(np.maximum(rng.normal(0.8, 0.5, t.shape[0]), 0.02)).astype(np.float32)
         ix.search_sparse_rows(t, qw, k)
-    tr = np.zeros(296 * 8, np.uint64)
-    lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 296 * 8)
-    tr = tr.reshape(296, 8).astype(np.int64); t0 = tr[:, 0].min(); rel = (tr - t0) / 1e3
+    tr = np.zeros(1024 * 8, np.uint64)
+    lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
+    tr = tr.reshape(1024, 8)[512:512 + 296].astype(np.int64); t0 = tr[:, 0].min(); rel = (tr - t0) / 1e3
     last = int(np.argmax(tr[:, 5]))
     print(f"k={k}: both kernels {ix.last_kernel_ms()*1e3:.0f} us | first step accumulate done: med {np.median(rel[:,1]):.1f} us | "
           f"first select done: med {np.median(rel[:,2]):.1f} | loop end: med {np.median(rel[:,3]):.1f} max {rel[:,3].max():.1f} | "
