@@ -172,10 +172,12 @@ struct SparseParams {
 };
 #define SPTRACE(slot) do { if (p.trace && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.trace[blockIdx.x * 8 + (slot)] = t_; } } while (0)
 
+constexpr uint32_t kSpR = 4;                       // 64-doc index blocks per warp block
+constexpr uint32_t kSpWDocs = kSpBlock * kSpR;     // docs owned by one warp at a time (256)
 struct SpSmem {
   ckey_t buf[kSpCap];                    // 32 KB
-  float acc[kSpWarps][kSpBlock];         //  4 KB
-  uint8_t touched[kSpWarps][kSpBlock];   //  1 KB
+  float acc[kSpWarps][kSpWDocs];         // 16 KB
+  uint8_t touched[kSpWarps][kSpWDocs];   //  4 KB
   uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
   const uint32_t* brow[kSpMaxQ];         //  8 KB  its block-boundary row (static index or this query's bounds)
   float qw[kSpMaxQ];                     //  4 KB
@@ -187,14 +189,18 @@ struct SpSmem {
 };
 
 // ---- pass 2: accumulate + select -------------------------------------------------------
-// A warp owns a 64-doc block: its accumulators sit in shared memory.  For a batch of 8
-// query tokens the block's slices of their posting lists (<= 64 postings each, a doc lists
-// a token once) are fetched into registers with all loads in flight, then applied IN
-// QUERY ORDER (the reference's accumulation order, index.rs:251-259): within one token
-// the docs are distinct, so the lanes update
+// A warp owns a block of 256 docs (four 64-doc index blocks): its accumulators sit in shared
+// memory.  The block's slice of every query token's posting list is contiguous; the slices of 32
+// tokens at a time are cut into 32-posting chunks and the (token, chunk) items are walked in query
+// order, eight per batch — all of a batch's loads in flight together, every load a full 256-byte
+// line, then applied IN QUERY ORDER (the reference's accumulation order, index.rs:251-259):
+// within one token the docs are distinct, so the lanes update
 //   acc[doc] = acc[doc] + qw*dw   (separate f32 multiply and add)
-// without conflicts, and only a __syncwarp separates tokens.  Touched docs that pass the
-// filter go to the CTA's top-k accumulator.
+// without conflicts, and only a __syncwarp separates items.  Touched docs that pass the filter go
+// to the CTA's top-k accumulator.
+// (Round 1 used 64-doc blocks: a heavy token has ~26 postings there, so a third of the lanes idled,
+// every (token, block) visit paid ~40 instructions of bookkeeping, and the kernel was issue-bound at
+// 62 % of the slots for 17 % of the DRAM bandwidth — profiles/r02_sparse_search_*.)
 constexpr int kSpBatch = 8;
 __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const SparseParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -213,88 +219,92 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
   __syncthreads();
   SPTRACE(0);
   const uint32_t k = p.k;
-  const uint32_t n_steps = (p.n_blocks + kSpWarps - 1) / kSpWarps;
+  const uint32_t n_wblocks = (p.n_blocks + kSpR - 1) / kSpR;
+  const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
   float* acc = s.acc[warp];
   uint8_t* touched = s.touched[warp];
   for (uint32_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
-    const uint32_t blk = step * kSpWarps + warp;
-    const ckey_t thr = s.thr;
-    if (blk < p.n_blocks) {
-      const uint32_t d0 = blk * kSpBlock;
+    const uint32_t wb = step * kSpWarps + warp;
+    const uint32_t d0 = wb * kSpWDocs;
+    if (wb < n_wblocks) {
+      const uint32_t b_lo = wb * kSpR, b_hi = min(b_lo + kSpR, p.n_blocks);
 #pragma unroll
-      for (uint32_t i = lane; i < kSpBlock; i += 32) {
+      for (uint32_t i = lane; i < kSpWDocs; i += 32) {
         acc[i] = 0.f;
         touched[i] = 0;
       }
       for (uint32_t i0 = 0; i0 < p.q_nnz; i0 += 32) {
-        // slice [lo, hi) of 32 query tokens at once (one token per lane)
+        // slice [lo, hi) of 32 query tokens at once (one token per lane), and its chunk count
         uint32_t lo = 0, hi = 0;
         if (i0 + lane < p.q_nnz) {
-          const uint32_t* row = s.brow[i0 + lane] + blk;
-          lo = __ldg(row);
-          hi = __ldg(row + 1);
+          const uint32_t* row = s.brow[i0 + lane];
+          lo = __ldg(row + b_lo);
+          hi = __ldg(row + b_hi);
         }
-        // Only the tokens that HAVE postings in this block are visited (most of a 64-token query's
-        // light tokens do not): the set bits of `present`, lowest first = query order, eight per
-        // batch so that all of a batch's posting loads are in flight together.  (Before: every token
-        // paid its shuffles and predicated loads — the kernel was issue-bound at 66 % of the slots.)
-        uint32_t present = __ballot_sync(0xffffffffu, hi > lo);
-        while (present) {
-          uint2 pp[kSpBatch][2];
-          uint32_t ln[kSpBatch], tix[kSpBatch];
+        const uint32_t nch = (hi - lo + 31) >> 5;
+        uint32_t incl = nch;                                  // inclusive prefix of the chunk counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (uint32_t)o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t j0 = 0; j0 < total; j0 += kSpBatch) {
+          uint2 pp[kSpBatch];
+          uint32_t cl[kSpBatch], tix[kSpBatch];
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
-            const bool have = present != 0;
-            tix[u] = have ? (uint32_t)(__ffs(present) - 1) : 0u;
-            present &= present - 1;     // clears the lowest set bit; 0 stays 0
+            const uint32_t j = j0 + u;
+            const bool have = j < total;
+            // the token that owns item j = the number of tokens whose chunks all come before it
+            tix[u] = min((uint32_t)__popc(__ballot_sync(0xffffffffu, incl <= j)), 31u);
+            const uint32_t first = __shfl_sync(0xffffffffu, incl - nch, tix[u]);
             const uint32_t tl = __shfl_sync(0xffffffffu, lo, tix[u]);
             const uint32_t th = __shfl_sync(0xffffffffu, hi, tix[u]);
-            ln[u] = have ? th - tl : 0;   // <= 64
-            const uint64_t e = s.base[i0 + tix[u]] + tl + lane;
-            pp[u][0] = make_uint2(0u, 0u);
-            pp[u][1] = make_uint2(0u, 0u);
-            if (lane < ln[u]) pp[u][0] = __ldg(p.post + e);
-            if (ln[u] > 32 && lane + 32 < ln[u]) pp[u][1] = __ldg(p.post + e + 32);   // warp-uniform outer test: rare
+            const uint32_t start = tl + (j - first) * 32;     // chunk (j - first) of that token's slice
+            cl[u] = have ? min(32u, th - start) : 0;
+            pp[u] = make_uint2(0u, 0u);
+            if (lane < cl[u]) pp[u] = __ldg(p.post + s.base[i0 + tix[u]] + start + lane);
           }
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
-            if (ln[u] == 0) continue;  // warp-uniform
+            if (cl[u] == 0) continue;  // warp-uniform
             const float qw = s.qw[i0 + tix[u]];
-            if (lane < ln[u]) {
-              const uint32_t d = pp[u][0].x - d0;
+            if (lane < cl[u]) {
+              const uint32_t d = pp[u].x - d0;
               // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
-              acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][0].y)));
+              acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u].y)));
               touched[d] = 1;
-            }
-            if (ln[u] > 32) {   // warp-uniform; a slice longer than 32 postings (of <= 64 docs) is the exception
-              if (lane + 32 < ln[u]) {
-                const uint32_t d = pp[u][1].x - d0;
-                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u][1].y)));
-                touched[d] = 1;
-              }
             }
             __syncwarp();
           }
         }
       }
       __syncwarp();
-      // candidates: touched docs that pass the filter, finite score (candidate.rs:275)
-      for (uint32_t d = lane; d < kSpBlock; d += 32) {
-        const uint64_t r = (uint64_t)d0 + d;
-        if (!touched[d] || r >= p.n_docs) continue;
-        if (p.bitset && !((__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u)) continue;
-        const float sc = acc[d];
-        if (!finite_bits(__float_as_uint(sc))) continue;
-        const ckey_t key = make_key(sc, (uint32_t)r);
-        if (key > thr) tk.push(key);
-      }
     }
-    __syncthreads();
-    if (step == blockIdx.x) SPTRACE(1);
-    // at most kSpWarps*kSpBlock = 1024 pushes per step
-    if (s.cnt + kSpWarps * kSpBlock > kSpCap || (s.thr == 0 && s.cnt >= k))
-      tk.template select<kSpCap / kSpThreads>(k);
-    __syncthreads();
+    // candidates: touched docs that pass the filter, finite score (candidate.rs:275), pushed in two
+    // halves of <= kSpWarps * 128 = 2048 keys with a re-selection in between: a selection leaves at
+    // most kSpCap / 2 keys, so the accumulator (4096 slots) cannot overflow whatever the scores are
+#pragma unroll 1
+    for (uint32_t half = 0; half < 2; ++half) {
+      const ckey_t thr = s.thr;
+      if (wb < n_wblocks) {
+        for (uint32_t d = half * (kSpWDocs / 2) + lane; d < (half + 1) * (kSpWDocs / 2); d += 32) {
+          const uint64_t r = (uint64_t)d0 + d;
+          if (!touched[d] || r >= p.n_docs) continue;
+          if (p.bitset && !((__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u)) continue;
+          const float sc = acc[d];
+          if (!finite_bits(__float_as_uint(sc))) continue;
+          const ckey_t key = make_key(sc, (uint32_t)r);
+          if (key > thr) tk.push(key);
+        }
+      }
+      __syncthreads();
+      if (step == blockIdx.x && half == 0) SPTRACE(1);
+      if (s.cnt + kSpWarps * (kSpWDocs / 2) > kSpCap || (s.thr == 0 && s.cnt >= k))
+        tk.template select<kSpCap / kSpThreads>(k);
+      __syncthreads();
+    }
     if (step == blockIdx.x) SPTRACE(2);
   }
   SPTRACE(3);
@@ -348,7 +358,8 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   p.partial = a.d_partial; p.partial_cnt = a.d_partial_cnt; p.done = a.d_done;
   p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
   p.trace = (unsigned long long*)a.d_trace;
-  const uint32_t n_steps = (n_blocks + kSpWarps - 1) / kSpWarps;
+  const uint32_t n_wblocks = (n_blocks + kSpR - 1) / kSpR;
+  const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
   int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
   if (grid > (int)kMaxGrid) grid = kMaxGrid;
   e = cudaFuncSetAttribute(sparse_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
