@@ -249,34 +249,39 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
           if (lane >= (uint32_t)o) incl += v;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        // Software pipeline over the (token, chunk) items: a ring of kSpBatch loads stays in flight —
+        // item j is applied kSpBatch items after its load was issued, and its slot is refilled with
+        // item j + kSpBatch right away — so the warp never waits for a whole batch's round trip.
+        uint2 pp[kSpBatch];
+        uint32_t cl[kSpBatch], tix[kSpBatch];
+        auto fetch = [&](int u, uint32_t j) {
+          const bool have = j < total;
+          // the token that owns item j = the number of tokens whose chunks all come before it
+          tix[u] = min((uint32_t)__popc(__ballot_sync(0xffffffffu, incl <= j)), 31u);
+          const uint32_t first = __shfl_sync(0xffffffffu, incl - nch, tix[u]);
+          const uint32_t tl = __shfl_sync(0xffffffffu, lo, tix[u]);
+          const uint32_t th = __shfl_sync(0xffffffffu, hi, tix[u]);
+          const uint32_t start = tl + (j - first) * 32;     // chunk (j - first) of that token's slice
+          cl[u] = have ? min(32u, th - start) : 0;
+          pp[u] = make_uint2(0u, 0u);
+          if (lane < cl[u]) pp[u] = __ldg(p.post + s.base[i0 + tix[u]] + start + lane);
+        };
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) fetch(u, (uint32_t)u);
         for (uint32_t j0 = 0; j0 < total; j0 += kSpBatch) {
-          uint2 pp[kSpBatch];
-          uint32_t cl[kSpBatch], tix[kSpBatch];
 #pragma unroll
           for (int u = 0; u < kSpBatch; ++u) {
-            const uint32_t j = j0 + u;
-            const bool have = j < total;
-            // the token that owns item j = the number of tokens whose chunks all come before it
-            tix[u] = min((uint32_t)__popc(__ballot_sync(0xffffffffu, incl <= j)), 31u);
-            const uint32_t first = __shfl_sync(0xffffffffu, incl - nch, tix[u]);
-            const uint32_t tl = __shfl_sync(0xffffffffu, lo, tix[u]);
-            const uint32_t th = __shfl_sync(0xffffffffu, hi, tix[u]);
-            const uint32_t start = tl + (j - first) * 32;     // chunk (j - first) of that token's slice
-            cl[u] = have ? min(32u, th - start) : 0;
-            pp[u] = make_uint2(0u, 0u);
-            if (lane < cl[u]) pp[u] = __ldg(p.post + s.base[i0 + tix[u]] + start + lane);
-          }
-#pragma unroll
-          for (int u = 0; u < kSpBatch; ++u) {
-            if (cl[u] == 0) continue;  // warp-uniform
-            const float qw = s.qw[i0 + tix[u]];
-            if (lane < cl[u]) {
-              const uint32_t d = pp[u].x - d0;
-              // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
-              acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u].y)));
-              touched[d] = 1;
+            if (cl[u] != 0) {  // warp-uniform
+              const float qw = s.qw[i0 + tix[u]];
+              if (lane < cl[u]) {
+                const uint32_t d = pp[u].x - d0;
+                // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
+                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u].y)));
+                touched[d] = 1;
+              }
+              __syncwarp();
             }
-            __syncwarp();
+            fetch(u, j0 + kSpBatch + u);
           }
         }
       }
