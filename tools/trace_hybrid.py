@@ -28,6 +28,7 @@ for i in range(8):
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
     tr = tr.reshape(1024, 8).astype(np.int64)
     d, s = tr[:148], tr[512:512 + 296]
+    s = s[s[:, 3] > d[:, 0].min()]                         # sparse CTAs of THIS query only (the grid can be < 296)
     t0 = d[:, 0].min()
     print(f"query {i}: dense CTAs start {(d[:,0].min()-t0)/1e3:.1f}..{(d[:,0].max()-t0)/1e3:.1f}, stream end {(d[:,1].max()-t0)/1e3:.1f}, "
           f"ticket {(d[:,3].max()-t0)/1e3:.1f}, kernel end {(d[:,4].max()-t0)/1e3:.1f} | sparse search CTAs start "

@@ -35,7 +35,9 @@ for k in (20, 500):
         ix.search_sparse_rows(t, qw, k)
     tr = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
-    tr = tr.reshape(1024, 8)[512:512 + 296].astype(np.int64); t0 = tr[:, 0].min(); rel = (tr - t0) / 1e3
+    tr = tr.reshape(1024, 8)[512:512 + 296].astype(np.int64)
+    tr = tr[tr[:, 3] > 0]                                  # CTAs of this launch only (the grid can be < 296)
+    t0 = tr[:, 0].min(); rel = (tr - t0) / 1e3
     last = int(np.argmax(tr[:, 5]))
     print(f"k={k}: both kernels {ix.last_kernel_ms()*1e3:.0f} us | first step accumulate done: med {np.median(rel[:,1]):.1f} us | "
           f"first select done: med {np.median(rel[:,2]):.1f} | loop end: med {np.median(rel[:,3]):.1f} max {rel[:,3].max():.1f} | "
