@@ -148,8 +148,11 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
 
 // compact() uses a rank sort up to this many keys, the register/shuffle bitonic network above.
 // Measured (tools/bench_topk.py, one 256-thread CTA, warm): rank sort 128 / 256 / 500 keys = 1.3 /
-// 2.5 / 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us: they cross near 380.
-constexpr uint32_t kRankSortMax = 384;
+// 2.5 / 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us: warm they cross near
+// 380 keys.  In the kernels, though, the sort that matters is the last CTA's final one, which runs
+// ONCE: the rank sort's few instructions have just been executed by every CTA's own finish (warm
+// instruction cache), the bitonic network's have not (11.6 us for 500 keys there) — so rank sort up to 512.
+constexpr uint32_t kRankSortMax = 512;
 constexpr uint32_t kSelBuckets = 2048;  // histogram resolution of select()
 
 // Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
@@ -175,7 +178,8 @@ struct TopK {
     if (slot < cap) buf[slot] = key;  // cannot fail when the caller honours the bound
   }
   // Collective.  Afterwards buf[0..min(n,k)) holds the best keys, descending.
-  __device__ __forceinline__ void compact(uint32_t k, uint32_t rank_sort_max = kRankSortMax) {
+  __device__ __forceinline__ void compact(uint32_t k, uint32_t rank_sort_max = kRankSortMax);
+  __device__ __forceinline__ void compact_impl(uint32_t k, uint32_t rank_sort_max) {
     g.sync();
     uint32_t n = min(*cnt, cap);
     if (n <= rank_sort_max) {
@@ -372,6 +376,12 @@ struct TopK {
 // per-CTA finish and the last CTA's merge: the merge runs once per kernel, and its private inlined
 // copies of this code were instruction-cache misses from L2 (2.6 us warm, 11 us measured there); the
 // streaming loop has executed the shared copy on the same SM moments earlier.
+static __device__ __noinline__ void topk_compact(TopK tk, uint32_t k, uint32_t rank_sort_max) {
+  tk.compact_impl(k, rank_sort_max);
+}
+__device__ __forceinline__ void TopK::compact(uint32_t k, uint32_t rank_sort_max) {
+  topk_compact(*this, k, rank_sort_max);
+}
 template <int ITEMS>
 __device__ __noinline__ void topk_select(TopK tk, uint32_t k, uint32_t m, ckey_t* vm_out) {
   tk.template select_impl<ITEMS>(k, m, vm_out);
