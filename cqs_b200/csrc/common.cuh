@@ -147,12 +147,12 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
 }
 
 // compact() uses a rank sort up to this many keys, the register/shuffle bitonic network above.
-// Measured (tools/bench_topk.py, one 256-thread CTA, warm): rank sort 128 / 256 / 500 keys = 1.3 /
-// 2.5 / 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us: warm they cross near
-// 380 keys.  In the kernels, though, the sort that matters is the last CTA's final one, which runs
-// ONCE: the rank sort's few instructions have just been executed by every CTA's own finish (warm
-// instruction cache), the bitonic network's have not (11.6 us for 500 keys there) — so rank sort up to 512.
-constexpr uint32_t kRankSortMax = 512;
+// Measured warm (tools/bench_topk.py, one 256-thread CTA): rank sort 128 / 256 / 500 keys = 1.3 / 2.5 /
+// 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us.  Measured where it matters —
+// the last CTA's final sort of ~500 keys inside the scan kernel (tools/trace_scan.py): bitonic 11.6 us
+// (its code runs once, instruction-cache cold), rank sort 20 us.  256 keeps the rank sort where it wins
+// either way.
+constexpr uint32_t kRankSortMax = 256;
 constexpr uint32_t kSelBuckets = 2048;  // histogram resolution of select()
 
 // Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
