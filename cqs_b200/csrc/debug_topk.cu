@@ -79,3 +79,52 @@ extern "C" int cqs_b200_debug_topk_ns(int device, int op, uint32_t n, uint32_t k
   cudaFree(d_cnt);
   return e == cudaSuccess ? 0 : -2;
 }
+
+// ---- co-residency probe (development aid) -------------------------------------------------------
+// Does a small CTA get scheduled on an SM whose register file partitions are almost filled by a
+// resident scan CTA (9 warps x 168 registers: one partition holds 3 of them = 16,128 of 16,384)?
+// Each probe CTA stamps %globaltimer when it starts, spins `spin_ns`, and leaves.
+namespace cqs {
+namespace {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) probe_kernel(unsigned long long* stamps, uint32_t* smid, unsigned long long spin_ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (threadIdx.x == 0) {
+    stamps[blockIdx.x] = t0;
+    uint32_t id;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+    smid[blockIdx.x] = id;
+  }
+  // ~48 live accumulators: the probe occupies about as many registers per thread (64) as the sparse kernel
+  float acc[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) acc[i] = (float)(threadIdx.x + i);
+  unsigned long long t;
+  do {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) acc[i] = fmaf(acc[i], 1.0001f, 0.5f);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < spin_ns);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 48; ++i) sum += acc[i];
+  if (sum == 12345.678f) stamps[blockIdx.x] = 0;   // keeps the accumulators alive
+}
+}  // namespace
+}  // namespace cqs
+
+extern "C" int cqs_b200_debug_probe(int threads, uint32_t grid, unsigned long long* d_stamps, uint32_t* d_smid,
+                                    unsigned long long spin_ns, void* stream) {
+  using namespace cqs;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (threads) {
+    case 64: probe_kernel<64><<<grid, 64, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 96: probe_kernel<96><<<grid, 96, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 128: probe_kernel<128><<<grid, 128, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 192: probe_kernel<192><<<grid, 192, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 256: probe_kernel<256><<<grid, 256, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    default: return -1;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

@@ -104,6 +104,9 @@ struct Shard {
   float* d_q_w = nullptr;
   uint32_t* d_bounds = nullptr;   // sparse pass-1 scratch, grown on demand
   size_t bounds_bytes = 0;
+  void* d_sp_block = nullptr;     // accumulate -> select hand-over: per-doc scores + touched bits, grown on demand
+  size_t sp_block_bytes = 0;
+  uint32_t* d_sp_claim = nullptr; // block counter of the accumulate kernel
   // fused output
   uint64_t* d_f_rows = nullptr;
   float* d_f_fused = nullptr;
@@ -207,7 +210,7 @@ static void free_shard(Shard& s) {
   cudaFree(s.d_sp_scores); cudaFree(s.d_sp_rows); cudaFree(s.d_sp_n);
   cudaFree(s.d_spm_scores); cudaFree(s.d_spm_rows); cudaFree(s.d_spm_n);
   cudaFree(s.d_sp_partial); cudaFree(s.d_sp_partial_cnt); cudaFree(s.d_sp_done);
-  cudaFree(s.d_q_tok); cudaFree(s.d_q_w); cudaFree(s.d_bounds);
+  cudaFree(s.d_q_tok); cudaFree(s.d_q_w); cudaFree(s.d_bounds); cudaFree(s.d_sp_block); cudaFree(s.d_sp_claim);
   cudaFree(s.d_f_rows); cudaFree(s.d_f_fused); cudaFree(s.d_f_dense); cudaFree(s.d_f_sraw);
   cudaFree(s.d_f_present); cudaFree(s.d_f_n); cudaFree(s.d_trace);
   cudaFree(s.d_bq); cudaFree(s.d_bscratch); cudaFree(s.d_bout_scores); cudaFree(s.d_bout_rows);
@@ -260,6 +263,8 @@ static int init_shard(cqs_b200_index* ix, Shard& s, int device) {
   CK(ix, cudaMalloc((void**)&s.d_sp_partial_cnt, sizeof(uint32_t) * kMaxGrid));
   CK(ix, cudaMalloc((void**)&s.d_sp_done, sizeof(uint32_t)));
   CK(ix, cudaMemset(s.d_sp_done, 0, sizeof(uint32_t)));
+  CK(ix, cudaMalloc((void**)&s.d_sp_claim, sizeof(uint32_t)));
+  CK(ix, cudaMemset(s.d_sp_claim, 0, sizeof(uint32_t)));
   CK(ix, cudaMalloc((void**)&s.d_q_tok, sizeof(uint32_t) * kSpMaxQ));
   CK(ix, cudaMalloc((void**)&s.d_q_w, sizeof(float) * kSpMaxQ));
   CK(ix, cudaMalloc((void**)&s.d_f_rows, sizeof(uint64_t) * kMaxK));
@@ -886,6 +891,7 @@ int cqs_b200_search_device(cqs_b200_index* ix, const float* d_query, uint32_t k,
   a.d_bitset = d_bitset; a.row_base = ix->row_base + s.first_row;
   a.d_partial = scr->d_partial; a.d_partial_cnt = scr->d_partial_cnt; a.d_done = scr->d_done; a.d_col = scr->d_col;
   a.d_out_scores = d_out_scores; a.d_out_rows = d_out_rows; a.d_out_n = d_out_n;
+  a.d_trace = s.d_trace;
   CK(ix, launch_scan_single(a, s.num_sms, st));
   return release_scratch(ix, scr, st);
 } API_CATCH
@@ -1681,7 +1687,8 @@ int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t*
 } API_CATCH
 
 static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
-                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st = nullptr) {
+                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st = nullptr,
+                         bool slim = false) {
   if (!st) st = s.stream;
   // through pinned staging: a pageable source would make these copies synchronous with the host
   memcpy(s.h_sq, q_tok, sizeof(uint32_t) * q_nnz);
@@ -1697,14 +1704,25 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
     CK(ix, cudaMalloc((void**)&s.d_bounds, need + need / 2));
     s.bounds_bytes = need + need / 2;
   }
+  const size_t need_blk = sparse_block_scratch_bytes(s.n_rows);
+  if (need_blk > s.sp_block_bytes) {
+    CK(ix, cudaStreamSynchronize(st));
+    cudaFree(s.d_sp_block);
+    s.d_sp_block = nullptr;
+    s.sp_block_bytes = 0;
+    CK(ix, cudaMalloc(&s.d_sp_block, need_blk));
+    s.sp_block_bytes = need_blk;
+  }
   SparseArgs a;
+  a.d_block_scratch = s.d_sp_block;
+  a.d_claim = s.d_sp_claim;
   a.d_bounds = s.d_bounds;
   a.d_trace = s.d_trace ? s.d_trace + 512 * 8 : nullptr;   // rows 512.. of the trace buffer (the scan uses rows 0..147 and 1023)
   a.sp = s.sparse; a.n_docs = s.n_rows; a.d_q_tok = s.d_q_tok; a.d_q_w = s.d_q_w; a.q_nnz = q_nnz;
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;
   a.d_out_scores = s.d_sp_scores; a.d_out_rows = s.d_sp_rows; a.d_out_n = s.d_sp_n;
-  CK(ix, launch_sparse_search(a, st));
+  CK(ix, launch_sparse_search(a, st, slim));
   return 0;
 }
 
@@ -1806,7 +1824,7 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
     // (ev_fork was recorded BEFORE the dense launch: the sparse stream only waits for the resets
     // above; the scan was submitted first and takes the SMs first)
     if (sp_st != s.stream) CK(ix, cudaStreamWaitEvent(sp_st, s.ev_fork, 0));
-    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits, sp_st);
+    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits, sp_st, /*slim=*/sp_st != s.stream);
     if (rc) return rc;
     if (sp_st != s.stream) {
       CK(ix, cudaEventRecord(s.ev_join[0], sp_st));

@@ -162,6 +162,8 @@ struct SparseArgs {
   const float* d_q_w;
   uint32_t q_nnz;
   uint32_t* d_bounds;       // scratch, sparse_bounds_bytes(n_docs, q_nnz)
+  void* d_block_scratch = nullptr;   // sparse_block_scratch_bytes(n_docs): per-doc scores + touched bits
+  uint32_t* d_claim = nullptr;       // [1] block counter of the accumulate kernel, zero between queries
   void* d_trace = nullptr;  // optional [kMaxGrid][8] u64 stamps (CQS_B200_TRACE=1)
   const uint32_t* d_bitset;
   uint32_t k;
@@ -175,7 +177,8 @@ struct SparseArgs {
 };
 constexpr uint32_t kSparseDocsPerBlock = 64;    // docs owned by one warp at a time
 size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz);
-cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
+size_t sparse_block_scratch_bytes(uint64_t n_docs);
+cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream, bool slim = false);
 
 // Inverted-index build on the device (sparse_build.cu): doc-major CSR -> token-major postings.
 struct SparseBuildArgs {

@@ -54,12 +54,15 @@ struct BoundsParams {
 };
 constexpr uint32_t kBoundsChunk = 8192;  // postings per streaming work unit
 constexpr uint32_t kBoundsShort = 256;   // lists up to this long are binary-searched per block instead
-__global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p) {
+// T threads per CTA: 256 normally; 96 when the leg runs beside a dense scan (a 3-warp CTA fits on an
+// SM next to the scan's CTA, see sparse_accum_kernel).
+template <int T>
+__global__ void __launch_bounds__(T) sparse_bounds_kernel(const BoundsParams p) {
   __shared__ uint64_t s_base[kSpMaxQ];
   __shared__ uint32_t s_len[kSpMaxQ];
   __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // work units before token i
   const uint32_t tid = threadIdx.x;
-  const uint32_t search_units = (p.n_blocks + 1 + 1023) / 1024;  // 1024 block boundaries per unit
+  const uint32_t search_units = (p.n_blocks + 1 + 4 * T - 1) / (4 * T);  // 4 T block boundaries per unit
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
     uint64_t b0 = 0, b1 = 0;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
       for (int step = 0; step < 9; ++step) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint64_t target = (uint64_t)(unit * 1024 + u * 256 + tid) * kSpBlock;
+          const uint64_t target = (uint64_t)(unit * 4 * T + u * T + tid) * kSpBlock;
           if (a[u] < b[u]) {
             const uint32_t m = (a[u] + b[u]) >> 1;
             if ((uint64_t)__ldg(p.doc + base + m) < target) a[u] = m + 1; else b[u] = m;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const uint32_t j = unit * 1024 + u * 256 + tid;  // block boundary
+        const uint32_t j = unit * 4 * T + u * T + tid;  // block boundary
         if (j <= p.n_blocks) row[j] = a[u];              // first posting with doc >= j*64
       }
       continue;
@@ -122,16 +125,16 @@ __global__ void __launch_bounds__(256) sparse_bounds_kernel(const BoundsParams p
     const uint32_t e_end = min(len, e0 + kBoundsChunk);
     const uint32_t lane = tid & 31;
     constexpr int kU = 8;  // independent loads in flight per thread
-    for (uint32_t eb = e0; eb < e_end; eb += 256 * kU) {
+    for (uint32_t eb = e0; eb < e_end; eb += T * kU) {
       uint32_t cur[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const uint32_t e = eb + u * 256 + tid;
+        const uint32_t e = eb + u * T + tid;
         cur[u] = (e < e_end) ? __ldg(p.doc + base + e) : 0;
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
-        const uint32_t e = eb + u * 256 + tid;
+        const uint32_t e = eb + u * T + tid;
         // block of the previous posting: the neighbouring lane holds it, lane 0 re-reads it
         uint32_t prv = __shfl_up_sync(0xffffffffu, cur[u], 1);
         if (lane == 0 && e > 0 && e < e_end) prv = __ldg(p.doc + base + e - 1);
@@ -165,6 +168,9 @@ struct SparseParams {
   ckey_t* partial;
   uint32_t* partial_cnt;
   uint32_t* done;
+  uint32_t* claim;            // accumulate kernel: next unclaimed 256-doc block (zero between queries)
+  float* blk_scores;          // [n_docs rounded up to 256] scores of the accumulated blocks
+  uint32_t* blk_mask;         // [n_wblocks][8] "touched" bits
   float* out_scores;
   uint64_t* out_rows;
   uint32_t* out_n;
@@ -174,21 +180,27 @@ struct SparseParams {
 
 constexpr uint32_t kSpR = 4;                       // 64-doc index blocks per warp block
 constexpr uint32_t kSpWDocs = kSpBlock * kSpR;     // docs owned by one warp at a time (256)
-struct SpSmem {
-  ckey_t buf[kSpCap];                    // 32 KB
-  float acc[kSpWarps][kSpWDocs];         // 16 KB
-  uint8_t touched[kSpWarps][kSpWDocs];   //  4 KB
+
+// The leg is two kernels.  ACCUMULATE (sparse_accum_kernel<WARPS>): warps claim 256-doc blocks from a
+// global counter, build the block's scores in shared memory and write them — 256 f32 + a 256-bit
+// "touched" mask — to a per-index scratch.  SELECT (sparse_select_kernel): streams that scratch through
+// the top-k accumulator, last-CTA merge.  The split exists for the hybrid call: the accumulate kernel has
+// a SLIM form — 96-thread CTAs, ~24 KB of shared memory, 64 registers — that fits on an SM BESIDE the
+// dense scan's CTA (the scan's 9 warps x 168 registers fill one of the four register-file partitions;
+// the hardware places a 3-warp CTA on the other three: tools/probe_coresidency.py), so the instruction-
+// bound sparse accumulation runs under the bandwidth-bound dense scan instead of after it.
+struct SpAccSmemBase {
   uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
   const uint32_t* brow[kSpMaxQ];         //  8 KB  its block-boundary row (static index or this query's bounds)
   float qw[kSpMaxQ];                     //  4 KB
-  uint32_t pos[kMaxGrid];                //  4 KB
-  uint32_t hist[kSelBuckets + 96];       //  8 KB  select() histogram
-  ckey_t thr;
-  uint32_t cnt;
-  uint32_t last;
+};
+template <int WARPS>
+struct SpAccSmem : SpAccSmemBase {
+  float acc[WARPS][kSpWDocs];            //  1 KB per warp
+  uint8_t touched[WARPS][kSpWDocs];      //  256 B per warp
 };
 
-// ---- pass 2: accumulate + select -------------------------------------------------------
+// ---- pass 2a: accumulate --------------------------------------------------------------------
 // A warp owns a block of 256 docs (four 64-doc index blocks): its accumulators sit in shared
 // memory.  The block's slice of every query token's posting list is contiguous; the slices of 32
 // tokens at a time are cut into 32-posting chunks and the (token, chunk) items are walked in query
@@ -196,20 +208,18 @@ struct SpSmem {
 // line, then applied IN QUERY ORDER (the reference's accumulation order, index.rs:251-259):
 // within one token the docs are distinct, so the lanes update
 //   acc[doc] = acc[doc] + qw*dw   (separate f32 multiply and add)
-// without conflicts, and only a __syncwarp separates items.  Touched docs that pass the filter go
-// to the CTA's top-k accumulator.
+// without conflicts, and only a __syncwarp separates items.
 // (Round 1 used 64-doc blocks: a heavy token has ~26 postings there, so a third of the lanes idled,
 // every (token, block) visit paid ~40 instructions of bookkeeping, and the kernel was issue-bound at
 // 62 % of the slots for 17 % of the DRAM bandwidth — profiles/r02_sparse_search_*.)
 constexpr int kSpBatch = 8;
-__global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const SparseParams p) {
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 3 ? 8 : 2) sparse_accum_kernel(const SparseParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  SpSmem& s = *reinterpret_cast<SpSmem*>(smem_raw);
+  SpAccSmem<WARPS>& s = *reinterpret_cast<SpAccSmem<WARPS>*>(smem_raw);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}, s.hist};
-  tk.init();
   const uint32_t stride = p.n_blocks + 1;
-  for (uint32_t i = tid; i < p.q_nnz; i += kSpThreads) {
+  for (uint32_t i = tid; i < p.q_nnz; i += WARPS * 32) {
     const uint32_t t = __ldg(p.q_tok + i);
     s.base[i] = (t < p.vocab) ? __ldg(p.tptr + t) : 0;
     s.qw[i] = __ldg(p.q_w + i);
@@ -217,44 +227,45 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
     s.brow[i] = slot >= 0 ? p.block_index + (size_t)slot * stride : p.bounds + (size_t)i * stride;
   }
   __syncthreads();
-  SPTRACE(0);
-  const uint32_t k = p.k;
+  SPTRACE(6);
   const uint32_t n_wblocks = (p.n_blocks + kSpR - 1) / kSpR;
-  const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
   float* acc = s.acc[warp];
   uint8_t* touched = s.touched[warp];
-  for (uint32_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
-    const uint32_t wb = step * kSpWarps + warp;
+  for (;;) {
+    // warps claim blocks one at a time: the slim and the regular form, any grid, finish together
+    uint32_t wb = 0;
+    if (lane == 0) wb = atomicAdd(p.claim, 1u);
+    wb = __shfl_sync(0xffffffffu, wb, 0);
+    if (wb >= n_wblocks) break;
     const uint32_t d0 = wb * kSpWDocs;
-    if (wb < n_wblocks) {
-      const uint32_t b_lo = wb * kSpR, b_hi = min(b_lo + kSpR, p.n_blocks);
+    const uint32_t b_lo = wb * kSpR, b_hi = min(b_lo + kSpR, p.n_blocks);
 #pragma unroll
-      for (uint32_t i = lane; i < kSpWDocs; i += 32) {
-        acc[i] = 0.f;
-        touched[i] = 0;
+    for (uint32_t i = lane; i < kSpWDocs; i += 32) {
+      acc[i] = 0.f;
+      touched[i] = 0;
+    }
+    for (uint32_t i0 = 0; i0 < p.q_nnz; i0 += 32) {
+      // slice [lo, hi) of 32 query tokens at once (one token per lane), and its chunk count
+      uint32_t lo = 0, hi = 0;
+      if (i0 + lane < p.q_nnz) {
+        const uint32_t* row = s.brow[i0 + lane];
+        lo = __ldg(row + b_lo);
+        hi = __ldg(row + b_hi);
       }
-      for (uint32_t i0 = 0; i0 < p.q_nnz; i0 += 32) {
-        // slice [lo, hi) of 32 query tokens at once (one token per lane), and its chunk count
-        uint32_t lo = 0, hi = 0;
-        if (i0 + lane < p.q_nnz) {
-          const uint32_t* row = s.brow[i0 + lane];
-          lo = __ldg(row + b_lo);
-          hi = __ldg(row + b_hi);
-        }
-        const uint32_t nch = (hi - lo + 31) >> 5;
-        uint32_t incl = nch;                                  // inclusive prefix of the chunk counts
+      const uint32_t nch = (hi - lo + 31) >> 5;
+      uint32_t incl = nch;                                  // inclusive prefix of the chunk counts
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= (uint32_t)o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        // Software pipeline over the (token, chunk) items: a ring of kSpBatch loads stays in flight —
-        // item j is applied kSpBatch items after its load was issued, and its slot is refilled with
-        // item j + kSpBatch right away — so the warp never waits for a whole batch's round trip.
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      for (uint32_t j0 = 0; j0 < total; j0 += kSpBatch) {
         uint2 pp[kSpBatch];
         uint32_t cl[kSpBatch], tix[kSpBatch];
-        auto fetch = [&](int u, uint32_t j) {
+#pragma unroll
+        for (int u = 0; u < kSpBatch; ++u) {
+          const uint32_t j = j0 + u;
           const bool have = j < total;
           // the token that owns item j = the number of tokens whose chunks all come before it
           tix[u] = min((uint32_t)__popc(__ballot_sync(0xffffffffu, incl <= j)), 31u);
@@ -265,40 +276,75 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
           cl[u] = have ? min(32u, th - start) : 0;
           pp[u] = make_uint2(0u, 0u);
           if (lane < cl[u]) pp[u] = __ldg(p.post + s.base[i0 + tix[u]] + start + lane);
-        };
+        }
 #pragma unroll
-        for (int u = 0; u < kSpBatch; ++u) fetch(u, (uint32_t)u);
-        for (uint32_t j0 = 0; j0 < total; j0 += kSpBatch) {
-#pragma unroll
-          for (int u = 0; u < kSpBatch; ++u) {
-            if (cl[u] != 0) {  // warp-uniform
-              const float qw = s.qw[i0 + tix[u]];
-              if (lane < cl[u]) {
-                const uint32_t d = pp[u].x - d0;
-                // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
-                acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u].y)));
-                touched[d] = 1;
-              }
-              __syncwarp();
-            }
-            fetch(u, j0 + kSpBatch + u);
+        for (int u = 0; u < kSpBatch; ++u) {
+          if (cl[u] == 0) continue;  // warp-uniform
+          const float qw = s.qw[i0 + tix[u]];
+          if (lane < cl[u]) {
+            const uint32_t d = pp[u].x - d0;
+            // *scores.entry(idx).or_insert(0.0) += query_weight * doc_weight   (index.rs:259)
+            acc[d] = __fadd_rn(acc[d], __fmul_rn(qw, __uint_as_float(pp[u].y)));
+            touched[d] = 1;
           }
+          __syncwarp();
         }
       }
-      __syncwarp();
     }
-    // candidates: touched docs that pass the filter, finite score (candidate.rs:275), pushed in two
-    // halves of <= kSpWarps * 128 = 2048 keys with a re-selection in between: a selection leaves at
-    // most kSpCap / 2 keys, so the accumulator (4096 slots) cannot overflow whatever the scores are
+    __syncwarp();
+    // hand the block to the select kernel: 256 scores (coalesced) + 8 words of "touched" bits
+#pragma unroll
+    for (uint32_t j = 0; j < kSpWDocs / 32; ++j) {
+      const uint32_t d = j * 32 + lane;
+      p.blk_scores[(size_t)d0 + d] = acc[d];
+      const uint32_t bits = __ballot_sync(0xffffffffu, touched[d] != 0);
+      if (lane == 0) p.blk_mask[(size_t)wb * (kSpWDocs / 32) + j] = bits;
+    }
+    __syncwarp();
+  }
+  SPTRACE(7);
+}
+
+struct SpSmem {
+  ckey_t buf[kSpCap];                    // 32 KB
+  uint32_t pos[kMaxGrid];                //  4 KB
+  uint32_t hist[kSelBuckets + 96];       //  8 KB  select() histogram
+  ckey_t thr;
+  uint32_t cnt;
+  uint32_t last;
+};
+
+// ---- pass 2b: select ------------------------------------------------------------------------
+// Streams the accumulated blocks (1 KB of scores + 32 B of mask each) through the CTA's top-k
+// accumulator: touched docs that pass the filter, finite score (candidate.rs:275).
+__global__ void __launch_bounds__(kSpThreads, 2) sparse_select_kernel(const SparseParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SpSmem& s = *reinterpret_cast<SpSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TopK tk{s.buf, &s.cnt, &s.thr, kSpCap, Group{tid, kSpThreads, 0}, s.hist};
+  tk.init();
+  __syncthreads();
+  SPTRACE(0);
+  const uint32_t k = p.k;
+  const uint32_t n_wblocks = (p.n_blocks + kSpR - 1) / kSpR;
+  const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
+  for (uint32_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
+    const uint32_t wb = step * kSpWarps + warp;
+    const uint32_t d0 = wb * kSpWDocs;
+    // pushed in two halves of <= kSpWarps * 128 = 2048 keys with a re-selection in between: a selection
+    // leaves at most kSpCap / 2 keys, so the accumulator (4096 slots) cannot overflow whatever the scores are
 #pragma unroll 1
     for (uint32_t half = 0; half < 2; ++half) {
       const ckey_t thr = s.thr;
       if (wb < n_wblocks) {
-        for (uint32_t d = half * (kSpWDocs / 2) + lane; d < (half + 1) * (kSpWDocs / 2); d += 32) {
+#pragma unroll
+        for (uint32_t j = half * (kSpWDocs / 64); j < (half + 1) * (kSpWDocs / 64); ++j) {
+          const uint32_t d = j * 32 + lane;
           const uint64_t r = (uint64_t)d0 + d;
-          if (!touched[d] || r >= p.n_docs) continue;
+          const uint32_t bits = __ldcg(p.blk_mask + (size_t)wb * (kSpWDocs / 32) + j);
+          if (!((bits >> lane) & 1u) || r >= p.n_docs) continue;
           if (p.bitset && !((__ldg(p.bitset + (r >> 5)) >> (r & 31)) & 1u)) continue;
-          const float sc = acc[d];
+          const float sc = __ldcg(p.blk_scores + r);
           if (!finite_bits(__float_as_uint(sc))) continue;
           const ckey_t key = make_key(sc, (uint32_t)r);
           if (key > thr) tk.push(key);
@@ -331,7 +377,10 @@ __global__ void __launch_bounds__(kSpThreads, 2) sparse_search_kernel(const Spar
   merge_partials_and_emit<kSpCap / kSpThreads>(tk, s.pos, k, p.partial, p.partial_cnt, gridDim.x,
                                                p.row_base, p.out_scores, p.out_rows, p.out_n);
   SPTRACE(5);
-  if (tid == 0) *p.done = 0;
+  if (tid == 0) {
+    *p.done = 0;
+    *p.claim = 0;     // the accumulate kernel's block counter, for the next query
+  }
 }
 
 size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz) {
@@ -339,9 +388,17 @@ size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz) {
   return (size_t)q_nnz * (n_blocks + 1) * sizeof(uint32_t);
 }
 
-cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
+size_t sparse_block_scratch_bytes(uint64_t n_docs) {
+  const uint64_t n_blocks = (n_docs + kSpBlock - 1) / kSpBlock;
+  const uint64_t n_wblocks = (n_blocks + kSpR - 1) / kSpR;
+  return (size_t)n_wblocks * kSpWDocs * sizeof(float) + (size_t)n_wblocks * (kSpWDocs / 32) * sizeof(uint32_t);
+}
+
+// slim: the accumulate kernel is launched in its co-resident form (see above) — the caller has a
+// dense scan in flight on another stream of the same device.
+cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st, bool slim) {
   if (a.n_docs == 0 || a.k == 0 || a.k > kMaxK || a.q_nnz == 0 || a.q_nnz > kSpMaxQ ||
-      a.n_docs > 0xFFFFFFFFull || !a.d_bounds)
+      a.n_docs > 0xFFFFFFFFull || !a.d_bounds || !a.d_block_scratch || !a.d_claim)
     return cudaErrorInvalidValue;
   const uint32_t n_blocks = (uint32_t)((a.n_docs + kSpBlock - 1) / kSpBlock);
   int dev = 0, sms = 148;
@@ -352,7 +409,8 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   const bool use_index = a.sp.d_slot_of && a.sp.d_block_index && a.sp.index_stride == n_blocks + 1;
   BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds,
                   use_index ? a.sp.d_slot_of : nullptr};
-  sparse_bounds_kernel<<<sms * 6, 256, 0, st>>>(bp);
+  if (slim) sparse_bounds_kernel<96><<<sms * 2, 96, 0, st>>>(bp);
+  else sparse_bounds_kernel<256><<<sms * 6, 256, 0, st>>>(bp);
   SparseParams p;
   p.tptr = a.sp.d_tptr; p.post = (const uint2*)a.sp.d_post; p.vocab = a.sp.vocab;
   p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
@@ -364,14 +422,34 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
   p.out_scores = a.d_out_scores; p.out_rows = a.d_out_rows; p.out_n = a.d_out_n;
   p.trace = (unsigned long long*)a.d_trace;
   const uint32_t n_wblocks = (n_blocks + kSpR - 1) / kSpR;
+  p.claim = a.d_claim;
+  p.blk_scores = (float*)a.d_block_scratch;
+  p.blk_mask = (uint32_t*)((uint8_t*)a.d_block_scratch + (size_t)n_wblocks * kSpWDocs * sizeof(float));
+  // ---- accumulate ----
+  if (slim) {
+    e = cudaFuncSetAttribute(sparse_accum_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(SpAccSmem<3>));
+    if (e != cudaSuccess) return e;
+    const uint32_t want = (n_wblocks + 2) / 3;
+    const int grid = (int)(want < (uint32_t)(2 * sms) ? want : (uint32_t)(2 * sms));
+    sparse_accum_kernel<3><<<grid, 96, sizeof(SpAccSmem<3>), st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(sparse_accum_kernel<kSpWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(SpAccSmem<kSpWarps>));
+    if (e != cudaSuccess) return e;
+    const uint32_t want = (n_wblocks + kSpWarps - 1) / kSpWarps;
+    const int grid = (int)(want < (uint32_t)(2 * sms) ? want : (uint32_t)(2 * sms));
+    sparse_accum_kernel<kSpWarps><<<grid, kSpThreads, sizeof(SpAccSmem<kSpWarps>), st>>>(p);
+  }
+  // ---- select ----
   const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
   int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
   if (grid > (int)kMaxGrid) grid = kMaxGrid;
-  e = cudaFuncSetAttribute(sparse_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(sparse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(SpSmem));
   if (e != cudaSuccess) return e;
-  sparse_search_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
-  g_kernel_launches.fetch_add(2, std::memory_order_relaxed);
+  sparse_select_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
+  g_kernel_launches.fetch_add(3, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
@@ -395,7 +473,7 @@ cudaError_t launch_sparse_block_index(const SparseDev& sp, const uint32_t* d_tok
   cudaError_t e = cudaMemsetAsync(rows, 0, (size_t)n_tok * sp.index_stride * sizeof(uint32_t), st);
   if (e != cudaSuccess) return e;
   BoundsParams bp{sp.d_tptr, sp.d_doc, sp.vocab, d_tokens, n_tok, n_blocks, rows, nullptr};
-  sparse_bounds_kernel<<<sms * 6, 256, 0, st>>>(bp);
+  sparse_bounds_kernel<256><<<sms * 6, 256, 0, st>>>(bp);
   g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

@@ -27,9 +27,13 @@ for i in range(8):
     tr = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
     tr = tr.reshape(1024, 8).astype(np.int64)
-    d, s = tr[:148], tr[512:512 + 296]
-    s = s[s[:, 3] > d[:, 0].min()]                         # sparse CTAs of THIS query only (the grid can be < 296)
+    d, sp = tr[:148], tr[512:512 + 296]
     t0 = d[:, 0].min()
-    print(f"query {i}: dense CTAs start {(d[:,0].min()-t0)/1e3:.1f}..{(d[:,0].max()-t0)/1e3:.1f}, stream end {(d[:,1].max()-t0)/1e3:.1f}, "
-          f"ticket {(d[:,3].max()-t0)/1e3:.1f}, kernel end {(d[:,4].max()-t0)/1e3:.1f} | sparse search CTAs start "
-          f"{(s[:,0].min()-t0)/1e3:.1f}..{(s[:,0].max()-t0)/1e3:.1f}, loop end {(s[:,3].max()-t0)/1e3:.1f}, merge end {(s[:,5].max()-t0)/1e3:.1f} us")
+    acc = sp[sp[:, 6] > t0]                                # accumulate CTAs of THIS query (slots 6, 7)
+    sel = sp[sp[:, 3] > t0]                                # select CTAs (slots 0..5)
+    us = lambda x: (x - t0) / 1e3
+    print(f"query {i}: dense CTAs start {us(d[:,0].min()):.1f}..{us(d[:,0].max()):.1f}, stream end {us(d[:,1].max()):.1f}, "
+          f"ticket {us(d[:,3].max()):.1f}, kernel end {us(d[:,4].max()):.1f} | sparse accumulate ({acc.shape[0]} CTAs) start "
+          f"{us(acc[:,6].min()):.1f}..{us(acc[:,6].max()):.1f}, end {us(acc[:,7].min()):.1f}..{us(acc[:,7].max()):.1f} | select "
+          f"({sel.shape[0]} CTAs) start {us(sel[:,0].min()):.1f}..{us(sel[:,0].max()):.1f}, loop end {us(sel[:,3].max()):.1f}, "
+          f"merge end {us(sel[:,5].max()):.1f} us")

@@ -36,9 +36,11 @@ for k in (20, 500):
     tr = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
     tr = tr.reshape(1024, 8)[512:512 + 296].astype(np.int64)
-    tr = tr[tr[:, 3] > 0]                                  # CTAs of this launch only (the grid can be < 296)
-    t0 = tr[:, 0].min(); rel = (tr - t0) / 1e3
-    last = int(np.argmax(tr[:, 5]))
-    print(f"k={k}: both kernels {ix.last_kernel_ms()*1e3:.0f} us | first step accumulate done: med {np.median(rel[:,1]):.1f} us | "
-          f"first select done: med {np.median(rel[:,2]):.1f} | loop end: med {np.median(rel[:,3]):.1f} max {rel[:,3].max():.1f} | "
-          f"final compact: {np.median(rel[:,4]-rel[:,3]):.1f} | merge (CTA {last}): {rel[last,4]:.1f} -> {rel[last,5]:.1f}")
+    acc = tr[tr[:, 6] > 0]
+    sel = tr[tr[:, 3] > 0]
+    t0 = acc[:, 6].min(); us = lambda x: (x - t0) / 1e3
+    last = int(np.argmax(sel[:, 5]))
+    print(f"k={k}: all kernels {ix.last_kernel_ms()*1e3:.0f} us | accumulate ({acc.shape[0]} CTAs): start 0..{us(acc[:,6].max()):.1f}, "
+          f"end {us(acc[:,7].min()):.1f}..{us(acc[:,7].max()):.1f} | select ({sel.shape[0]} CTAs): start {us(sel[:,0].min()):.1f}, first "
+          f"half pushed {np.median(us(sel[:,1])):.1f}, loop end med {np.median(us(sel[:,3])):.1f} max {us(sel[:,3].max()):.1f}, "
+          f"finish {np.median(sel[:,4]-sel[:,3])/1e3:.1f}, merge (CTA {last}) {us(sel[last,4]):.1f} -> {us(sel[last,5]):.1f}")
