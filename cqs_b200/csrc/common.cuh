@@ -146,13 +146,109 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
   }
 }
 
-// compact() uses a rank sort up to this many keys, the register/shuffle bitonic network above.
-// Measured warm (tools/bench_topk.py, one 256-thread CTA): rank sort 128 / 256 / 500 keys = 1.3 / 2.5 /
-// 8.6 us (quadratic); bitonic 256 / 512 / 1024 slots = 4.6 / 6.0 / 7.8 us.  Measured where it matters —
-// the last CTA's final sort of ~500 keys inside the scan kernel (tools/trace_scan.py): bitonic 11.6 us
-// (its code runs once, instruction-cache cold), rank sort 20 us.  256 keeps the rank sort where it wins
-// either way.
-constexpr uint32_t kRankSortMax = 256;
+// ---- chunk sort + cross rank ----------------------------------------------------
+// Descending sort of buf[0..n), result in buf[0..n); `scratch` holds n rounded up to C keys.  The warps
+// sort chunks of C = 32 R keys in registers (bitonic network: strides < 32 are lane
+// shuffles, the others register to register) and writes it to scratch; then every key's final position
+// is its index in its own chunk plus, for every other chunk, the number of keys there that beat it — a
+// branch-free binary search (log2 C + 1 probes, four chunks' searches interleaved).  Keys are unique;
+// padding keys are 0 and land at positions >= n, where they are dropped.  Two barriers, no quadratic loop:
+// 500 keys cost ~2 us on 8 warps where the rank sort this replaces took 11 us and the full bitonic
+// network 18 us (measured inside the scan kernel, tools/trace_scan.py).
+template <int R>
+__device__ __forceinline__ void chunk_network(ckey_t (&reg)[R], uint32_t lane) {
+  constexpr uint32_t C = 32 * R;
+#pragma unroll
+  for (uint32_t size = 2; size <= C; size <<= 1) {
+#pragma unroll
+    for (uint32_t st = size >> 1; st > 0; st >>= 1) {
+      if (st >= 32) {
+        const uint32_t rs = st >> 5;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)R; ++r) {
+          if (r & rs) continue;
+          const bool dir = ((r * 32 + lane) & size) == 0;   // true: larger key first
+          const ckey_t a = reg[r], b2 = reg[r | rs];
+          if ((a < b2) == dir) {
+            reg[r] = b2;
+            reg[r | rs] = a;
+          }
+        }
+      } else {
+        const bool lower = (lane & st) == 0;
+#pragma unroll
+        for (uint32_t r = 0; r < (uint32_t)R; ++r) {
+          const bool dir = (((r * 32 + lane) & ~st) & size) == 0;
+          const ckey_t mine = reg[r];
+          const ckey_t other = __shfl_xor_sync(0xffffffffu, mine, st);
+          reg[r] = (lower == dir) ? (mine > other ? mine : other) : (mine < other ? mine : other);
+        }
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void chunk_rank_sort(const Group& g, ckey_t* buf, ckey_t* scratch, uint32_t n) {
+  constexpr uint32_t C = 32 * R;
+  const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
+  const uint32_t nchunks = (n + C - 1) / C;   // a warp takes chunks warp, warp + nwarps, ..
+  ckey_t reg[R];
+  for (uint32_t c = warp; c < nchunks; c += nwarps) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t i = c * C + r * 32 + lane;
+      reg[r] = i < n ? buf[i] : 0;
+    }
+    chunk_network<R>(reg, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) scratch[c * C + r * 32 + lane] = reg[r];
+  }
+  g.sync();
+  for (uint32_t c = warp; c < nchunks; c += nwarps) {
+    uint32_t pos[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      pos[r] = r * 32 + lane;
+      reg[r] = scratch[c * C + pos[r]];
+    }
+    // other chunks, four at a time: 4 R independent probe chains
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += 4) {
+      uint32_t lo[4][R];
+      const ckey_t* arr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // the own chunk and chunks past the end are searched too (keeps the code uniform); their counts
+        // are discarded below
+        arr[u] = scratch + min(c0 + u, nchunks - 1) * C;
+#pragma unroll
+        for (int r = 0; r < R; ++r) lo[u][r] = 0;
+      }
+#pragma unroll
+      for (uint32_t st = C >> 1; st > 0; st >>= 1)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (arr[u][lo[u][r] + st - 1] > reg[r]) lo[u][r] += st;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (arr[u][lo[u][r]] > reg[r]) lo[u][r] += 1;
+          if (c0 + u < nchunks && c0 + u != c) pos[r] += lo[u][r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (pos[r] < n) buf[pos[r]] = reg[r];
+  }
+  g.sync();
+}
+
+// Up to this many keys the finishing code sorts directly (chunk sort); above it a histogram selection
+// (3 us) first cuts the buffer down to ~k keys.
+constexpr uint32_t kDirectSortMax = 1024;
 constexpr uint32_t kSelBuckets = 2048;  // histogram resolution of select()
 
 // Group-level streaming top-k accumulator.  `buf` has CAP slots (power of two).
@@ -173,35 +269,66 @@ struct TopK {
       *thr = 0;
     }
   }
+  // The out-of-line functions below receive this struct by value and would otherwise address the
+  // buffer with GENERIC loads and stores (LD.E/ST.E through the global pipe: a final sort of 500 keys
+  // took 15 us inside the scan kernel and 5.5 us in a test kernel that could see the __shared__
+  // declaration).  Tells the compiler which window the pointers are in.
+  __device__ __forceinline__ void assume_shared() const {
+    __builtin_assume(__isShared(buf));
+    __builtin_assume(__isShared(cnt));
+    __builtin_assume(__isShared(thr));
+  }
   __device__ __forceinline__ void push(ckey_t key) {
     uint32_t slot = atomicAdd(cnt, 1u);
     if (slot < cap) buf[slot] = key;  // cannot fail when the caller honours the bound
   }
   // Collective.  Afterwards buf[0..min(n,k)) holds the best keys, descending.
-  __device__ __forceinline__ void compact(uint32_t k, uint32_t rank_sort_max = kRankSortMax);
-  __device__ __forceinline__ void compact_impl(uint32_t k, uint32_t rank_sort_max) {
+  __device__ __forceinline__ void compact(uint32_t k, bool force_network = false);
+  __device__ __forceinline__ void compact_impl(uint32_t k, bool force_network) {
     g.sync();
     uint32_t n = min(*cnt, cap);
-    if (n <= rank_sort_max) {
-      // small n: rank sort.  Every thread counts how many keys beat its own (all
-      // threads read the same address each step -> shared-memory broadcast) and
-      // scatters the key to that rank in the scratch half of the buffer.  Keys are
-      // unique (the row is part of the key).
-      ckey_t* scratch = buf + (cap >> 1);
-      for (uint32_t i = g.tid; i < n; i += g.nthr) {
-        const ckey_t mine = buf[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < n; ++j) rank += (buf[j] > mine) ? 1u : 0u;
-        scratch[rank] = mine;
-      }
-      g.sync();
-      for (uint32_t i = g.tid; i < n; i += g.nthr) buf[i] = scratch[i];
-      g.sync();
-    } else {
+    const uint32_t per_r = g.nthr;   // keys per register of chunk_rank_sort when every warp takes one chunk
+    ckey_t* scratch = buf + (cap >> 1);   // the sorted chunks (n <= cap / 2 on that path)
+    if (force_network || n > (cap >> 1)) {
       uint32_t P = max(next_pow2(n), kSortChunk);  // cap >= kSortChunk
       for (uint32_t i = n + g.tid; i < P; i += g.nthr) buf[i] = 0;
       g.sync();
       block_sort_desc(g, buf, P);
+    } else if (n <= per_r) {
+      chunk_rank_sort<1>(g, buf, scratch, n);
+    } else if (n <= 2 * per_r) {
+      chunk_rank_sort<2>(g, buf, scratch, n);
+    } else {
+      // Above 4 keys per thread the warps take several chunks each — except for a FEW keys more than one
+      // chunk per warp (a selection for k = 4 nthr leaves k plus the ties of the k-th key's bucket), where a
+      // second round of chunks would double the cost: sort the first 4 nthr keys, then merge the e <= 32
+      // others in (a sorted key moves down by the number of extras that beat it; an extra goes to its rank
+      // among the sorted keys plus its rank among the extras).
+      const uint32_t n0 = (n > 4 * per_r && n <= 4 * per_r + 32) ? 4 * per_r : n;
+      chunk_rank_sort<4>(g, buf, scratch, n0);          // leaves buf[n0..n) alone; scratch is free again
+      if (n0 < n) {
+        const uint32_t e = n - n0;
+        for (uint32_t i = g.tid; i < n0; i += g.nthr) {
+          const ckey_t key = buf[i];
+          uint32_t pos = i;
+          for (uint32_t x = 0; x < e; ++x) pos += (buf[n0 + x] > key) ? 1u : 0u;
+          scratch[pos] = key;
+        }
+        if (g.tid < e) {
+          const ckey_t key = buf[n0 + g.tid];
+          uint32_t lo = 0, hi = n0;                     // first sorted key <= key
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (buf[mid] > key) lo = mid + 1; else hi = mid;
+          }
+          uint32_t pos = lo;
+          for (uint32_t x = 0; x < e; ++x) pos += (buf[n0 + x] > key) ? 1u : 0u;
+          scratch[pos] = key;
+        }
+        g.sync();
+        for (uint32_t i = g.tid; i < n; i += g.nthr) buf[i] = scratch[i];
+        g.sync();
+      }
     }
     if (g.tid == 0) {
       *cnt = min(n, k);
@@ -225,12 +352,14 @@ struct TopK {
   __device__ __forceinline__ void select_impl(uint32_t k, uint32_t m, ckey_t* vm_out) {
     g.sync();
     const uint32_t n = min(*cnt, cap);
-    if (n <= kRankSortMax || n <= k || hist == nullptr) {
+    if (n <= kDirectSortMax || n <= k || hist == nullptr) {
       compact(k);
       if (vm_out && g.tid == 0) *vm_out = (m > 0 && m <= min(n, k)) ? buf[m - 1] : 0;
       g.sync();
       return;
     }
+    __builtin_assume(__isShared(hist));   // (non-null past the early return)
+    if (vm_out) __builtin_assume(__isShared(vm_out));
     const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
     ckey_t r[ITEMS];
     ckey_t lo = ~0ull, hi = 0;
@@ -376,14 +505,16 @@ struct TopK {
 // per-CTA finish and the last CTA's merge: the merge runs once per kernel, and its private inlined
 // copies of this code were instruction-cache misses from L2 (2.6 us warm, 11 us measured there); the
 // streaming loop has executed the shared copy on the same SM moments earlier.
-static __device__ __noinline__ void topk_compact(TopK tk, uint32_t k, uint32_t rank_sort_max) {
-  tk.compact_impl(k, rank_sort_max);
+static __device__ __noinline__ void topk_compact(TopK tk, uint32_t k, bool force_network) {
+  tk.assume_shared();
+  tk.compact_impl(k, force_network);
 }
-__device__ __forceinline__ void TopK::compact(uint32_t k, uint32_t rank_sort_max) {
-  topk_compact(*this, k, rank_sort_max);
+__device__ __forceinline__ void TopK::compact(uint32_t k, bool force_network) {
+  topk_compact(*this, k, force_network);
 }
 template <int ITEMS>
 __device__ __noinline__ void topk_select(TopK tk, uint32_t k, uint32_t m, ckey_t* vm_out) {
+  tk.assume_shared();
   tk.template select_impl<ITEMS>(k, m, vm_out);
 }
 template <int ITEMS>
@@ -393,8 +524,8 @@ __device__ __forceinline__ void TopK::select(uint32_t k, uint32_t m, ckey_t* vm_
 
 // Collective: exact top-k of whatever the accumulator holds, descending in buf[0..min(n,k)).
 // Two histogram selections (3 us each) first cut the buffer down to the k best plus the few
-// keys sharing the k-th key's bucket, so the exact sort runs on ~k keys (rank sort when
-// k <= 512) instead of on the whole buffer (a 2048-4096 key bitonic sort costs 20-40 us,
+// keys sharing the k-th key's bucket, so the exact sort runs on ~k keys (the chunk sort above)
+// instead of on the whole buffer (a 2048-4096 key bitonic sort costs 20-40 us,
 // paid by every CTA at the end of its scan and again by the last CTA's merge).
 // Not inlined (TopK by value: a handful of shared-memory pointers): the scan file instantiates
 // 48 kernels and this tail code would otherwise be compiled into each of them.
@@ -404,20 +535,30 @@ __device__ __forceinline__ void TopK::select(uint32_t k, uint32_t m, ckey_t* vm_
   } while (0)
 template <int ITEMS>
 __device__ __noinline__ void topk_finish(TopK tk, uint32_t k, unsigned long long* stamps = nullptr) {
+  tk.assume_shared();
   tk.g.sync();
   if (stamps && tk.g.tid == 0) stamps[7] = *tk.cnt;
   // a selection (2.6 us) pays off when it moves the sort to a smaller network / into rank-sort range
-  if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k + 64) {
+  if (min(*tk.cnt, tk.cap) > kDirectSortMax && *tk.cnt > k + 64) {
     const ckey_t before = *tk.thr;
     tk.template select<ITEMS>(k);
     if (tk.g.tid == 0 && before > *tk.thr) *tk.thr = before;
     tk.g.sync();
     CQS_STAMP(stamps, 4);
-    if (min(*tk.cnt, tk.cap) > kRankSortMax && *tk.cnt > k + 64) tk.template select<ITEMS>(k);
+    if (min(*tk.cnt, tk.cap) > kDirectSortMax && *tk.cnt > k + 64) tk.template select<ITEMS>(k);
     CQS_STAMP(stamps, 5);
   }
   if (stamps && tk.g.tid == 0) stamps[6] = *tk.cnt;
+  long long c0 = 0;
+  if (stamps && tk.g.tid == 0) {   // development aid: SM cycles beside the wall-clock stamps (row below)
+    c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"((stamps - 8)[0]));
+  }
   tk.compact(k);
+  if (stamps && tk.g.tid == 0) {
+    (stamps - 8)[2] = (unsigned long long)(clock64() - c0);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"((stamps - 8)[1]));
+  }
 }
 
 constexpr uint32_t kPartialStride = 1024;  // == kMaxK: slots per CTA in the partial-list scratch
@@ -448,6 +589,8 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
                                                         unsigned long long* trace = nullptr,
                                                         ckey_t thr0 = 0) {
   // thr0: a lower bound of the global k-th best key the caller already knows (0 = none)
+  tk.assume_shared();
+  __builtin_assume(__isShared(s_pos));
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
   // development aid: extra stamps of the merge go to the last row of the trace buffer
   unsigned long long* mstamps = trace ? trace - (size_t)blockIdx.x * 8 + (size_t)(kPartialStride - 1) * 8 : nullptr;
@@ -478,8 +621,15 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
       if (mine == 0) continue;
       const uint32_t j = (k + ms[c2] - 1) / ms[c2];  // need the j-th largest of this column
       const ckey_t* cc = col + c2 * G;
-      uint32_t rank = 0;
-      for (uint32_t i = 0; i < G; ++i) rank += (cc[i] > mine) ? 1u : 0u;  // keys are unique
+      uint32_t rank = 0, i = 0;  // keys are unique
+      for (; i + 8 <= G; i += 8) {
+        ckey_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = cc[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rank += (v[u] > mine) ? 1u : 0u;
+      }
+      for (; i < G; ++i) rank += (cc[i] > mine) ? 1u : 0u;
       if (rank == j - 1) atomicMax(tk.thr, mine - 1);  // keys >= v pass "key > thr"
     }
     tk.g.sync();

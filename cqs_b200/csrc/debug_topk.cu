@@ -4,6 +4,8 @@
 // tuned from measurements instead of guesses.  tools/bench_topk.py drives it.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -22,13 +24,15 @@ __device__ __forceinline__ uint64_t splitmix(uint64_t x) {
 // op: 0 = select(k), 1 = compact(k), 2 = topk_finish(k), 3 = prune(median key), 4 = compact(k) forced bitonic
 __global__ void __launch_bounds__(kDbgThreads) debug_topk_kernel(int op, uint32_t n, uint32_t k, uint32_t reps,
                                                                  unsigned long long* out_ns, uint32_t* out_cnt) {
-  __shared__ ckey_t s_buf[kDbgCap];
+  __shared__ __align__(16) ckey_t s_buf[kDbgCap];
   __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   const uint32_t tid = threadIdx.x;
   TopK tk{s_buf, &s_cnt, &s_thr, kDbgCap, Group{tid, kDbgThreads, 0}, s_hist};
-  unsigned long long total = 0;
+  const bool cold = (op & 16) != 0;   // report the FIRST repetition (cold instruction cache) instead of the mean of the rest
+  op &= 15;
+  unsigned long long total = 0, first = 0;
   for (uint32_t r = 0; r < reps; ++r) {
     // keys shaped like scan candidates: scores ~ tail of a normal (0.1 .. 0.2), unique rows
     for (uint32_t i = tid; i < n; i += kDbgThreads) {
@@ -47,21 +51,67 @@ __global__ void __launch_bounds__(kDbgThreads) debug_topk_kernel(int op, uint32_
     if (op == 0) tk.template select<kDbgCap / kDbgThreads>(k);
     else if (op == 1) tk.compact(k);
     else if (op == 2) topk_finish<kDbgCap / kDbgThreads>(tk, k);
-    else if (op == 4) tk.compact(k, 0);   // always the register/shuffle bitonic network
+    else if (op == 4) tk.compact(k, true);   // always the register/shuffle bitonic network
     else tk.template prune<kDbgCap / kDbgThreads>(make_key(0.105f, 0));
     __syncthreads();
     if (tid == 0) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (r > 0) total += t1 - t0;   // first repetition warms the instruction cache
+      else first = t1 - t0;
     }
   }
   if (tid == 0) {
-    *out_ns = total / (reps > 1 ? reps - 1 : 1);
+    *out_ns = cold ? first : total / (reps > 1 ? reps - 1 : 1);
     *out_cnt = s_cnt;
   }
 }
+// compact(k) of caller-supplied keys by a CTA of THREADS threads: the sorted survivors go back to the host
+// (tests/test_gpu_dense.py checks them against numpy for every sort path and chunk boundary)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) debug_sort_kernel(const ckey_t* in, uint32_t n, uint32_t k, int op,
+                                                             ckey_t* out, uint32_t* out_cnt) {
+  __shared__ __align__(16) ckey_t s_buf[kDbgCap];
+  __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
+  __shared__ uint32_t s_cnt;
+  __shared__ ckey_t s_thr;
+  const uint32_t tid = threadIdx.x;
+  TopK tk{s_buf, &s_cnt, &s_thr, kDbgCap, Group{tid, THREADS, 0}, s_hist};
+  for (uint32_t i = tid; i < n; i += THREADS) s_buf[i] = in[i];
+  if (tid == 0) {
+    s_cnt = n;
+    s_thr = 0;
+  }
+  __syncthreads();
+  if (op == 2) topk_finish<kDbgCap / THREADS>(tk, k);
+  else tk.compact(k, op == 4);
+  __syncthreads();
+  for (uint32_t i = tid; i < s_cnt; i += THREADS) out[i] = s_buf[i];
+  if (tid == 0) *out_cnt = s_cnt;
+}
 }  // namespace
 }  // namespace cqs
+
+extern "C" int cqs_b200_debug_sort(int device, int threads, int op, const unsigned long long* keys, uint32_t n, uint32_t k,
+                                   unsigned long long* out, uint32_t* out_cnt) {
+  using namespace cqs;
+  if (n > kDbgCap || (threads != 256 && threads != 512)) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -2;
+  ckey_t *d_in = nullptr, *d_out = nullptr;
+  uint32_t* d_cnt = nullptr;
+  if (cudaMalloc((void**)&d_in, 8 * (size_t)kDbgCap) != cudaSuccess || cudaMalloc((void**)&d_out, 8 * (size_t)kDbgCap) != cudaSuccess ||
+      cudaMalloc((void**)&d_cnt, 4) != cudaSuccess)
+    return -2;
+  cudaError_t e = cudaMemcpy(d_in, keys, 8 * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    if (threads == 256) debug_sort_kernel<256><<<1, 256>>>(d_in, n, k, op, d_out, d_cnt);
+    else debug_sort_kernel<512><<<1, 512>>>(d_in, n, k, op, d_out, d_cnt);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_cnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 8 * (size_t)std::min<uint32_t>(*out_cnt, kDbgCap), cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_cnt);
+  return e == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int cqs_b200_debug_topk_ns(int device, int op, uint32_t n, uint32_t k, uint32_t reps,
                                       unsigned long long* out_ns, uint32_t* out_cnt) {
@@ -88,6 +138,8 @@ namespace cqs {
 namespace {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) probe_kernel(unsigned long long* stamps, uint32_t* smid, unsigned long long spin_ns) {
+  extern __shared__ uint8_t probe_smem[];
+  if (spin_ns == 1) probe_smem[threadIdx.x] = 1;   // keeps the dynamic shared memory referenced
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   if (threadIdx.x == 0) {
@@ -115,15 +167,15 @@ __global__ void __launch_bounds__(THREADS) probe_kernel(unsigned long long* stam
 }  // namespace cqs
 
 extern "C" int cqs_b200_debug_probe(int threads, uint32_t grid, unsigned long long* d_stamps, uint32_t* d_smid,
-                                    unsigned long long spin_ns, void* stream) {
+                                    unsigned long long spin_ns, void* stream, uint32_t smem_bytes) {
   using namespace cqs;
   cudaStream_t st = (cudaStream_t)stream;
   switch (threads) {
-    case 64: probe_kernel<64><<<grid, 64, 0, st>>>(d_stamps, d_smid, spin_ns); break;
-    case 96: probe_kernel<96><<<grid, 96, 0, st>>>(d_stamps, d_smid, spin_ns); break;
-    case 128: probe_kernel<128><<<grid, 128, 0, st>>>(d_stamps, d_smid, spin_ns); break;
-    case 192: probe_kernel<192><<<grid, 192, 0, st>>>(d_stamps, d_smid, spin_ns); break;
-    case 256: probe_kernel<256><<<grid, 256, 0, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 64: probe_kernel<64><<<grid, 64, smem_bytes, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 96: probe_kernel<96><<<grid, 96, smem_bytes, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 128: probe_kernel<128><<<grid, 128, smem_bytes, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 192: probe_kernel<192><<<grid, 192, smem_bytes, st>>>(d_stamps, d_smid, spin_ns); break;
+    case 256: probe_kernel<256><<<grid, 256, smem_bytes, st>>>(d_stamps, d_smid, spin_ns); break;
     default: return -1;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;

@@ -1686,10 +1686,9 @@ int cqs_b200_debug_sparse_postings(cqs_b200_index* ix, uint64_t* tptr, uint32_t*
   return cudaGetLastError() == cudaSuccess ? CQS_B200_OK : CQS_B200_ERR_CUDA;
 } API_CATCH
 
-static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
-                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st = nullptr,
-                         bool slim = false) {
-  if (!st) st = s.stream;
+// uploads the sparse query on `st`, sizes the per-query scratch and fills the launch arguments
+static int stage_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
+                        uint32_t q_nnz, uint32_t k, const uint32_t* d_bits, cudaStream_t st, SparseArgs& a) {
   // through pinned staging: a pageable source would make these copies synchronous with the host
   memcpy(s.h_sq, q_tok, sizeof(uint32_t) * q_nnz);
   memcpy(s.h_sq + kSpMaxQ, q_w, sizeof(float) * q_nnz);
@@ -1713,7 +1712,6 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
     CK(ix, cudaMalloc(&s.d_sp_block, need_blk));
     s.sp_block_bytes = need_blk;
   }
-  SparseArgs a;
   a.d_block_scratch = s.d_sp_block;
   a.d_claim = s.d_sp_claim;
   a.d_bounds = s.d_bounds;
@@ -1722,7 +1720,15 @@ static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, co
   a.d_bitset = d_bits; a.k = k; a.row_base = ix->row_base + s.first_row;
   a.d_partial = s.d_sp_partial; a.d_partial_cnt = s.d_sp_partial_cnt; a.d_done = s.d_sp_done;
   a.d_out_scores = s.d_sp_scores; a.d_out_rows = s.d_sp_rows; a.d_out_n = s.d_sp_n;
-  CK(ix, launch_sparse_search(a, st, slim));
+  return 0;
+}
+
+static int launch_sparse(cqs_b200_index* ix, Shard& s, const uint32_t* q_tok, const float* q_w,
+                         uint32_t q_nnz, uint32_t k, const uint32_t* d_bits) {
+  SparseArgs a;
+  int rc = stage_sparse(ix, s, q_tok, q_w, q_nnz, k, d_bits, s.stream, a);
+  if (rc) return rc;
+  CK(ix, launch_sparse_search(a, s.stream));
   return 0;
 }
 
@@ -1798,7 +1804,19 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   CK(ix, cudaMemsetAsync(s.d_out_n, 0, 4, s.stream));
   CK(ix, cudaMemsetAsync(s.d_sp_n, 0, 4, s.stream));
   if (peer) CK(ix, cudaMemsetAsync(s.d_spm_n, 0, 4, s.stream));
-  CK(ix, cudaEventRecord(s.ev_fork, s.stream));   // fork point of the sparse leg's stream (see below)
+  // The legs are independent until the fusion.  Without a filter or a peer group (one staging buffer,
+  // one ordered exchange stream) the sparse leg's accumulate + select go to a second stream: their CTAs
+  // cannot share an SM with the scan's, so they start as the scan's CTAs retire and run while the scan's
+  // LAST CTA merges the per-CTA lists (tens of microseconds on one SM at k = 500) — the dense leg's tail
+  // is hidden behind the sparse leg instead of preceding it.  The query upload and the bounds pass go
+  // BEFORE the scan (a few microseconds on an idle device instead of after the scan).
+  const bool overlap = !peer && !bitset && dense_ok && q_nnz != 0 && q_tok && q_w;
+  SparseArgs sa;
+  if (overlap) {
+    if ((rc = stage_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, nullptr, s.stream, sa))) return rc;
+    CK(ix, launch_sparse_stage(sa, kSparseBounds, s.stream));
+  }
+  CK(ix, cudaEventRecord(s.ev_fork, s.stream));   // fork point of the sparse leg's streams
   const uint32_t* d_bits = nullptr;
   if (dense_ok) {
     PeerCtx pc;
@@ -1814,21 +1832,15 @@ static int search_hybrid_impl(cqs_b200_index* ix, cqs_b200_peer* peer, const flo
   }
   if (q_nnz) {
     if (!q_tok || !q_w) return fail(CQS_B200_ERR_INVALID, "NULL sparse query");
-    // The legs are independent until the fusion.  The sparse leg goes to a second stream: its CTAs
-    // cannot share an SM with the scan's (shared memory), so they start as the scan's CTAs retire and
-    // run while the scan's LAST CTA merges the per-CTA lists (tens of microseconds on one SM at
-    // k = 500) — the dense leg's tail is hidden behind the sparse leg instead of preceding it.
-    // (Not with a filter bitset, which both legs read from one staging buffer, nor with a peer
-    // group, whose exchanges are ordered on one stream.)
-    cudaStream_t sp_st = (!peer && !bitset && dense_ok) ? s.lane_stream[0] : s.stream;
-    // (ev_fork was recorded BEFORE the dense launch: the sparse stream only waits for the resets
-    // above; the scan was submitted first and takes the SMs first)
-    if (sp_st != s.stream) CK(ix, cudaStreamWaitEvent(sp_st, s.ev_fork, 0));
-    rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits, sp_st, /*slim=*/sp_st != s.stream);
-    if (rc) return rc;
-    if (sp_st != s.stream) {
-      CK(ix, cudaEventRecord(s.ev_join[0], sp_st));
+    if (overlap) {
+      cudaStream_t l0 = s.lane_stream[0];
+      CK(ix, cudaStreamWaitEvent(l0, s.ev_fork, 0));
+      CK(ix, launch_sparse_stage(sa, kSparseAccum | kSparseSelect, l0));
+      CK(ix, cudaEventRecord(s.ev_join[0], l0));
       CK(ix, cudaStreamWaitEvent(s.stream, s.ev_join[0], 0));
+    } else {
+      rc = launch_sparse(ix, s, q_tok, q_w, q_nnz, pool_k, d_bits);
+      if (rc) return rc;
     }
     if (peer) {
       PeerCtx pc;

@@ -178,7 +178,10 @@ struct SparseArgs {
 constexpr uint32_t kSparseDocsPerBlock = 64;    // docs owned by one warp at a time
 size_t sparse_bounds_bytes(uint64_t n_docs, uint32_t q_nnz);
 size_t sparse_block_scratch_bytes(uint64_t n_docs);
-cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream, bool slim = false);
+cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t stream);
+// the leg's launches one by one (sparse_fuse.cu): the hybrid call places them around its dense scan
+enum : uint32_t { kSparseBounds = 1, kSparseAccum = 2, kSparseSelect = 8 };
+cudaError_t launch_sparse_stage(const SparseArgs& a, uint32_t stage, cudaStream_t stream);
 
 // Inverted-index build on the device (sparse_build.cu): doc-major CSR -> token-major postings.
 struct SparseBuildArgs {

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, u
                                                                  uint32_t kprime, const ckey_t* sub,
                                                                  const uint8_t* subcnt,
                                                                  uint32_t sub_grid, uint32_t nq_pad) {
-  __shared__ ckey_t s_buf[kUpdCap];
+  __shared__ __align__(16) ckey_t s_buf[kUpdCap];
   __shared__ uint32_t s_hist[kSelBuckets + 96];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kUpdThreads) final_select_kernel(
     const ckey_t* cand, const uint32_t* cnt, const ckey_t* thr, const uint32_t* overflow,
     const float* qnorm, const float* dqnorm, float max_row_norm, float max_row_delta, uint32_t cap, uint32_t kprime, uint32_t k,
     uint64_t row_base, float* out_scores, uint64_t* out_rows, uint32_t* out_n, uint32_t* flags) {
-  __shared__ ckey_t s_buf[kUpdCap];
+  __shared__ __align__(16) ckey_t s_buf[kUpdCap];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;

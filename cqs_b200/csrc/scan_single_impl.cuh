@@ -135,6 +135,8 @@ struct ScanCfg {
 // Not inlined: one copy per translation unit instead of one per instantiation.
 static __device__ __noinline__ void refresh_global_thr(TopK tk, ckey_t* colv, const ckey_t* col,
                                                        uint32_t G, uint32_t j) {
+  tk.assume_shared();
+  __builtin_assume(__isShared(colv));
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
   for (uint32_t l = tid; l < G; l += T) colv[l] = __ldcg(col + l);
   tk.g.sync();
@@ -157,6 +159,7 @@ static __device__ __noinline__ void refresh_global_thr(TopK tk, ckey_t* colv, co
 // Four rows are in flight per warp.  Collective over tk.g; on return buf[0..*cnt) holds the valid
 // exact keys, descending.
 static __device__ __noinline__ void rescore_local(TopK tk, const ScanParams& p) {
+  tk.assume_shared();
   const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   tk.g.sync();
   const uint32_t n = min(*tk.cnt, tk.cap);
@@ -228,6 +231,9 @@ static __device__ __noinline__ void rescore_local(TopK tk, const ScanParams& p) 
 // Returns kUnprovenBit when the proof fails (the host then re-runs the query on the f32 master rows).
 static __device__ __noinline__ uint32_t prove_shadow(TopK tk, const ScanParams& p, const ckey_t* excl, uint32_t G,
                                                      float* s_red, ckey_t* s_cut) {
+  tk.assume_shared();
+  __builtin_assume(__isShared(s_red));
+  __builtin_assume(__isShared(s_cut));
   const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   if (tid == 0) *s_cut = 0;
   const uint32_t ld = p.exact_nv * 128;
@@ -639,6 +645,14 @@ static cudaError_t launch_nv(const ScanParams& p, int num_sms, cudaStream_t st) 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM);
   if (e != cudaSuccess) return e;
+  // CQS_B200_MAX_CARVEOUT (development aid, tools/probe_coresidency.py): with the largest shared-memory
+  // carveout the ~57 KB this kernel leaves unused become available to a small CTA of another kernel on
+  // the same SM.  Off by default — DESIGN.md §4.3c records why nothing is launched beside the scan.
+  static const bool max_carveout = getenv("CQS_B200_MAX_CARVEOUT") != nullptr;
+  if (max_carveout) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+  }
   kern<<<grid, kThreads, Cfg::SMEM, st>>>(q);
   g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();

@@ -51,17 +51,21 @@ struct BoundsParams {
   uint32_t n_blocks;
   uint32_t* bounds;  // [q_nnz][n_blocks + 1]
   const int32_t* slot_of;  // nullable: tokens with slot_of[t] >= 0 have a static row and are skipped
+  unsigned long long* trace = nullptr;  // optional stamps, rows 300.. of the sparse trace (development aid)
 };
 constexpr uint32_t kBoundsChunk = 8192;  // postings per streaming work unit
 constexpr uint32_t kBoundsShort = 256;   // lists up to this long are binary-searched per block instead
-// T threads per CTA: 256 normally; 96 when the leg runs beside a dense scan (a 3-warp CTA fits on an
-// SM next to the scan's CTA, see sparse_accum_kernel).
+// T threads per CTA (256).
 template <int T>
 __global__ void __launch_bounds__(T) sparse_bounds_kernel(const BoundsParams p) {
   __shared__ uint64_t s_base[kSpMaxQ];
   __shared__ uint32_t s_len[kSpMaxQ];
   __shared__ uint64_t s_prefix[kSpMaxQ + 1];  // work units before token i
   const uint32_t tid = threadIdx.x;
+  if (p.trace && tid == 0 && blockIdx.x < 148) {
+    unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.trace[(300 + blockIdx.x) * 8] = t_;
+  }
   const uint32_t search_units = (p.n_blocks + 1 + 4 * T - 1) / (4 * T);  // 4 T block boundaries per unit
   for (uint32_t i = tid; i < p.q_nnz; i += blockDim.x) {
     const uint32_t t = __ldg(p.q_tok + i);
@@ -148,6 +152,10 @@ __global__ void __launch_bounds__(T) sparse_bounds_kernel(const BoundsParams p) 
       }
     }
   }
+  if (p.trace && tid == 0 && blockIdx.x < 148) {
+    unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.trace[(300 + blockIdx.x) * 8 + 1] = t_;
+  }
 }
 
 struct SparseParams {
@@ -181,14 +189,14 @@ struct SparseParams {
 constexpr uint32_t kSpR = 4;                       // 64-doc index blocks per warp block
 constexpr uint32_t kSpWDocs = kSpBlock * kSpR;     // docs owned by one warp at a time (256)
 
-// The leg is two kernels.  ACCUMULATE (sparse_accum_kernel<WARPS>): warps claim 256-doc blocks from a
-// global counter, build the block's scores in shared memory and write them — 256 f32 + a 256-bit
-// "touched" mask — to a per-index scratch.  SELECT (sparse_select_kernel): streams that scratch through
-// the top-k accumulator, last-CTA merge.  The split exists for the hybrid call: the accumulate kernel has
-// a SLIM form — 96-thread CTAs, ~24 KB of shared memory, 64 registers — that fits on an SM BESIDE the
-// dense scan's CTA (the scan's 9 warps x 168 registers fill one of the four register-file partitions;
-// the hardware places a 3-warp CTA on the other three: tools/probe_coresidency.py), so the instruction-
-// bound sparse accumulation runs under the bandwidth-bound dense scan instead of after it.
+// The leg is two kernels.  ACCUMULATE (sparse_accum_kernel): warps claim 256-doc blocks from a global
+// counter, build the block's scores in shared memory and write them — 256 f32 + a 256-bit "touched"
+// mask — to a per-index scratch.  SELECT (sparse_select_kernel): streams that scratch through the top-k
+// accumulator, last-CTA merge.  Split, the two cost 148 us at k = 500 where the single kernel cost 162 us
+// (the accumulate loop runs without the accumulator's registers and shared memory, 2 CTAs per SM).
+// (A 3-warp "slim" accumulate kernel that runs on the SMs BESIDE the hybrid call's dense scan was built
+// and measured — DESIGN.md §4.3c: it fits, but its 444 warps do a third of the work in the scan's 440 us
+// and slow the scan by 18 us; dropped.)
 struct SpAccSmemBase {
   uint64_t base[kSpMaxQ];                //  8 KB  start of query token i's posting list
   const uint32_t* brow[kSpMaxQ];         //  8 KB  its block-boundary row (static index or this query's bounds)
@@ -214,7 +222,7 @@ struct SpAccSmem : SpAccSmemBase {
 // 62 % of the slots for 17 % of the DRAM bandwidth — profiles/r02_sparse_search_*.)
 constexpr int kSpBatch = 8;
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 3 ? 8 : 2) sparse_accum_kernel(const SparseParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 2) sparse_accum_kernel(const SparseParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpAccSmem<WARPS>& s = *reinterpret_cast<SpAccSmem<WARPS>*>(smem_raw);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 3 ? 8 : 2) sparse_accum_k
   float* acc = s.acc[warp];
   uint8_t* touched = s.touched[warp];
   for (;;) {
-    // warps claim blocks one at a time: the slim and the regular form, any grid, finish together
+    // warps claim blocks one at a time: no warp waits for the slowest block of a static slice
     uint32_t wb = 0;
     if (lane == 0) wb = atomicAdd(p.claim, 1u);
     wb = __shfl_sync(0xffffffffu, wb, 0);
@@ -394,9 +402,9 @@ size_t sparse_block_scratch_bytes(uint64_t n_docs) {
   return (size_t)n_wblocks * kSpWDocs * sizeof(float) + (size_t)n_wblocks * (kSpWDocs / 32) * sizeof(uint32_t);
 }
 
-// slim: the accumulate kernel is launched in its co-resident form (see above) — the caller has a
-// dense scan in flight on another stream of the same device.
-cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st, bool slim) {
+// The leg's three launches, separately, so that the hybrid call can place them around its dense scan
+// (index.cu, search_hybrid_impl).  stage: kSparseBounds | kSparseAccum | kSparseSelect.
+cudaError_t launch_sparse_stage(const SparseArgs& a, uint32_t stage, cudaStream_t st) {
   if (a.n_docs == 0 || a.k == 0 || a.k > kMaxK || a.q_nnz == 0 || a.q_nnz > kSpMaxQ ||
       a.n_docs > 0xFFFFFFFFull || !a.d_bounds || !a.d_block_scratch || !a.d_claim)
     return cudaErrorInvalidValue;
@@ -407,10 +415,13 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st, bool slim
   cudaError_t e = cudaSuccess;
   // the static block index only applies while the corpus still has the block count it was built for
   const bool use_index = a.sp.d_slot_of && a.sp.d_block_index && a.sp.index_stride == n_blocks + 1;
-  BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds,
-                  use_index ? a.sp.d_slot_of : nullptr};
-  if (slim) sparse_bounds_kernel<96><<<sms * 2, 96, 0, st>>>(bp);
-  else sparse_bounds_kernel<256><<<sms * 6, 256, 0, st>>>(bp);
+  if (stage & kSparseBounds) {
+    BoundsParams bp{a.sp.d_tptr, a.sp.d_doc, a.sp.vocab, a.d_q_tok, a.q_nnz, n_blocks, a.d_bounds,
+                    use_index ? a.sp.d_slot_of : nullptr};
+    bp.trace = (unsigned long long*)a.d_trace;
+    sparse_bounds_kernel<256><<<sms * 6, 256, 0, st>>>(bp);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   SparseParams p;
   p.tptr = a.sp.d_tptr; p.post = (const uint2*)a.sp.d_post; p.vocab = a.sp.vocab;
   p.n_docs = a.n_docs; p.q_tok = a.d_q_tok; p.q_w = a.d_q_w; p.q_nnz = a.q_nnz;
@@ -425,32 +436,32 @@ cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st, bool slim
   p.claim = a.d_claim;
   p.blk_scores = (float*)a.d_block_scratch;
   p.blk_mask = (uint32_t*)((uint8_t*)a.d_block_scratch + (size_t)n_wblocks * kSpWDocs * sizeof(float));
-  // ---- accumulate ----
-  if (slim) {
-    e = cudaFuncSetAttribute(sparse_accum_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(SpAccSmem<3>));
-    if (e != cudaSuccess) return e;
-    const uint32_t want = (n_wblocks + 2) / 3;
-    const int grid = (int)(want < (uint32_t)(2 * sms) ? want : (uint32_t)(2 * sms));
-    sparse_accum_kernel<3><<<grid, 96, sizeof(SpAccSmem<3>), st>>>(p);
-  } else {
+  if (stage & kSparseAccum) {
     e = cudaFuncSetAttribute(sparse_accum_kernel<kSpWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(SpAccSmem<kSpWarps>));
     if (e != cudaSuccess) return e;
     const uint32_t want = (n_wblocks + kSpWarps - 1) / kSpWarps;
     const int grid = (int)(want < (uint32_t)(2 * sms) ? want : (uint32_t)(2 * sms));
+    if (p.trace) p.trace += 150 * 8;   // development aid: the select kernel's stamps use rows 0..
     sparse_accum_kernel<kSpWarps><<<grid, kSpThreads, sizeof(SpAccSmem<kSpWarps>), st>>>(p);
+    p.trace = (unsigned long long*)a.d_trace;
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  // ---- select ----
-  const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
-  int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
-  if (grid > (int)kMaxGrid) grid = kMaxGrid;
-  e = cudaFuncSetAttribute(sparse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)sizeof(SpSmem));
-  if (e != cudaSuccess) return e;
-  sparse_select_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
-  g_kernel_launches.fetch_add(3, std::memory_order_relaxed);
+  if (stage & kSparseSelect) {
+    const uint32_t n_steps = (n_wblocks + kSpWarps - 1) / kSpWarps;
+    int grid = (int)(n_steps < (uint32_t)(2 * sms) ? n_steps : (uint32_t)(2 * sms));
+    if (grid > (int)kMaxGrid) grid = kMaxGrid;
+    e = cudaFuncSetAttribute(sparse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(SpSmem));
+    if (e != cudaSuccess) return e;
+    sparse_select_kernel<<<grid, kSpThreads, sizeof(SpSmem), st>>>(p);
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_search(const SparseArgs& a, cudaStream_t st) {
+  return launch_sparse_stage(a, kSparseBounds | kSparseAccum | kSparseSelect, st);
 }
 
 void free_sparse(SparseDev& sp) {

@@ -14,4 +14,6 @@ for op, cases in ((1, [(64, 64), (128, 128), (173, 100), (256, 256), (500, 500),
     for n, k in cases:
         ns, cnt = C.c_uint64(0), C.c_uint32(0)
         rc = f(0, op, n, k, 20, C.byref(ns), C.byref(cnt))
-        print(f"{names[op]:12s} n={n:5d} k={k:5d}: {ns.value / 1e3:7.2f} us  (cnt after {cnt.value}) rc={rc}")
+        cold = C.c_uint64(0)
+        f(0, op | 16, n, k, 2, C.byref(cold), C.byref(cnt))   # fresh kernel, first repetition: cold instruction cache
+        print(f"{names[op]:12s} n={n:5d} k={k:5d}: {ns.value / 1e3:7.2f} us warm, {cold.value / 1e3:7.2f} us cold  (cnt after {cnt.value}) rc={rc}")

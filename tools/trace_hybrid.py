@@ -27,13 +27,15 @@ for i in range(8):
     tr = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
     tr = tr.reshape(1024, 8).astype(np.int64)
-    d, sp = tr[:148], tr[512:512 + 296]
+    d = tr[:148]
     t0 = d[:, 0].min()
-    acc = sp[sp[:, 6] > t0]                                # accumulate CTAs of THIS query (slots 6, 7)
-    sel = sp[sp[:, 3] > t0]                                # select CTAs (slots 0..5)
     us = lambda x: (x - t0) / 1e3
-    print(f"query {i}: dense CTAs start {us(d[:,0].min()):.1f}..{us(d[:,0].max()):.1f}, stream end {us(d[:,1].max()):.1f}, "
-          f"ticket {us(d[:,3].max()):.1f}, kernel end {us(d[:,4].max()):.1f} | sparse accumulate ({acc.shape[0]} CTAs) start "
-          f"{us(acc[:,6].min()):.1f}..{us(acc[:,6].max()):.1f}, end {us(acc[:,7].min()):.1f}..{us(acc[:,7].max()):.1f} | select "
-          f"({sel.shape[0]} CTAs) start {us(sel[:,0].min()):.1f}..{us(sel[:,0].max()):.1f}, loop end {us(sel[:,3].max()):.1f}, "
-          f"merge end {us(sel[:,5].max()):.1f} us")
+    live = lambda rows, slot: rows[rows[:, slot] > t0 - 2000000]
+    bd = live(tr[812:960], 0)                               # bounds pass (first 148 CTAs), before the scan
+    reg = live(tr[662:662 + 296], 6)                        # accumulate CTAs (slots 6, 7)
+    sel = live(tr[512:512 + 296], 3)                        # select CTAs (slots 0..5)
+    btxt = f"{us(bd[:,0].min()):.1f}..{us(bd[:,1].max()):.1f}" if bd.shape[0] else "n/a"
+    print(f"query {i}: bounds {btxt} | dense CTAs start {us(d[:,0].min()):.1f}..{us(d[:,0].max()):.1f}, "
+          f"stream end {us(d[:,1].max()):.1f}, ticket {us(d[:,3].max()):.1f}, kernel end {us(d[:,4].max()):.1f}")
+    print(f"   accumulate ({reg.shape[0]} CTAs): start {us(reg[:,6].min()):.1f}..{us(reg[:,6].max()):.1f}, end {us(reg[:,7].min()):.1f}..{us(reg[:,7].max()):.1f} | "
+          f"select ({sel.shape[0]} CTAs) start {us(sel[:,0].min()):.1f}..{us(sel[:,0].max()):.1f}, loop end {us(sel[:,3].max()):.1f}, merge end {us(sel[:,5].max()):.1f} us")

@@ -23,6 +23,7 @@ for k in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1,
     trall = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, trall.ctypes.data_as(C.c_void_p), 1024 * 8)
     ms = trall.reshape(1024, 8)[1023].astype(np.int64)       # extra stamps of the merge (last CTA)
+    cs = trall.reshape(1024, 8)[1022].astype(np.int64)       # final sort: wall clock and SM cycles
     tr = trall.reshape(1024, 8)[:148].astype(np.int64)
     t0 = tr[:, 0].min()
     rel = (tr - t0) / 1e3
@@ -34,4 +35,6 @@ for k in ([int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else (1,
     print(f"  ticket         : max {rel[:,3].max():.1f} us")
     print(f"  merge detail   : start {(ms[0]-t0)/1e3:.1f}, col bounds done {(ms[1]-t0)/1e3:.1f}, rounds done {(ms[2]-t0)/1e3:.1f}, "
           f"select1 done {(ms[4]-t0)/1e3:.1f}, select2 done {(ms[5]-t0)/1e3:.1f}; cnt at finish {ms[7]}, cnt before final sort {ms[6]}, thr score word {ms[3] >> 32:#x}")
+    if cs[1] > cs[0] > 0:
+        print(f"  final sort     : {(cs[1]-cs[0])/1e3:.2f} us, {cs[2]} SM cycles ({cs[2]/(cs[1]-cs[0]):.2f} GHz)")
     print(f"  merge (CTA {last}) : {rel[last,3]:.1f} -> {rel[last,4]:.1f} us; loads+push done {rel[last,5]:.1f}, compact done {rel[last,6]:.1f}, cnt before compact {tr[last,7]}")

@@ -35,9 +35,9 @@ for k in (20, 500):
         ix.search_sparse_rows(t, qw, k)
     tr = np.zeros(1024 * 8, np.uint64)
     lib.cqs_b200_debug_trace(ix._h, tr.ctypes.data_as(C.c_void_p), 1024 * 8)
-    tr = tr.reshape(1024, 8)[512:512 + 296].astype(np.int64)
-    acc = tr[tr[:, 6] > 0]
-    sel = tr[tr[:, 3] > 0]
+    tr = tr.reshape(1024, 8).astype(np.int64)
+    acc = tr[662:662 + 296]; acc = acc[acc[:, 6] > 0]     # regular accumulate CTAs (rows 150.. of the sparse trace)
+    sel = tr[512:512 + 296]; sel = sel[sel[:, 3] > 0]
     t0 = acc[:, 6].min(); us = lambda x: (x - t0) / 1e3
     last = int(np.argmax(sel[:, 5]))
     print(f"k={k}: all kernels {ix.last_kernel_ms()*1e3:.0f} us | accumulate ({acc.shape[0]} CTAs): start 0..{us(acc[:,6].max()):.1f}, "
