@@ -19,6 +19,13 @@ namespace cqs {
 
 typedef unsigned long long ckey_t;
 
+// "this generic pointer is in the shared window" hint (see TopK::assume_shared)
+#ifdef CQS_NO_ASSUME_SHARED   // development aid: build without the hints
+#define CQS_ASSUME_SHARED(p) ((void)0)
+#else
+#define CQS_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#endif
+
 __host__ __device__ __forceinline__ uint32_t ordered_u32(uint32_t bits) {
   return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
 }
@@ -200,6 +207,7 @@ __device__ __forceinline__ void chunk_rank_sort(const Group& g, ckey_t* buf, cke
       const uint32_t i = c * C + r * 32 + lane;
       reg[r] = i < n ? buf[i] : 0;
     }
+    __syncwarp();   // the network's shuffles want a converged warp (see the note on chunk_rank_sort)
     chunk_network<R>(reg, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) scratch[c * C + r * 32 + lane] = reg[r];
@@ -274,9 +282,9 @@ struct TopK {
   // took 15 us inside the scan kernel and 5.5 us in a test kernel that could see the __shared__
   // declaration).  Tells the compiler which window the pointers are in.
   __device__ __forceinline__ void assume_shared() const {
-    __builtin_assume(__isShared(buf));
-    __builtin_assume(__isShared(cnt));
-    __builtin_assume(__isShared(thr));
+    CQS_ASSUME_SHARED(buf);
+    CQS_ASSUME_SHARED(cnt);
+    CQS_ASSUME_SHARED(thr);
   }
   __device__ __forceinline__ void push(ckey_t key) {
     uint32_t slot = atomicAdd(cnt, 1u);
@@ -289,6 +297,9 @@ struct TopK {
     uint32_t n = min(*cnt, cap);
     const uint32_t per_r = g.nthr;   // keys per register of chunk_rank_sort when every warp takes one chunk
     ckey_t* scratch = buf + (cap >> 1);   // the sorted chunks (n <= cap / 2 on that path)
+#ifdef CQS_FORCE_NETWORK   // development aid: always the bitonic network
+    force_network = true;
+#endif
     if (force_network || n > (cap >> 1)) {
       uint32_t P = max(next_pow2(n), kSortChunk);  // cap >= kSortChunk
       for (uint32_t i = n + g.tid; i < P; i += g.nthr) buf[i] = 0;
@@ -358,8 +369,8 @@ struct TopK {
       g.sync();
       return;
     }
-    __builtin_assume(__isShared(hist));   // (non-null past the early return)
-    if (vm_out) __builtin_assume(__isShared(vm_out));
+    CQS_ASSUME_SHARED(hist);   // (non-null past the early return)
+    if (vm_out) CQS_ASSUME_SHARED(vm_out);
     const uint32_t lane = g.tid & 31, warp = g.tid >> 5, nwarps = g.nthr >> 5;
     ckey_t r[ITEMS];
     ckey_t lo = ~0ull, hi = 0;
@@ -590,7 +601,7 @@ __device__ __noinline__ void merge_partials_and_emit(TopK tk, uint32_t* s_pos, u
                                                         ckey_t thr0 = 0) {
   // thr0: a lower bound of the global k-th best key the caller already knows (0 = none)
   tk.assume_shared();
-  __builtin_assume(__isShared(s_pos));
+  CQS_ASSUME_SHARED(s_pos);
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
   // development aid: extra stamps of the merge go to the last row of the trace buffer
   unsigned long long* mstamps = trace ? trace - (size_t)blockIdx.x * 8 + (size_t)(kPartialStride - 1) * 8 : nullptr;

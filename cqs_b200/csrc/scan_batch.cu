@@ -25,7 +25,10 @@
 // separated from the pool's cut-off by the rigorous rounding bound is flagged
 // and re-run through the exact single-query kernel by the caller.  Results are
 // identical to nq calls of cqs_b200_search.
+#define CQS_FORCE_NETWORK 1   // the batch kernels keep the bitonic network: see DESIGN.md §4.6 (chunk sort, update_thr_kernel)
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_thr_kernel(ckey_t* cand, u
                                                                  const uint8_t* subcnt,
                                                                  uint32_t sub_grid, uint32_t nq_pad) {
   __shared__ __align__(16) ckey_t s_buf[kUpdCap];
-  __shared__ uint32_t s_hist[kSelBuckets + 96];
+  __shared__ __align__(8) uint32_t s_hist[kSelBuckets + 96];
   __shared__ uint32_t s_cnt;
   __shared__ ckey_t s_thr;
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
@@ -684,6 +687,14 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   if (!make_tmap(&tmQ, q16, nq_pad, ld, kBM) || !make_tmap(&tmR, a.d_rows, a.n_rows, ld, kBN))
     return cudaErrorNotSupported;
 
+  // CQS_B200_DEBUG_SYNC (development aid): synchronise after every launch and name the one that failed
+  static const bool dbg = getenv("CQS_B200_DEBUG_SYNC") != nullptr;
+  auto check = [&](const char* what) {
+    if (!dbg) return cudaSuccess;
+    const cudaError_t ee = cudaStreamSynchronize(st);
+    if (ee != cudaSuccess) fprintf(stderr, "[cqs_b200] %s failed: %s\n", what, cudaGetErrorString(ee));
+    return ee;
+  };
   const uint64_t r0 = a.n_rows < kBatchDenseRows ? a.n_rows : kBatchDenseRows;
   prep_queries_kernel<<<nq_pad, 128, 0, st>>>(a.d_queries, a.nq, nq_pad, ld, q16, qnorm, dqnorm, thr, cnt,
                                               overflow, (uint32_t)r0);
@@ -714,8 +725,10 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
     const uint64_t items = ((end - begin + kBN - 1) / kBN) * p.n_qt;
     const int grid = (int)(items < (uint64_t)num_sms ? items : (uint64_t)num_sms);
     scan_batch_kernel<<<grid, kBatchThreads, kBatchSmem, st>>>(tmQ, tmR, p);
+    if ((e = check("scan_batch_kernel")) != cudaSuccess) return e;
     update_thr_kernel<<<nq_pad, kUpdThreads, 0, st>>>(cand, cnt, thr, kBatchCap, kprime, sub, subcnt,
                                                       p.dense ? 0u : (uint32_t)grid, nq_pad);
+    if ((e = check("update_thr_kernel")) != cudaSuccess) return e;
     launches += 2;
     begin = end;
     end = (end * 9 < a.n_rows) ? end * 9 : a.n_rows;
@@ -723,10 +736,12 @@ cudaError_t launch_scan_batch(const BatchArgs& a, int num_sms, cudaStream_t st) 
   }
   rescore_kernel<<<a.nq, 256, 0, st>>>((const uint8_t*)a.d_exact_rows, ld, a.exact_layout.mode,
                                        a.exact_layout.nv, a.d_queries, cand, cnt, kBatchCap, kprime);
+  if ((e = check("rescore_kernel")) != cudaSuccess) return e;
   final_select_kernel<<<a.nq, kUpdThreads, 0, st>>>(cand, cnt, thr, overflow, qnorm, dqnorm,
                                                     a.max_row_norm, a.max_row_delta, kBatchCap, kprime, a.k,
                                                     a.row_base, a.d_out_scores, a.d_out_rows,
                                                     a.d_out_n, a.d_flags);
+  if ((e = check("final_select_kernel")) != cudaSuccess) return e;
   launches += 2;
   g_kernel_launches.fetch_add(launches, std::memory_order_relaxed);
   return cudaGetLastError();

@@ -136,7 +136,7 @@ struct ScanCfg {
 static __device__ __noinline__ void refresh_global_thr(TopK tk, ckey_t* colv, const ckey_t* col,
                                                        uint32_t G, uint32_t j) {
   tk.assume_shared();
-  __builtin_assume(__isShared(colv));
+  CQS_ASSUME_SHARED(colv);
   const uint32_t tid = tk.g.tid, T = tk.g.nthr;
   for (uint32_t l = tid; l < G; l += T) colv[l] = __ldcg(col + l);
   tk.g.sync();
@@ -232,8 +232,8 @@ static __device__ __noinline__ void rescore_local(TopK tk, const ScanParams& p) 
 static __device__ __noinline__ uint32_t prove_shadow(TopK tk, const ScanParams& p, const ckey_t* excl, uint32_t G,
                                                      float* s_red, ckey_t* s_cut) {
   tk.assume_shared();
-  __builtin_assume(__isShared(s_red));
-  __builtin_assume(__isShared(s_cut));
+  CQS_ASSUME_SHARED(s_red);
+  CQS_ASSUME_SHARED(s_cut);
   const uint32_t tid = tk.g.tid, T = tk.g.nthr, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   if (tid == 0) *s_cut = 0;
   const uint32_t ld = p.exact_nv * 128;
