@@ -844,7 +844,7 @@ def hybrid_record(c, ix, rows_host, sp, mode, steps, warmup, name):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("hybrid:1000000x768:f32:pool500"), "peak_source": peak_src,
-                     "kernel": "scan_topk_kernel (k=500) + sparse_bounds_kernel + sparse_search_kernel + fuse_pools_kernel",
+                     "kernel": "scan_topk_kernel (k=500) + sparse_bounds_kernel + sparse_accum_kernel + sparse_select_kernel + fuse_pools_kernel",
                      "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
         "parity": {"parity_queries": P, "dense_pool_ids_identical_or_near_tie": f"{dense_ok}/{P}",
                    "dense_max_rel_score_err": worst, "sparse_pool_bit_exact": f"{sparse_ok}/{P}",

@@ -1,7 +1,8 @@
 // sparse_fuse.cu — kernel 4 of the north star: SPLADE sparse·query scoring with
 // a fused top-k pool, the dense+sparse alpha fusion, and centroid routing.
 //
-//   sparse_search_kernel   <- SpladeIndex::search_with_filter
+//   sparse_bounds_kernel, sparse_accum_kernel, sparse_select_kernel
+//                          <- SpladeIndex::search_with_filter
 //                             (src/splade/index.rs:223-291)
 //   fuse_pools_kernel      <- the fusion block of search_hybrid_inner
 //                             (src/search/query.rs:914-1005)
@@ -18,12 +19,12 @@
 // for the bounds pass) sorted by doc ascending — the order
 // SpladeIndex::build produces (index.rs:197-203).  A query touches only
 // sum_t |postings(t)| * 8 bytes, versus the whole 8*nnz bytes of a doc-major
-// scan.  Docs are processed in blocks of kSparseDocsPerBlock (64) owned by one warp (accumulators in
-// shared memory); a first pass streams the doc ids of the touched lists once to
-// find where every block starts in every query token's list, the second applies
+// scan.  Docs are processed in blocks of 256 (four 64-doc index blocks) owned by one warp, accumulators
+// in shared memory; a bounds pass (once per index for the long lists, per query for the short ones)
+// finds where every 64-doc block starts in every token's list, the accumulate kernel applies
 // the tokens IN QUERY ORDER (the reference's accumulation order,
-// index.rs:251-259).  Candidates go through the same shared-memory top-k
-// accumulator as the dense scan; the last CTA merges.
+// index.rs:251-259) and writes the blocks' scores to a scratch; the select kernel streams them
+// through the same shared-memory top-k accumulator as the dense scan; its last CTA merges.
 #include "common.cuh"
 #include "internal.h"
 
