@@ -160,8 +160,11 @@ __device__ __forceinline__ void block_sort_desc(const Group& g, ckey_t* buf, uin
 // is its index in its own chunk plus, for every other chunk, the number of keys there that beat it — a
 // branch-free binary search (log2 C + 1 probes, four chunks' searches interleaved).  Keys are unique;
 // padding keys are 0 and land at positions >= n, where they are dropped.  Two barriers, no quadratic loop:
-// 500 keys cost ~2 us on 8 warps where the rank sort this replaces took 11 us and the full bitonic
-// network 18 us (measured inside the scan kernel, tools/trace_scan.py).
+// ~860 keys (a k = 500 merge) cost 5.6 us on 8 warps inside the scan kernel where selection + rank sort took
+// 15 us and selection + the full bitonic network 22 us (tools/trace_scan.py); 500 keys 2.5 us in isolation.
+// NOT used by the batch kernels: scan_batch.cu defines CQS_FORCE_NETWORK because this sort, executed inside
+// update_thr_kernel, faulted about once per 100-500 batch calls — cause not found; it is
+// clean in isolation (tools/stress_sort.py) and in the scan and sparse kernels (tools/stress_single.py).
 template <int R>
 __device__ __forceinline__ void chunk_network(ckey_t (&reg)[R], uint32_t lane) {
   constexpr uint32_t C = 32 * R;
@@ -207,7 +210,7 @@ __device__ __forceinline__ void chunk_rank_sort(const Group& g, ckey_t* buf, cke
       const uint32_t i = c * C + r * 32 + lane;
       reg[r] = i < n ? buf[i] : 0;
     }
-    __syncwarp();   // the network's shuffles want a converged warp (see the note on chunk_rank_sort)
+    __syncwarp();   // the network's shuffles run on the converged-warp fast path
     chunk_network<R>(reg, lane);
 #pragma unroll
     for (int r = 0; r < R; ++r) scratch[c * C + r * 32 + lane] = reg[r];
@@ -549,7 +552,7 @@ __device__ __noinline__ void topk_finish(TopK tk, uint32_t k, unsigned long long
   tk.assume_shared();
   tk.g.sync();
   if (stamps && tk.g.tid == 0) stamps[7] = *tk.cnt;
-  // a selection (2.6 us) pays off when it moves the sort to a smaller network / into rank-sort range
+  // a selection (3 us) pays off only above the range the chunk sort handles directly
   if (min(*tk.cnt, tk.cap) > kDirectSortMax && *tk.cnt > k + 64) {
     const ckey_t before = *tk.thr;
     tk.template select<ITEMS>(k);

@@ -198,7 +198,7 @@ static __device__ __noinline__ void rescore_local(TopK tk, const ScanParams& p) 
       for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
     __syncwarp();
     // a non-finite exact score drops the row (candidate.rs:275): its key becomes (0, ~row) — below every
-    // valid key (whose high word is >= 0x00800000) yet unique, as the rank sort requires
+    // valid key (whose high word is >= 0x00800000) yet unique, as the exact sort requires
     if (lane < 4 && j0 + lane < n) {
       float mine = sc[0];
 #pragma unroll
