@@ -7,20 +7,21 @@ import numpy as np, torch, cqs_b200
 import bench as B
 n = 1_000_000
 per = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+only_sparse = len(sys.argv) > 2 and sys.argv[2] == "sparse"   # skip the dense k sweep, f32 storage only
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(3)
-q = B.make_queries(per, 77)
+q = B.make_queries(min(per, 4096), 77)
 t0 = time.time()
-for storage in ("f32", "bf16+f32"):
+for storage in (("f32",) if only_sparse else ("f32", "bf16+f32")):
     ix = cqs_b200.B200Index(768, storage=storage)
     ix.reserve(n)
     for b in range(n // B.BLK):
         x = B.gen_block(torch, dev, b, "uniform")
         ix.append_device(x.data_ptr(), x.shape[0])
     ix.finalize()
-    for k in (20, 100, 500, 1024):
+    for k in (() if only_sparse else (20, 100, 500, 1024)):
         for i in range(per):
-            ix.search_rows(q[i], k)
+            ix.search_rows(q[i % q.shape[0]], k)
         print(f"{storage} k={k}: {per} searches ok ({time.time() - t0:.0f}s)", flush=True)
     if storage == "f32":
         d_indptr, d_tok, d_w, cdf_h = B.gen_sparse_device(torch, dev, n)
@@ -31,7 +32,7 @@ for storage in ("f32", "bf16+f32"):
                 ix.search_sparse_rows(sq[i % 256][0], sq[i % 256][1], k)
             print(f"sparse k={k}: {per // 2} searches ok ({time.time() - t0:.0f}s)", flush=True)
             for i in range(per // 2):
-                ix.search_hybrid_rows(q[i], sq[i % 256][0], sq[i % 256][1], 0.8, k)
+                ix.search_hybrid_rows(q[i % q.shape[0]], sq[i % 256][0], sq[i % 256][1], 0.8, k)
             print(f"hybrid pool={k}: {per // 2} searches ok ({time.time() - t0:.0f}s)", flush=True)
     del ix
 print("done")
